@@ -1,0 +1,120 @@
+"""ctypes binding of the C ABI declared in include/cugs_b200.h.
+
+The library is hand-written CUDA for sm_100a. There is NO CPU fallback: if the shared object is
+missing or the device is not a B200-class GPU, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libcugs_b200.so"
+
+
+class CugsView(C.Structure):
+    """struct cugs_view (include/cugs_b200.h) — CameraInfo + RenderSettings of the reference."""
+
+    _fields_ = [
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("fx", C.c_float),
+        ("fy", C.c_float),
+        ("cx", C.c_float),
+        ("cy", C.c_float),
+        ("view", C.c_float * 16),
+        ("cam_center", C.c_float * 3),
+        ("bg", C.c_float * 3),
+        ("active_sh_degree", C.c_int32),
+        ("num_coeffs", C.c_int32),
+        ("scale_modifier", C.c_float),
+    ]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_SZ = C.c_size_t
+_INT = C.c_int
+_F = C.c_float
+_VP = C.POINTER(CugsView)
+
+# name -> (restype, argtypes); must list EVERY symbol include/cugs_b200.h declares
+SIGNATURES = {
+    "cugs_b200_create": (_INT, [_INT, C.POINTER(_P)]),
+    "cugs_b200_destroy": (None, [_P]),
+    "cugs_b200_last_error": (C.c_char_p, [_P]),
+    "cugs_b200_abi_version": (_INT, []),
+    "cugs_b200_sm_count": (_INT, [_P]),
+    "cugs_b200_preprocess_fwd": (_INT, [_P, _P, _I64, _VP] + [_P] * 14),
+    "cugs_b200_sh_forward": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P]),
+    "cugs_b200_sh_backward": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P, _P]),
+    "cugs_b200_scan_temp_bytes": (_SZ, [_I64]),
+    "cugs_b200_scan": (_INT, [_P, _P, _I64, _P, _P, _P, C.POINTER(_I64), _P, _SZ]),
+    "cugs_b200_duplicate_with_keys": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "cugs_b200_sort_temp_bytes": (_SZ, [_I64]),
+    "cugs_b200_sort_pairs": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P, _P, _P, _SZ]),
+    "cugs_b200_tile_ranges": (_INT, [_P, _P, _I64, _P, _INT, _P]),
+    "cugs_b200_blend_fwd": (_INT, [_P, _P, _VP] + [_P] * 10),
+    "cugs_b200_blend_bwd": (_INT, [_P, _P, _I64, _VP] + [_P] * 15),
+    "cugs_b200_preprocess_bwd": (_INT, [_P, _P, _I64, _VP] + [_P] * 19),
+    "cugs_b200_render_workspace_bytes": (_SZ, [_I64, _I64]),
+    "cugs_b200_render_plan": (_INT, [_P, _P, _I64, _VP] + [_P] * 11 + [_P, _SZ, C.POINTER(_I64)]),
+    "cugs_b200_render_finish": (_INT, [_P, _P, _I64, _I64, _VP] + [_P] * 11 + [_P, _SZ]),
+    "cugs_b200_render_backward": (_INT, [_P, _P, _I64, _VP] + [_P] * 24 + [_P, _SZ]),
+    "cugs_b200_loss_workspace_bytes": (_SZ, [_INT, _INT]),
+    "cugs_b200_loss_l1_ssim": (_INT, [_P, _P, _INT, _INT, _F, _P, _P, _P, _P, _P, _SZ]),
+    "cugs_b200_adam_step": (_INT, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
+                                    C.POINTER(_I64), C.POINTER(_F), _F, _F, _F, _F, _F, _F]),
+    "cugs_b200_accumulate_stats": (_INT, [_P, _P, _I64, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree library and bind every declared symbol (no GPU needed for this)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("CUGS_B200_LIB", LIB_PATH))
+    if not path.exists():
+        raise RuntimeError(
+            f"{path} not found: the sm_100a CUDA library has not been built (run ./build.sh or "
+            "__graft_entry__.build()). There is no CPU fallback.")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class CugsError(RuntimeError):
+    """Raised for a non-zero status of the C ABI (mirrors the reference's c10::Error /
+    std::runtime_error("CUDA error ...") behaviour, utils/cuda_utils.cuh:12-20)."""
+
+
+_handles: dict[int, int] = {}
+
+
+def handle(device_index: int) -> int:
+    """One handle per device (created lazily)."""
+    h = _handles.get(device_index)
+    if h is None:
+        lib = load_library()
+        out = _P()
+        st = lib.cugs_b200_create(int(device_index), C.byref(out))
+        if st != 0:
+            raise CugsError(f"cugs_b200_create(device={device_index}) failed with status {st} "
+                            "(-5 = not an sm_100 device; there is no fallback path)")
+        h = out.value
+        _handles[device_index] = h
+    return h
+
+
+def check(h: int, status: int, what: str) -> None:
+    if status != 0:
+        msg = load_library().cugs_b200_last_error(h)
+        raise CugsError(f"{what} failed (status {status}): {msg.decode() if msg else ''}")

@@ -1,0 +1,256 @@
+// api.cu — handle management and the fused render entry points of the C ABI.
+//
+// cugs_b200_render_plan / _finish / _backward compose the stage kernels exactly as the reference
+// host code does (rasterizer/rasterizer.cpp:22-113 render, :115-186 render_backward), minus its
+// ~45 ATen allocations and memsets: every scratch buffer lives in one caller-provided workspace.
+#include "common.cuh"
+
+#include <cstring>
+
+using namespace cugs;
+
+// internal launchers implemented in the other translation units
+int cugs_scan_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, const int32_t* tiles_touched,
+                     int32_t* offsets, int64_t* total_dev, bool to_pinned, void* scan_temp,
+                     const unsigned* aux_pair);
+int cugs_blend_bwd_accumulate(cugs_handle_t* h, cudaStream_t s, int64_t n, const cugs_view_t* v,
+                              const int32_t* tile_ranges, const int32_t* gaussian_idx,
+                              const float* means_2d, const float* cov_2d_inv, const float* rgb,
+                              const float* opacities_act, const float* packed, const float* dL_dcolor,
+                              const float* final_T, const int32_t* n_contrib, float* grad_acc);
+int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, const cugs_view_t* v,
+                               const float* positions, const float* rotations, const float* scales,
+                               const float* opacities, const float* sh_coeffs, const int32_t* radii,
+                               const float* rgb, const float* dL_dmeans_2d, const float* dL_dcov_2d_inv,
+                               const float* dL_drgb, const float* dL_dopacity_act, float* dL_dpositions,
+                               float* dL_drotations, float* dL_dscales, float* dL_dopacities,
+                               float* dL_dsh_coeffs, float* grad_accum, float* grad_count,
+                               float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out);
+extern "C" int cugs_b200_sort_num_passes(int depth_bits, int tile_bits);
+extern "C" int cugs_b200_sort_pairs_pingpong(cugs_handle_t* h, void* stream, int64_t p, int depth_bits,
+                                             int tile_bits, uint64_t* keys_a, int32_t* vals_a,
+                                             uint64_t* keys_b, int32_t* vals_b, void* temp,
+                                             size_t temp_bytes, int* result_in_b);
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+extern "C" int cugs_b200_abi_version(void) { return CUGS_B200_ABI_VERSION; }
+
+extern "C" int cugs_b200_create(int device, cugs_handle_t** out) {
+    if (!out) return CUGS_ERR_INVALID_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return (int)e;
+    if (prop.major != 10) return CUGS_ERR_NOT_BLACKWELL;  // built for sm_100a only; no fallback
+    cugs_handle* h = new cugs_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->err[0] = 0;
+    h->pinned = nullptr;
+    e = cudaHostAlloc(reinterpret_cast<void**>(&h->pinned), 64, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) { delete h; return (int)e; }
+    std::memset(h->pinned, 0, 64);
+    *out = h;
+    return CUGS_OK;
+}
+
+extern "C" void cugs_b200_destroy(cugs_handle_t* h) {
+    if (!h) return;
+    if (h->pinned) cudaFreeHost(h->pinned);
+    delete h;
+}
+
+extern "C" const char* cugs_b200_last_error(const cugs_handle_t* h) { return h ? h->err : "null handle"; }
+extern "C" int cugs_b200_sm_count(const cugs_handle_t* h) { return h ? h->sm_count : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout of one frame
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct FrameWorkspace {
+    float* packed;          // [N,12]
+    int32_t* tiles_touched; // [N]
+    int32_t* offsets;       // [N]
+    void* scan_temp;
+    unsigned* depth_minmax; // 2 words (+ int64 total)
+    int64_t* total_dev;
+    uint64_t* keys_x;       // [Pcap]  (sorted keys end up here)
+    uint64_t* keys_y;       // [Pcap]
+    int32_t* vals_y;        // [Pcap]
+    void* sort_temp;
+    size_t sort_temp_bytes;
+    float* grad_acc;        // [N,12]
+    size_t total_bytes;
+};
+
+FrameWorkspace carve(void* base, int64_t n, int64_t pcap) {
+    FrameWorkspace w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += align_up(bytes ? bytes : 16, 256);
+        return p;
+    };
+    const size_t nn = (size_t)(n > 0 ? n : 0), pp = (size_t)(pcap > 0 ? pcap : 0);
+    // N-sized regions first: their addresses do not depend on the pair capacity, so plan, finish
+    // and render_backward of one frame agree on them whatever P turns out to be.
+    w.packed = static_cast<float*>(take(nn * 48));
+    w.tiles_touched = static_cast<int32_t*>(take(nn * 4));
+    w.offsets = static_cast<int32_t*>(take(nn * 4));
+    w.scan_temp = take(cugs_b200_scan_temp_bytes(n));
+    w.depth_minmax = static_cast<unsigned*>(take(64));
+    w.total_dev = reinterpret_cast<int64_t*>(w.depth_minmax ? w.depth_minmax + 4 : nullptr);
+    w.grad_acc = static_cast<float*>(take(nn * 48));
+    // P-sized scratch, live only inside render_finish
+    w.keys_x = static_cast<uint64_t*>(take(pp * 8));
+    w.keys_y = static_cast<uint64_t*>(take(pp * 8));
+    w.vals_y = static_cast<int32_t*>(take(pp * 4));
+    w.sort_temp_bytes = cugs_b200_sort_temp_bytes(pcap);
+    w.sort_temp = take(w.sort_temp_bytes);
+    w.total_bytes = off;
+    return w;
+}
+
+int ceil_log2(int x) {
+    int b = 0;
+    while ((1 << b) < x) ++b;
+    return b;
+}
+
+}  // namespace
+
+extern "C" size_t cugs_b200_render_workspace_bytes(int64_t n, int64_t p_capacity) {
+    return carve(nullptr, n, p_capacity).total_bytes;
+}
+
+// ------------------------------------------------------------------------------------------------
+// render: plan (preprocess + scan, returns P) and finish (dup + sort + ranges + blend)
+// ------------------------------------------------------------------------------------------------
+extern "C" int cugs_b200_render_plan(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
+                                     const float* positions, const float* rotations,
+                                     const float* scales, const float* opacities,
+                                     const float* sh_coeffs, float* means_2d, float* depths,
+                                     float* cov_2d_inv, int32_t* radii, float* rgb,
+                                     float* opacities_act, void* workspace, size_t workspace_bytes,
+                                     int64_t* p_host) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    CUGS_REQUIRE(h, n >= 0, "n must be >= 0");
+    CUGS_REQUIRE(h, p_host != nullptr, "p_host is null");
+    *p_host = 0;
+    if (n == 0) return CUGS_OK;
+    CUGS_REQUIRE(h, workspace != nullptr, "workspace is null");
+    if (workspace_bytes < cugs_b200_render_workspace_bytes(n, 0))
+        return set_error(h, CUGS_ERR_WORKSPACE, "workspace too small for N=%lld: %zu < %zu", (long long)n,
+                         workspace_bytes, cugs_b200_render_workspace_bytes(n, 0));
+    cudaStream_t s = (cudaStream_t)stream;
+    // the N-sized regions come first in the layout, so carving with pcap = 0 addresses them
+    const FrameWorkspace w = carve(workspace, n, 0);
+    CUGS_CUDA_TRY(h, cudaMemsetAsync(w.depth_minmax, 0xff, 4, s));
+    CUGS_CUDA_TRY(h, cudaMemsetAsync(w.depth_minmax + 1, 0, 4, s));
+    if (int e = cugs_b200_preprocess_fwd(h, stream, n, v, positions, rotations, scales, opacities, sh_coeffs,
+                                         means_2d, depths, cov_2d_inv, radii, w.tiles_touched, rgb,
+                                         opacities_act, w.packed, w.depth_minmax))
+        return e;
+    if (int e = cugs_scan_launch(h, s, n, w.tiles_touched, w.offsets, w.total_dev, true, w.scan_temp,
+                                 w.depth_minmax))
+        return e;
+    CUGS_CUDA_TRY(h, cudaStreamSynchronize(s));  // the one blocking read (reference: sorting.cu:146)
+    *p_host = h->pinned[0];
+    return CUGS_OK;
+}
+
+extern "C" int cugs_b200_render_finish(cugs_handle_t* h, void* stream, int64_t n, int64_t p,
+                                       const cugs_view_t* v, const float* means_2d, const float* depths,
+                                       const float* cov_2d_inv, const int32_t* radii, const float* rgb,
+                                       const float* opacities_act, int32_t* gaussian_idx,
+                                       int32_t* tile_ranges, float* color, float* final_T,
+                                       int32_t* n_contrib, void* workspace, size_t workspace_bytes) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    CUGS_REQUIRE(h, v != nullptr && v->width > 0 && v->height > 0, "bad view");
+    CUGS_REQUIRE(h, n >= 0 && p >= 0, "n and p must be >= 0");
+    CUGS_REQUIRE(h, tile_ranges && color && final_T && n_contrib, "null output");
+    CUGS_REQUIRE(h, p == 0 || gaussian_idx != nullptr, "gaussian_idx is null");
+    const int ntx = (v->width + kTile - 1) / kTile, nty = (v->height + kTile - 1) / kTile;
+    const int num_tiles = ntx * nty;
+    cudaStream_t s = (cudaStream_t)stream;
+    FrameWorkspace w{};
+    if (n > 0) {
+        CUGS_REQUIRE(h, workspace != nullptr, "workspace is null");
+        if (workspace_bytes < cugs_b200_render_workspace_bytes(n, p))
+            return set_error(h, CUGS_ERR_WORKSPACE, "workspace too small for N=%lld P=%lld: %zu < %zu",
+                             (long long)n, (long long)p, workspace_bytes,
+                             cugs_b200_render_workspace_bytes(n, p));
+        w = carve(workspace, n, p);
+    }
+    if (p > 0) {
+        // key bits that can differ: tile bits + depth bits below the highest differing one
+        const uint64_t mm = (uint64_t)h->pinned[1];
+        const unsigned dmin = (unsigned)(mm & 0xffffffffu), dmax = (unsigned)(mm >> 32);
+        int depth_bits = 32;
+        if (h->pinned[0] == p && dmin <= dmax) {
+            const unsigned x = dmin ^ dmax;
+            depth_bits = x ? 32 - __builtin_clz(x) : 0;
+        }
+        const int tile_bits = ceil_log2(num_tiles);
+        const int passes = cugs_b200_sort_num_passes(depth_bits, tile_bits);
+        // choose where the unsorted pairs go so that the sorted VALUES land in gaussian_idx
+        uint64_t* ka; int32_t* va; uint64_t* kb; int32_t* vb;
+        if (passes & 1) { ka = w.keys_y; va = w.vals_y; kb = w.keys_x; vb = gaussian_idx; }
+        else            { ka = w.keys_x; va = gaussian_idx; kb = w.keys_y; vb = w.vals_y; }
+        if (int e = cugs_b200_duplicate_with_keys(h, stream, n, v->width, v->height, means_2d, depths, radii,
+                                                  w.tiles_touched, w.offsets, p, ka, va))
+            return e;
+        int in_b = 0;
+        if (int e = cugs_b200_sort_pairs_pingpong(h, stream, p, depth_bits, tile_bits, ka, va, kb, vb,
+                                                  w.sort_temp, w.sort_temp_bytes, &in_b))
+            return e;
+    }
+    if (int e = cugs_b200_tile_ranges(h, stream, p, w.keys_x, num_tiles, tile_ranges)) return e;
+    if (int e = cugs_b200_blend_fwd(h, stream, v, tile_ranges, gaussian_idx, means_2d, cov_2d_inv, rgb,
+                                    opacities_act, n > 0 ? w.packed : nullptr, color, final_T, n_contrib)) {
+        return e;
+    }
+    (void)s;
+    return CUGS_OK;
+}
+
+extern "C" int cugs_b200_render_backward(
+    cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v, const float* positions,
+    const float* rotations, const float* scales, const float* opacities, const float* sh_coeffs,
+    const float* means_2d, const float* cov_2d_inv, const int32_t* radii, const float* rgb,
+    const float* opacities_act, const int32_t* gaussian_idx, const int32_t* tile_ranges,
+    const float* final_T, const int32_t* n_contrib, const float* dL_dcolor, float* dL_dpositions,
+    float* dL_drotations, float* dL_dscales, float* dL_dopacities, float* dL_dsh_coeffs,
+    float* dL_dmeans_2d, float* grad_accum, float* grad_count, float* max_radii, void* workspace,
+    size_t workspace_bytes) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    CUGS_REQUIRE(h, n >= 0, "n must be >= 0");
+    if (n == 0) return CUGS_OK;
+    CUGS_REQUIRE(h, v != nullptr && v->width > 0 && v->height > 0, "bad view");
+    CUGS_REQUIRE(h, workspace != nullptr, "workspace is null");
+    CUGS_REQUIRE(h, dL_dcolor && final_T && n_contrib && tile_ranges, "null input");
+    CUGS_REQUIRE(h, dL_dpositions && dL_drotations && dL_dscales && dL_dopacities && dL_dsh_coeffs &&
+                        dL_dmeans_2d, "null output");
+    const bool any_stats = grad_accum || grad_count || max_radii;
+    CUGS_REQUIRE(h, !any_stats || (grad_accum && grad_count && max_radii),
+                 "stats pointers must be all set or all null");
+    if (workspace_bytes < cugs_b200_render_workspace_bytes(n, 0))
+        return set_error(h, CUGS_ERR_WORKSPACE, "workspace too small for N=%lld: %zu < %zu", (long long)n,
+                         workspace_bytes, cugs_b200_render_workspace_bytes(n, 0));
+    cudaStream_t s = (cudaStream_t)stream;
+    const FrameWorkspace w = carve(workspace, n, 0);
+    // stage 1 (rasterizer.cpp:146-158): pixel gradients -> packed per-Gaussian 2-D gradients
+    if (int e = cugs_blend_bwd_accumulate(h, s, n, v, tile_ranges, gaussian_idx, means_2d, cov_2d_inv, rgb,
+                                          opacities_act, w.packed, dL_dcolor, final_T, n_contrib, w.grad_acc))
+        return e;
+    // stage 2 (rasterizer.cpp:163-176): 2-D gradients -> parameter gradients (+ SH backward, + stats)
+    return cugs_preprocess_bwd_launch(h, s, n, v, positions, rotations, scales, opacities, sh_coeffs, radii,
+                                      rgb, nullptr, nullptr, nullptr, nullptr, dL_dpositions, dL_drotations,
+                                      dL_dscales, dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count,
+                                      max_radii, w.grad_acc, dL_dmeans_2d);
+}

@@ -1,0 +1,174 @@
+// common.cuh — shared device/host helpers for the sm_100a rasterizer kernels.
+// No torch headers anywhere under csrc/ (keeps each TU at seconds of nvcc time).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/cugs_b200.h"
+
+struct cugs_handle {
+    int device;
+    int sm_count;
+    int64_t* pinned;      // mapped pinned host words {P, depth_min|depth_max<<32, ...}
+    char err[512];
+};
+
+namespace cugs {
+
+constexpr int kTile = CUGS_TILE;
+constexpr unsigned kFull = 0xffffffffu;
+
+inline int set_error(cugs_handle* h, int code, const char* fmt, ...) {
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CUGS_CUDA_TRY(h, expr)                                                                  \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return cugs::set_error((h), (int)_e, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,   \
+                                   cudaGetErrorString(_e));                                     \
+    } while (0)
+
+#define CUGS_LAUNCH_CHECK(h, name)                                                              \
+    do {                                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess)                                                                  \
+            return cugs::set_error((h), (int)_e, "launch %s failed: %s", (name),                \
+                                   cudaGetErrorString(_e));                                     \
+    } while (0)
+
+#define CUGS_REQUIRE(h, cond, msg)                                                              \
+    do {                                                                                        \
+        if (!(cond)) return cugs::set_error((h), CUGS_ERR_INVALID_ARG, "%s (%s)", (msg), #cond); \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- explicit-rounding helpers: spell out the FMA contraction nvcc applies to the reference's
+// expressions so integer outputs derived from float math stay bit-identical. ----
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+// a*b + c*d  ->  fma(a, b, rn(c*d))
+__device__ __forceinline__ float dot2c(float a, float b, float c, float d) {
+    return __fmaf_rn(a, b, __fmul_rn(c, d));
+}
+// a*b + c*d + e*f  ->  fma(e, f, fma(a, b, rn(c*d)))
+__device__ __forceinline__ float dot3c(float a, float b, float c, float d, float e, float f) {
+    return __fmaf_rn(e, f, __fmaf_rn(a, b, __fmul_rn(c, d)));
+}
+
+// Tile rectangle of a projected Gaussian, shared by preprocess (projection.cu:172-188) and key
+// emission (sorting.cu:52-57). (int) casts are cvt.rzi (truncate, saturate, NaN -> 0).
+struct TileRect {
+    int tx0, ty0, tx1, ty1;
+};
+__device__ __forceinline__ TileRect tile_rect(float x, float y, int radius, int w, int h, int ntx,
+                                              int nty) {
+    const float r = (float)radius;
+    const int rminx = max(0, (int)(x - r));
+    const int rminy = max(0, (int)(y - r));
+    const int rmaxx = min(w, (int)(x + r + 1.0f));
+    const int rmaxy = min(h, (int)(y + r + 1.0f));
+    TileRect t;
+    t.tx0 = rminx / kTile;
+    t.ty0 = rminy / kTile;
+    t.tx1 = min(ntx, (rmaxx + kTile - 1) / kTile);
+    t.ty1 = min(nty, (rmaxy + kTile - 1) / kTile);
+    return t;
+}
+
+// SH basis Y_k(dir), constants and signs as core/sh.cu:44-74. Entries >= (deg+1)^2 are 0.
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float Y[16]) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) Y[k] = 0.0f;
+    Y[0] = 0.28209479177387814f;
+    if (deg >= 1) {
+        Y[1] = -0.4886025119029199f * y;
+        Y[2] = 0.4886025119029199f * z;
+        Y[3] = -0.4886025119029199f * x;
+    }
+    if (deg >= 2) {
+        const float xx = x * x, yy = y * y, zz = z * z;
+        Y[4] = 1.0925484305920792f * (x * y);
+        Y[5] = 1.0925484305920792f * (y * z);
+        Y[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+        Y[7] = 1.0925484305920792f * (x * z);
+        Y[8] = 0.5462742152960396f * (xx - yy);
+        if (deg >= 3) {
+            Y[9] = 0.5900435899266435f * y * (3.0f * xx - yy);
+            Y[10] = 2.890611442640554f * x * y * z;
+            Y[11] = 0.4570457994644658f * y * (4.0f * zz - xx - yy);
+            Y[12] = 0.3731763325901154f * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+            Y[13] = 0.4570457994644658f * x * (4.0f * zz - xx - yy);
+            Y[14] = 1.4453057213202769f * z * (xx - yy);
+            Y[15] = 0.5900435899266435f * x * (xx - 3.0f * yy);
+        }
+    }
+}
+
+// Normalised view direction (projection.cu:273-280: (p - c) / clamp_min(||p - c||, 1e-8)).
+__device__ __forceinline__ void view_dir(float px, float py, float pz, const float c[3], float& dx,
+                                         float& dy, float& dz) {
+    dx = px - c[0];
+    dy = py - c[1];
+    dz = pz - c[2];
+    const float n = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
+    dx = dx / n;
+    dy = dy / n;
+    dz = dz / n;
+}
+
+// Conservative early-reject threshold for the blend kernels: alpha = op * exp(power) can reach
+// 1/255 only if power >= -log(255 * op). Evaluations with power below (that - 1e-4) are rejected
+// without evaluating exp; everything else takes the exact path (accurate expf, the reference's
+// own comparisons), so n_contrib / final_T decisions stay bit-identical. The 1e-4 guard band is
+// ~300x the combined rounding error of __logf, expf and the product. NaN opacity -> -inf
+// (always exact path); op <= 0 -> +1 (never contributes, as in the reference).
+__device__ __forceinline__ float blend_reject_threshold(float op) {
+    if (op != op) return -INFINITY;
+    if (!(op > 0.0f)) return 1.0f;
+    return -__logf(255.0f * op) - 1e-4f;
+}
+
+// Per-launch constants shared by the per-Gaussian kernels (passed by value: lives in the
+// constant bank, so the 16-entry view matrix is not re-read from global by every thread).
+struct ViewParams {
+    float W[9];       // rotation rows of the row-major view matrix
+    float t[3];       // view[3], view[7], view[11]
+    float cam[3];
+    float fx, fy, cx, cy;
+    float scale_mod;  // kernels add logf(scale_mod + 1e-8f) on the device (projection.cu:126-130)
+    int width, height, ntx, nty;
+    int deg, C;
+};
+
+inline ViewParams make_view_params(const cugs_view_t* v) {
+    ViewParams p;
+    p.W[0] = v->view[0]; p.W[1] = v->view[1]; p.W[2] = v->view[2];
+    p.W[3] = v->view[4]; p.W[4] = v->view[5]; p.W[5] = v->view[6];
+    p.W[6] = v->view[8]; p.W[7] = v->view[9]; p.W[8] = v->view[10];
+    p.t[0] = v->view[3]; p.t[1] = v->view[7]; p.t[2] = v->view[11];
+    p.cam[0] = v->cam_center[0]; p.cam[1] = v->cam_center[1]; p.cam[2] = v->cam_center[2];
+    p.fx = v->fx; p.fy = v->fy; p.cx = v->cx; p.cy = v->cy;
+    p.scale_mod = v->scale_modifier;
+    p.width = v->width; p.height = v->height;
+    p.ntx = (v->width + kTile - 1) / kTile;
+    p.nty = (v->height + kTile - 1) / kTile;
+    p.deg = v->active_sh_degree;
+    p.C = v->num_coeffs;
+    return p;
+}
+
+}  // namespace cugs

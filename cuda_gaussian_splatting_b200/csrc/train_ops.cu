@@ -1,0 +1,357 @@
+// train_ops.cu — the per-step kernels either side of the rasterizer:
+//   * fused L1 + SSIM loss, value AND gradient w.r.t. the rendered image, replacing the libtorch
+//     op graph of reference training/loss.cpp:83-135 (5 grouped 11x11 conv2d + ~20 elementwise
+//     kernels forward, the same again in autograd backward, training/trainer.cpp:214-217);
+//   * multi-tensor fused Adam: all five parameter groups in ONE launch, float4 accesses,
+//     replacing 5 x k_fused_adam (reference optimizer/fused_adam.cu:44-76, :140-164);
+//   * densification statistics (reference optimizer/densification.cpp:59-88, ~10 libtorch kernels
+//     with boolean-mask gathers) as one elementwise kernel.
+// All three are HBM-bound: loss 36 B/pixel algorithmic (+72 B/pixel for the three derivative maps
+// kept between the two passes), Adam 28 B/element, stats 36 B/Gaussian.
+#include "common.cuh"
+
+#include <cmath>
+
+namespace cugs {
+
+// ================================================================================================
+// L1 + SSIM
+// ================================================================================================
+constexpr int kLossTile = 16;
+constexpr int kHalo = 5;
+constexpr int kLossIn = kLossTile + 2 * kHalo;  // 26
+
+struct SsimWindow {
+    float w[11];  // separable factor of the reference's 2-D window (loss.cpp:57-70)
+};
+
+// pass 1: local moments -> SSIM map value (summed) and the three partial-derivative maps
+//   g1 = dS/dmu_x, g2 = dS/dE[x^2], g3 = dS/dE[xy]   (raw moments held fixed)
+__global__ void __launch_bounds__(256)
+k_ssim_moments(int width, int height, SsimWindow win, const float* __restrict__ x_img,
+               const float* __restrict__ y_img, float* __restrict__ g1, float* __restrict__ g2,
+               float* __restrict__ g3, double* __restrict__ sums /* [2]: sum|x-y|, sum S */) {
+    __shared__ float sx[kLossIn][kLossIn * 3];
+    __shared__ float sy[kLossIn][kLossIn * 3];
+    __shared__ float sh[5][kLossIn][kLossTile * 3];
+    __shared__ float s_red[2][8];
+
+    const int tx0 = blockIdx.x * kLossTile, ty0 = blockIdx.y * kLossTile;
+    // load tile + halo, zero padding outside the image (conv2d padding=5, loss.cpp:102-103)
+    for (int e = threadIdx.x; e < kLossIn * kLossIn * 3; e += 256) {
+        const int r = e / (kLossIn * 3), cc = e % (kLossIn * 3);
+        const int gx = tx0 - kHalo + cc / 3, gy = ty0 - kHalo + r, ch = cc % 3;
+        float vx = 0.f, vy = 0.f;
+        if (gx >= 0 && gx < width && gy >= 0 && gy < height) {
+            const int64_t gi = ((int64_t)gy * width + gx) * 3 + ch;
+            vx = x_img[gi];
+            vy = y_img[gi];
+        }
+        sx[r][cc] = vx;
+        sy[r][cc] = vy;
+    }
+    __syncthreads();
+    // horizontal pass: 26 rows x 16 columns x 3 channels, five moments each
+    for (int e = threadIdx.x; e < kLossIn * kLossTile * 3; e += 256) {
+        const int r = e / (kLossTile * 3), cc = e % (kLossTile * 3);
+        const int col = cc / 3, ch = cc % 3;
+        float mx = 0.f, my = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const float a = sx[r][(col + k) * 3 + ch], b = sy[r][(col + k) * 3 + ch], w = win.w[k];
+            mx = fmaf(w, a, mx);
+            my = fmaf(w, b, my);
+            xx = fmaf(w, a * a, xx);
+            yy = fmaf(w, b * b, yy);
+            xy = fmaf(w, a * b, xy);
+        }
+        sh[0][r][cc] = mx; sh[1][r][cc] = my; sh[2][r][cc] = xx; sh[3][r][cc] = yy; sh[4][r][cc] = xy;
+    }
+    __syncthreads();
+    // vertical pass + SSIM
+    const int lx = threadIdx.x % kLossTile, ly = threadIdx.x / kLossTile;
+    const int gx = tx0 + lx, gy = ty0 + ly;
+    float l1_local = 0.f, s_local = 0.f;
+    if (gx < width && gy < height) {
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float mx = 0.f, my = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) {
+                const float w = win.w[k];
+                mx = fmaf(w, sh[0][ly + k][lx * 3 + ch], mx);
+                my = fmaf(w, sh[1][ly + k][lx * 3 + ch], my);
+                xx = fmaf(w, sh[2][ly + k][lx * 3 + ch], xx);
+                yy = fmaf(w, sh[3][ly + k][lx * 3 + ch], yy);
+                xy = fmaf(w, sh[4][ly + k][lx * 3 + ch], xy);
+            }
+            const float sxx = xx - mx * mx, syy = yy - my * my, sxy = xy - mx * my;
+            const float A1 = 2.0f * mx * my + C1, A2 = 2.0f * sxy + C2;
+            const float B1 = mx * mx + my * my + C1, B2 = sxx + syy + C2;
+            const float inv = 1.0f / (B1 * B2);
+            const float S = A1 * A2 * inv;
+            const int64_t gi = ((int64_t)gy * width + gx) * 3 + ch;
+            // dS/dmu_x = (A1' A2 + A1 A2')/(B1 B2) - S (B1'/B1 + B2'/B2)
+            g1[gi] = (2.0f * my * A2 - 2.0f * my * A1) * inv - S * (2.0f * mx / B1 - 2.0f * mx / B2);
+            g2[gi] = -S / B2;
+            g3[gi] = 2.0f * A1 * inv;
+            s_local += S;
+            l1_local += fabsf(sx[ly + kHalo][(lx + kHalo) * 3 + ch] - sy[ly + kHalo][(lx + kHalo) * 3 + ch]);
+        }
+    }
+    // block reduction -> one double atomic per block and quantity
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        l1_local += __shfl_xor_sync(kFull, l1_local, d);
+        s_local += __shfl_xor_sync(kFull, s_local, d);
+    }
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = l1_local; s_red[1][threadIdx.x >> 5] = s_local; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += (double)s_red[0][w]; b += (double)s_red[1][w]; }
+        atomicAdd(&sums[0], a);
+        atomicAdd(&sums[1], b);
+    }
+}
+
+// pass 2: dL/dx = (1-l) sign(x-y)/n - l/n * (W*g1 + 2 x (W*g2) + y (W*g3))
+__global__ void __launch_bounds__(256)
+k_ssim_gradient(int width, int height, SsimWindow win, float lambda, const float* __restrict__ x_img,
+                const float* __restrict__ y_img, const float* __restrict__ g1,
+                const float* __restrict__ g2, const float* __restrict__ g3, float* __restrict__ dL_dx) {
+    __shared__ float sg[3][kLossIn][kLossIn * 3];
+    __shared__ float sh[3][kLossIn][kLossTile * 3];
+    const int tx0 = blockIdx.x * kLossTile, ty0 = blockIdx.y * kLossTile;
+    for (int e = threadIdx.x; e < kLossIn * kLossIn * 3; e += 256) {
+        const int r = e / (kLossIn * 3), cc = e % (kLossIn * 3);
+        const int gx = tx0 - kHalo + cc / 3, gy = ty0 - kHalo + r, ch = cc % 3;
+        float a = 0.f, b = 0.f, c = 0.f;
+        if (gx >= 0 && gx < width && gy >= 0 && gy < height) {
+            const int64_t gi = ((int64_t)gy * width + gx) * 3 + ch;
+            a = g1[gi]; b = g2[gi]; c = g3[gi];
+        }
+        sg[0][r][cc] = a; sg[1][r][cc] = b; sg[2][r][cc] = c;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kLossIn * kLossTile * 3; e += 256) {
+        const int r = e / (kLossTile * 3), cc = e % (kLossTile * 3);
+        const int col = cc / 3, ch = cc % 3;
+        float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const float w = win.w[k];
+            a = fmaf(w, sg[0][r][(col + k) * 3 + ch], a);
+            b = fmaf(w, sg[1][r][(col + k) * 3 + ch], b);
+            c = fmaf(w, sg[2][r][(col + k) * 3 + ch], c);
+        }
+        sh[0][r][cc] = a; sh[1][r][cc] = b; sh[2][r][cc] = c;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x % kLossTile, ly = threadIdx.x / kLossTile;
+    const int gx = tx0 + lx, gy = ty0 + ly;
+    if (gx >= width || gy >= height) return;
+    const float inv_n = 1.0f / (3.0f * (float)width * (float)height);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const float w = win.w[k];
+            a = fmaf(w, sh[0][ly + k][lx * 3 + ch], a);
+            b = fmaf(w, sh[1][ly + k][lx * 3 + ch], b);
+            c = fmaf(w, sh[2][ly + k][lx * 3 + ch], c);
+        }
+        const int64_t gi = ((int64_t)gy * width + gx) * 3 + ch;
+        const float xv = x_img[gi], yv = y_img[gi];
+        const float d = xv - yv;
+        const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+        const float dssim = a + 2.0f * xv * b + yv * c;
+        dL_dx[gi] = (1.0f - lambda) * sgn * inv_n - lambda * inv_n * dssim;
+    }
+}
+
+__global__ void k_loss_finalize(int width, int height, float lambda, const double* __restrict__ sums,
+                                float* __restrict__ scalars3) {
+    const double n = 3.0 * (double)width * (double)height;
+    const double l1 = sums[0] / n, ss = sums[1] / n;
+    scalars3[0] = (float)((1.0 - (double)lambda) * l1 + (double)lambda * (1.0 - ss));
+    scalars3[1] = (float)l1;
+    scalars3[2] = (float)ss;
+}
+
+static SsimWindow make_window() {
+    // loss.cpp:57-70: float 1-D gaussian (sigma 1.5) / sum; 2-D = outer product / its sum
+    float k[11], sum = 0.f;
+    for (int i = 0; i < 11; ++i) {
+        const float x = (float)(i - 5);
+        k[i] = std::exp(-x * x / (2.0f * 1.5f * 1.5f));
+        sum += k[i];
+    }
+    for (int i = 0; i < 11; ++i) k[i] = k[i] / sum;
+    double s2 = 0.0;
+    for (int i = 0; i < 11; ++i)
+        for (int j = 0; j < 11; ++j) s2 += (double)(k[i] * k[j]);
+    SsimWindow w;
+    for (int i = 0; i < 11; ++i) w.w[i] = (float)((double)k[i] / std::sqrt(s2));
+    return w;
+}
+
+// ================================================================================================
+// multi-tensor Adam
+// ================================================================================================
+struct AdamGroups {
+    float* p[5];
+    const float* g[5];
+    float* m[5];
+    float* v[5];
+    int64_t count[5];
+    int64_t chunk_end[5];  // cumulative number of float4 chunks
+    float lr[5];
+};
+
+__device__ __forceinline__ void adam_element(float& p, float g, float& m, float& v, float lr, float b1,
+                                             float b2, float eps, float bc1, float bc2) {
+    // fused_adam.cu:57-75 with nvcc's contraction spelled out
+    const float mi = fma_rn(b1, m, mul_rn(add_rn(1.0f, -b1), g));
+    const float vi = fma_rn(b2, v, mul_rn(mul_rn(add_rn(1.0f, -b2), g), g));
+    m = mi;
+    v = vi;
+    const float m_hat = mul_rn(mi, bc1), v_hat = mul_rn(vi, bc2);
+    p = add_rn(p, -(mul_rn(lr, m_hat) / add_rn(sqrtf(v_hat), eps)));
+}
+
+__global__ void __launch_bounds__(256)
+k_adam_multi(AdamGroups G, int64_t total_chunks, float b1, float b2, float eps, float bc1, float bc2,
+             float grad_scale) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total_chunks;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        int grp = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c >= G.chunk_end[k]) grp = k + 1;
+        const int64_t local = c - (grp ? G.chunk_end[grp - 1] : 0);
+        const int64_t e0 = local * 4;
+        float* p = G.p[grp];
+        const float* g = G.g[grp];
+        float* m = G.m[grp];
+        float* v = G.v[grp];
+        const float lr = G.lr[grp];
+        if (e0 + 4 <= G.count[grp]) {
+            float4 pv = *reinterpret_cast<float4*>(p + e0);
+            const float4 gv = __ldcs(reinterpret_cast<const float4*>(g + e0));
+            float4 mv = *reinterpret_cast<float4*>(m + e0);
+            float4 vv = *reinterpret_cast<float4*>(v + e0);
+            adam_element(pv.x, gv.x * grad_scale, mv.x, vv.x, lr, b1, b2, eps, bc1, bc2);
+            adam_element(pv.y, gv.y * grad_scale, mv.y, vv.y, lr, b1, b2, eps, bc1, bc2);
+            adam_element(pv.z, gv.z * grad_scale, mv.z, vv.z, lr, b1, b2, eps, bc1, bc2);
+            adam_element(pv.w, gv.w * grad_scale, mv.w, vv.w, lr, b1, b2, eps, bc1, bc2);
+            *reinterpret_cast<float4*>(p + e0) = pv;
+            *reinterpret_cast<float4*>(m + e0) = mv;
+            *reinterpret_cast<float4*>(v + e0) = vv;
+        } else {
+            for (int64_t e = e0; e < G.count[grp]; ++e) {
+                float pe = p[e], me = m[e], ve = v[e];
+                adam_element(pe, g[e] * grad_scale, me, ve, lr, b1, b2, eps, bc1, bc2);
+                p[e] = pe; m[e] = me; v[e] = ve;
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// densification statistics
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+k_accumulate_stats(int64_t n, const float* __restrict__ dL_dmeans_2d, const int* __restrict__ radii,
+                   float* __restrict__ grad_accum, float* __restrict__ grad_count,
+                   float* __restrict__ max_radii) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = radii[i];
+    if (r > 0) {  // visible = radii > 0 (densification.cpp:71)
+        const float2 g = reinterpret_cast<const float2*>(dL_dmeans_2d)[i];
+        grad_accum[i] += sqrtf(g.x * g.x + g.y * g.y);
+        grad_count[i] += 1.0f;
+    }
+    max_radii[i] = fmaxf(max_radii[i], (float)r);
+}
+
+}  // namespace cugs
+
+using namespace cugs;
+
+extern "C" size_t cugs_b200_loss_workspace_bytes(int width, int height) {
+    if (width <= 0 || height <= 0) return 64;
+    return 64 + (size_t)3 * 3 * (size_t)width * (size_t)height * sizeof(float);
+}
+
+extern "C" int cugs_b200_loss_l1_ssim(cugs_handle_t* h, void* stream, int width, int height, float lambda,
+                                      const float* rendered, const float* target, float* dL_dcolor,
+                                      float* scalars3, void* workspace, size_t workspace_bytes) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    CUGS_REQUIRE(h, width > 0 && height > 0, "image size must be positive");
+    CUGS_REQUIRE(h, rendered && target && scalars3 && workspace, "null pointer");
+    if (workspace_bytes < cugs_b200_loss_workspace_bytes(width, height))
+        return set_error(h, CUGS_ERR_WORKSPACE, "loss workspace too small: %zu < %zu", workspace_bytes,
+                         cugs_b200_loss_workspace_bytes(width, height));
+    static const SsimWindow win = make_window();
+    cudaStream_t s = (cudaStream_t)stream;
+    double* sums = reinterpret_cast<double*>(workspace);
+    const size_t plane = (size_t)3 * width * height;
+    float* g1 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 64);
+    float* g2 = g1 + plane;
+    float* g3 = g2 + plane;
+    CUGS_CUDA_TRY(h, cudaMemsetAsync(sums, 0, 64, s));
+    const dim3 grid((width + kLossTile - 1) / kLossTile, (height + kLossTile - 1) / kLossTile);
+    k_ssim_moments<<<grid, 256, 0, s>>>(width, height, win, rendered, target, g1, g2, g3, sums);
+    CUGS_LAUNCH_CHECK(h, "k_ssim_moments");
+    if (dL_dcolor) {
+        k_ssim_gradient<<<grid, 256, 0, s>>>(width, height, win, lambda, rendered, target, g1, g2, g3, dL_dcolor);
+        CUGS_LAUNCH_CHECK(h, "k_ssim_gradient");
+    }
+    k_loss_finalize<<<1, 1, 0, s>>>(width, height, lambda, sums, scalars3);
+    CUGS_LAUNCH_CHECK(h, "k_loss_finalize");
+    return CUGS_OK;
+}
+
+extern "C" int cugs_b200_adam_step(cugs_handle_t* h, void* stream, float* const params[5],
+                                   const float* const grads[5], float* const m[5], float* const v[5],
+                                   const int64_t counts[5], const float lr[5], float beta1, float beta2,
+                                   float eps, float bc1, float bc2, float grad_scale) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    CUGS_REQUIRE(h, params && grads && m && v && counts && lr, "null pointer");
+    AdamGroups G;
+    int64_t chunks = 0;
+    for (int k = 0; k < 5; ++k) {
+        CUGS_REQUIRE(h, counts[k] >= 0, "negative count");
+        CUGS_REQUIRE(h, counts[k] == 0 || (params[k] && grads[k] && m[k] && v[k]), "null group pointer");
+        G.p[k] = params[k]; G.g[k] = grads[k]; G.m[k] = m[k]; G.v[k] = v[k];
+        G.count[k] = counts[k];
+        G.lr[k] = lr[k];
+        chunks += (counts[k] + 3) / 4;
+        G.chunk_end[k] = chunks;
+    }
+    if (chunks == 0) return CUGS_OK;
+    int64_t blocks = (chunks + 255) / 256;
+    const int64_t cap = (int64_t)h->sm_count * 8 * 4;  // persistent-ish grid, multiple of the SM count
+    if (blocks > cap) blocks = cap;
+    k_adam_multi<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(G, chunks, beta1, beta2, eps, bc1, bc2,
+                                                                    grad_scale);
+    CUGS_LAUNCH_CHECK(h, "k_adam_multi");
+    return CUGS_OK;
+}
+
+extern "C" int cugs_b200_accumulate_stats(cugs_handle_t* h, void* stream, int64_t n,
+                                          const float* dL_dmeans_2d, const int32_t* radii,
+                                          float* grad_accum, float* grad_count, float* max_radii) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    CUGS_REQUIRE(h, n >= 0, "n must be >= 0");
+    if (n == 0) return CUGS_OK;
+    CUGS_REQUIRE(h, dL_dmeans_2d && radii && grad_accum && grad_count && max_radii, "null pointer");
+    k_accumulate_stats<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n, dL_dmeans_2d, radii, grad_accum, grad_count, max_radii);
+    CUGS_LAUNCH_CHECK(h, "k_accumulate_stats");
+    return CUGS_OK;
+}

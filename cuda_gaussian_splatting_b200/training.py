@@ -1,0 +1,206 @@
+"""Host-side mirror of the two per-step pieces either side of the rasterizer, on the C ABI:
+
+* ``combined_loss`` / ``l1_loss`` / ``ssim_loss`` (reference training/loss.hpp:22-53) — here the
+  fused kernel also returns the gradient the reference obtains from libtorch autograd
+  (training/trainer.cpp:214-217): ``combined_loss_with_grad``.
+* ``FusedAdam`` / ``AdamConfig`` / ``position_lr`` / ``active_sh_degree_for_step``
+  (optimizer/fused_adam.hpp:29-106, optimizer/adam.hpp:30-41, training/lr_schedule.hpp:36-80).
+* ``DensificationStats.accumulate_gradients`` (optimizer/densification.cpp:59-88).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .rasterizer import BackwardOutput, GaussianModel, _check, _lib_and_handle, _ptr, _stream
+
+
+# ----------------------------------------------------------------------------------------------
+# loss
+# ----------------------------------------------------------------------------------------------
+def _validate_image(img: torch.Tensor, name: str) -> None:  # loss.cpp:15-25
+    _check(img.dim() == 3, f"{name} must be 3-dimensional [H, W, 3], got {img.dim()} dims")
+    _check(img.shape[2] == 3, f"{name} must have 3 channels, got {img.shape[2]}")
+    _check(img.dtype == torch.float32, f"{name} must be float32, got {img.dtype}")
+    _check(img.is_cuda, f"{name} must be on a CUDA device")
+
+
+def _validate_pair(rendered: torch.Tensor, target: torch.Tensor) -> None:  # loss.cpp:28-34
+    _validate_image(rendered, "rendered")
+    _validate_image(target, "target")
+    _check(rendered.shape == target.shape,
+           f"rendered and target must have the same shape, got {tuple(rendered.shape)} vs {tuple(target.shape)}")
+
+
+_loss_ws: dict = {}
+
+
+def combined_loss_with_grad(rendered: torch.Tensor, target: torch.Tensor, lambda_: float = 0.2,
+                            want_grad: bool = True):
+    """One fused pass: returns (scalars[3] = {loss, l1, mean ssim} on device, dL/d(rendered))."""
+    _validate_pair(rendered, target)
+    dev = rendered.device
+    lib, h = _lib_and_handle(dev)
+    H, W = int(rendered.shape[0]), int(rendered.shape[1])
+    key = (dev.index, W, H)
+    ws = _loss_ws.get(key)
+    if ws is None:
+        ws = torch.empty((lib.cugs_b200_loss_workspace_bytes(W, H),), dtype=torch.uint8, device=dev)
+        _loss_ws[key] = ws
+    scalars = torch.empty((3,), dtype=torch.float32, device=dev)
+    grad = torch.empty_like(rendered, memory_format=torch.contiguous_format) if want_grad else None
+    st = lib.cugs_b200_loss_l1_ssim(h, _stream(dev), W, H, float(lambda_), _ptr(rendered.contiguous()),
+                                    _ptr(target.contiguous()), _ptr(grad), _ptr(scalars), _ptr(ws), ws.numel())
+    _lib.check(h, st, "cugs_b200_loss_l1_ssim")
+    return scalars, grad
+
+
+def combined_loss(rendered, target, lambda_: float = 0.2) -> torch.Tensor:  # loss.hpp:52
+    return combined_loss_with_grad(rendered, target, lambda_, want_grad=False)[0][0]
+
+
+def l1_loss(rendered, target) -> torch.Tensor:  # loss.hpp:22
+    return combined_loss_with_grad(rendered, target, 0.0, want_grad=False)[0][1]
+
+
+def ssim_loss(rendered, target) -> torch.Tensor:  # loss.hpp:43
+    return 1.0 - combined_loss_with_grad(rendered, target, 1.0, want_grad=False)[0][2]
+
+
+def ssim_mean(rendered, target) -> torch.Tensor:
+    return combined_loss_with_grad(rendered, target, 1.0, want_grad=False)[0][2]
+
+
+# ----------------------------------------------------------------------------------------------
+# learning-rate schedule (training/lr_schedule.hpp)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class PositionLRConfig:
+    lr_init: float = 1.6e-4
+    lr_final: float = 1.6e-6
+    max_steps: int = 30000
+
+
+def position_lr(step: int, config: PositionLRConfig) -> float:  # lr_schedule.hpp:49-57
+    if step >= config.max_steps:
+        return float(np.float32(config.lr_final))
+    if step <= 0:
+        return float(np.float32(config.lr_init))
+    t = np.float32(step) / np.float32(config.max_steps)
+    log_ratio = np.float32(math.log(np.float32(config.lr_final) / np.float32(config.lr_init)))
+    return float(np.float32(config.lr_init) * np.float32(math.exp(np.float32(t * log_ratio))))
+
+
+def active_sh_degree_for_step(step: int, max_degree: int) -> int:  # lr_schedule.hpp:70-72
+    return min(step // 1000, max_degree)
+
+
+@dataclass
+class AdamConfig:  # optimizer/adam.hpp:30-41
+    position_lr_config: PositionLRConfig = field(default_factory=PositionLRConfig)
+    lr_sh_coeffs: float = 2.5e-3
+    lr_opacities: float = 0.05
+    lr_scales: float = 5e-3
+    lr_rotations: float = 1e-3
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-15
+
+
+class FusedAdam:
+    """optimizer/fused_adam.hpp:29-106. Group order positions, sh_coeffs, opacities, scales,
+    rotations (fused_adam.cu:94-97); all five groups are updated by ONE kernel launch."""
+
+    K_POSITIONS, K_SH, K_OPACITIES, K_SCALES, K_ROTATIONS = range(5)
+
+    def __init__(self, model: GaussianModel, config: Optional[AdamConfig] = None):
+        self.model = model
+        self.config = config or AdamConfig()
+        self.step_count = 0
+        self._params = [model.positions, model.sh_coeffs, model.opacities, model.scales, model.rotations]
+        for p in self._params:
+            _check(p.is_cuda, "FusedAdam: param must be on CUDA")
+            _check(p.is_contiguous() and p.dtype == torch.float32, "FusedAdam: params must be contiguous f32")
+        self.m = [torch.zeros_like(p) for p in self._params]
+        self.v = [torch.zeros_like(p) for p in self._params]
+        self.grads = [None] * 5
+        c = self.config
+        self.learning_rates = [c.position_lr_config.lr_init, c.lr_sh_coeffs, c.lr_opacities, c.lr_scales,
+                               c.lr_rotations]
+        self.grad_scale = 1.0
+
+    def apply_gradients(self, grads: BackwardOutput) -> None:  # fused_adam.cu:113-120
+        self.grads = [grads.dL_dpositions, grads.dL_dsh_coeffs, grads.dL_dopacities, grads.dL_dscales,
+                      grads.dL_drotations]
+
+    def update_lr(self, step: int) -> None:  # fused_adam.cu:122-124
+        self.learning_rates[0] = position_lr(step, self.config.position_lr_config)
+
+    def zero_grad(self) -> None:  # fused_adam.cu:126-138
+        self.grads = [None] * 5
+
+    def get_lr(self, group: int) -> float:
+        return self.learning_rates[group]
+
+    def step(self) -> None:  # fused_adam.cu:140-164
+        self.step_count += 1
+        b1, b2 = float(np.float32(self.config.beta1)), float(np.float32(self.config.beta2))
+        bc1 = 1.0 / (1.0 - b1 ** self.step_count)  # double precision on the host (:145-149)
+        bc2 = 1.0 / (1.0 - b2 ** self.step_count)
+        dev = self._params[0].device
+        lib, h = _lib_and_handle(dev)
+        P = (C.c_void_p * 5)()
+        G = (C.c_void_p * 5)()
+        M = (C.c_void_p * 5)()
+        V = (C.c_void_p * 5)()
+        cnt = (C.c_int64 * 5)()
+        lr = (C.c_float * 5)()
+        keep = []
+        for k in range(5):
+            g = self.grads[k]
+            if g is None:  # "if (!grads_[i].defined()) continue" (:157)
+                cnt[k] = 0
+                continue
+            _check(g.is_cuda, "FusedAdam: grad must be on CUDA")
+            _check(g.numel() == self._params[k].numel(),
+                   f"FusedAdam: param/grad size mismatch: {self._params[k].numel()} vs {g.numel()}")
+            g = g.contiguous()
+            keep.append(g)
+            P[k], G[k], M[k], V[k] = (self._params[k].data_ptr(), g.data_ptr(), self.m[k].data_ptr(),
+                                      self.v[k].data_ptr())
+            cnt[k] = self._params[k].numel()
+            lr[k] = self.learning_rates[k]
+        st = lib.cugs_b200_adam_step(h, _stream(dev), P, G, M, V, cnt, lr, self.config.beta1, self.config.beta2,
+                                     self.config.eps, bc1, bc2, float(self.grad_scale))
+        _lib.check(h, st, "cugs_b200_adam_step")
+
+
+class DensificationStats:
+    """The per-step accumulators of DensificationController (optimizer/densification.cpp:59-88)."""
+
+    def __init__(self, n: int, device):
+        self.grad_accum = torch.zeros((n,), dtype=torch.float32, device=device)
+        self.grad_count = torch.zeros((n,), dtype=torch.float32, device=device)
+        self.max_radii_2d = torch.zeros((n,), dtype=torch.float32, device=device)
+
+    def as_tuple(self):
+        return (self.grad_accum, self.grad_count, self.max_radii_2d)
+
+    def accumulate_gradients(self, dL_dmeans_2d: torch.Tensor, radii: torch.Tensor) -> None:
+        n = dL_dmeans_2d.shape[0]
+        if self.grad_accum.shape[0] != n:  # lazy re-init (:66-68)
+            self.__init__(n, dL_dmeans_2d.device)
+        if n == 0:
+            return
+        dev = dL_dmeans_2d.device
+        lib, h = _lib_and_handle(dev)
+        st = lib.cugs_b200_accumulate_stats(h, _stream(dev), n, _ptr(dL_dmeans_2d.contiguous()),
+                                            _ptr(radii.contiguous()), _ptr(self.grad_accum),
+                                            _ptr(self.grad_count), _ptr(self.max_radii_2d))
+        _lib.check(h, st, "cugs_b200_accumulate_stats")

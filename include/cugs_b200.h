@@ -1,0 +1,213 @@
+/* cugs_b200.h — C ABI of the B200-native (sm_100a) Gaussian-splatting rasterizer hot path.
+ *
+ * Drop-in boundary for the rasterizer of Artemarius/cuda-gaussian-splatting. Every entry point
+ * below takes raw DEVICE pointers, sizes and an explicit cudaStream_t (passed as void* so that
+ * this header needs no CUDA include); nothing here allocates caller-visible memory, throws, or
+ * synchronises the device except where documented. Return value: 0 = success, < 0 = argument
+ * error (CUGS_ERR_*), > 0 = cudaError_t of the failing runtime call / launch. After a non-zero
+ * return cugs_b200_last_error(h) holds a message.
+ *
+ * Tensor layouts are the reference's (citations relative to /root/reference/src):
+ *   positions [N,3], rotations [N,4] wxyz un-normalised, scales [N,3] log-space,
+ *   opacities [N,1] logit-space, sh_coeffs [N,3,C] channel-major        (core/gaussian.hpp:24-40)
+ *   means_2d [N,2], depths [N], cov_2d_inv [N,3] (a,b,c), radii [N] i32, tiles_touched [N] i32,
+ *   rgb [N,3], opacities_act [N]                                  (rasterizer/projection.hpp:15-24)
+ *   keys [P] u64 = tile_id<<32 | float_bits(depth), values [P] i32, tile_ranges [T,2] i32
+ *                                                                    (rasterizer/sorting.hpp:19-24)
+ *   color [H,W,3], final_T [H,W], n_contrib [H,W] i32                (rasterizer/forward.hpp:11-15)
+ *   all f32 unless noted, contiguous, row-major, 16-byte aligned base pointers.
+ */
+#ifndef CUGS_B200_H_
+#define CUGS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUGS_B200_ABI_VERSION 1
+#define CUGS_TILE 16 /* rasterizer/sorting.hpp:16 kTileSize */
+
+enum {
+    CUGS_OK = 0,
+    CUGS_ERR_INVALID_ARG = -1,   /* null pointer, negative size, bad SH degree / coefficient count */
+    CUGS_ERR_WORKSPACE = -2,     /* workspace too small (see *_workspace_bytes) */
+    CUGS_ERR_CAPACITY = -3,      /* P exceeds the pair capacity the caller provided */
+    CUGS_ERR_UNSUPPORTED = -4,   /* e.g. P >= 2^30 (look-back counters are 30-bit) */
+    CUGS_ERR_NOT_BLACKWELL = -5  /* device is not sm_100 */
+};
+
+typedef struct cugs_handle cugs_handle_t;
+
+/* One camera view + render settings. Replaces CameraInfo (core/types.hpp:78-109: width, height,
+ * intrinsics, w2c rotation/translation) and RenderSettings (rasterizer/rasterizer.hpp:17-21).
+ * view is the ROW-MAJOR 4x4 world->camera matrix the reference launchers build
+ * (rasterizer/projection.cu:227-233); cam_center = -R^T t (core/types.hpp:98-100). */
+typedef struct cugs_view {
+    int32_t width, height;
+    float fx, fy, cx, cy;
+    float view[16];
+    float cam_center[3];
+    float bg[3];
+    int32_t active_sh_degree; /* 0..3, already min(settings, model) as rasterizer.cpp:60 */
+    int32_t num_coeffs;       /* C = allocated coefficients per channel, >= (deg+1)^2 */
+    float scale_modifier;
+} cugs_view_t;
+
+/* ---- handle ------------------------------------------------------------------------------ */
+int cugs_b200_create(int device, cugs_handle_t** out);
+void cugs_b200_destroy(cugs_handle_t* h);
+const char* cugs_b200_last_error(const cugs_handle_t* h);
+int cugs_b200_abi_version(void);
+int cugs_b200_sm_count(const cugs_handle_t* h);
+
+/* ---- stage 1: preprocess forward ---------------------------------------------------------
+ * Replaces project_gaussians (rasterizer/projection.cu:195-289): k_project_gaussians (:55-189),
+ * the libtorch view-direction ops (:273-280), evaluate_sh_cuda (core/sh.cu:81-123) and
+ * clamp_min(0) (:284), fused into one launch. Every output element is written (zeros where the
+ * reference leaves its torch::zeros untouched), so outputs may be uninitialised.
+ * packed (optional, may be NULL): [N,12] f32 private record {x,y,a,b | c,thr,op,r | g,b,0,0}
+ * consumed by the blend kernels. depth_minmax (optional): 2 x u32 device words, pre-set by the
+ * caller to {0xFFFFFFFF, 0}; receives min / max of float_bits(depth) over Gaussians with
+ * tiles_touched > 0 (used to trim the sort's key bits). */
+int cugs_b200_preprocess_fwd(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
+                             const float* positions, const float* rotations, const float* scales,
+                             const float* opacities, const float* sh_coeffs, float* means_2d,
+                             float* depths, float* cov_2d_inv, int32_t* radii,
+                             int32_t* tiles_touched, float* rgb, float* opacities_act,
+                             float* packed, uint32_t* depth_minmax);
+
+/* Stage functions evaluate_sh_cuda (core/sh.hpp:29) / evaluate_sh_backward_cuda
+ * (core/sh_backward.hpp:25): directions [N,3] are given explicitly; rgb is NOT clamped. */
+int cugs_b200_sh_forward(cugs_handle_t* h, void* stream, int64_t n, int degree, int num_coeffs,
+                         const float* sh_coeffs, const float* directions, float* rgb);
+int cugs_b200_sh_backward(cugs_handle_t* h, void* stream, int64_t n, int degree, int num_coeffs,
+                          const float* sh_coeffs, const float* directions, const float* dL_drgb,
+                          float* dL_dsh);
+
+/* ---- stage 2: device-wide scan + duplicateWithKeys ---------------------------------------
+ * Replaces cumsum/.item()/slice-copy (rasterizer/sorting.cu:145-152) and k_fill_sort_pairs
+ * (:30-72). scan: offsets = exclusive int32 prefix sum; the total P is written to *total_dev
+ * (device, int64, may be NULL) and, if total_host != NULL, copied to host with ONE stream
+ * synchronisation (the same blocking read the reference does at sorting.cu:146).
+ * scan_temp: cugs_b200_scan_temp_bytes(n) bytes of device scratch. */
+size_t cugs_b200_scan_temp_bytes(int64_t n);
+int cugs_b200_scan(cugs_handle_t* h, void* stream, int64_t n, const int32_t* tiles_touched,
+                   int32_t* offsets, int64_t* total_dev, int64_t* total_host, void* scan_temp,
+                   size_t scan_temp_bytes);
+/* keys/values [P]: every slot in [0,P) is written, including the zero key/value filler of the
+ * tile-count quirk (slots reserved by tiles_touched but not emitted). */
+int cugs_b200_duplicate_with_keys(cugs_handle_t* h, void* stream, int64_t n, int width, int height,
+                                  const float* means_2d, const float* depths, const int32_t* radii,
+                                  const int32_t* tiles_touched, const int32_t* offsets, int64_t p,
+                                  uint64_t* keys, int32_t* values);
+
+/* ---- stage 3: onesweep radix sort ---------------------------------------------------------
+ * Replaces cub::DeviceRadixSort::SortPairs (rasterizer/sorting.cu:190-211). Stable ascending
+ * LSD sort of (u64 key, u32 value) pairs over the key bits in [0,depth_bits) U [32,32+tile_bits)
+ * only (all other bits must be equal across keys, which holds for tile|depth keys when
+ * depth_bits covers the highest differing depth bit and tile_bits = ceil(log2(num_tiles))).
+ * depth_bits = 32, tile_bits = 32 sorts on all 64 bits like the reference call.
+ * keys_in/values_in are clobbered (used as the ping-pong buffer). Result in keys_out/values_out. */
+size_t cugs_b200_sort_temp_bytes(int64_t p);
+int cugs_b200_sort_pairs(cugs_handle_t* h, void* stream, int64_t p, int depth_bits, int tile_bits,
+                         uint64_t* keys_in, int32_t* values_in, uint64_t* keys_out,
+                         int32_t* values_out, void* temp, size_t temp_bytes);
+
+/* ---- stage 4: tile ranges (rasterizer/sorting.cu:82-109); zero-fills tile_ranges first ----- */
+int cugs_b200_tile_ranges(cugs_handle_t* h, void* stream, int64_t p, const uint64_t* keys_sorted,
+                          int num_tiles, int32_t* tile_ranges);
+
+/* ---- stage 5: blend forward (rasterize_forward, rasterizer/forward.cu:180-240, :48-174) ----
+ * packed may be NULL, in which case the records are gathered from the four public arrays. */
+int cugs_b200_blend_fwd(cugs_handle_t* h, void* stream, const cugs_view_t* v,
+                        const int32_t* tile_ranges, const int32_t* gaussian_idx,
+                        const float* means_2d, const float* cov_2d_inv, const float* rgb,
+                        const float* opacities_act, const float* packed, float* color,
+                        float* final_T, int32_t* n_contrib);
+
+/* ---- stage 6: backward --------------------------------------------------------------------
+ * blend_bwd replaces rasterize_backward (rasterizer/backward.cu:239-306, :31-233). The four
+ * outputs are zero-filled by this call and then accumulated (warp-reduced, one vector
+ * reduction per warp and Gaussian). grad_acc: [N,12] f32 scratch. */
+int cugs_b200_blend_bwd(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
+                        const int32_t* tile_ranges, const int32_t* gaussian_idx,
+                        const float* means_2d, const float* cov_2d_inv, const float* rgb,
+                        const float* opacities_act, const float* packed, const float* dL_dcolor,
+                        const float* final_T, const int32_t* n_contrib, float* dL_drgb,
+                        float* dL_dopacity_act, float* dL_dmeans_2d, float* dL_dcov_2d_inv,
+                        float* grad_acc);
+/* preprocess_bwd replaces project_backward (rasterizer/projection_backward.cu:253-344):
+ * k_project_backward (:26-247) + directions + evaluate_sh_backward_cuda (core/sh_backward.cu),
+ * one launch. rgb = forward output (its sign is the ReLU gate). All outputs fully written.
+ * stats (optional, all three or none): densification accumulators updated in place as
+ * DensificationController::accumulate_gradients does (optimizer/densification.cpp:59-88). */
+int cugs_b200_preprocess_bwd(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
+                             const float* positions, const float* rotations, const float* scales,
+                             const float* opacities, const float* sh_coeffs, const int32_t* radii,
+                             const float* rgb, const float* dL_dmeans_2d,
+                             const float* dL_dcov_2d_inv, const float* dL_drgb,
+                             const float* dL_dopacity_act, float* dL_dpositions,
+                             float* dL_drotations, float* dL_dscales, float* dL_dopacities,
+                             float* dL_dsh_coeffs, float* grad_accum, float* grad_count,
+                             float* max_radii);
+
+/* ---- fused entry points: cugs::render / cugs::render_backward ------------------------------
+ * render_plan = preprocess + scan, returns P on the host (one sync, as the reference).
+ * render_finish = duplicateWithKeys + sort + tile ranges + blend; gaussian_idx must hold P
+ * entries. workspace: cugs_b200_render_workspace_bytes(n, p_capacity) bytes; the SAME workspace
+ * must be passed to plan, finish and render_backward of one frame (it carries the packed
+ * records). render_backward = blend_bwd + preprocess_bwd (rasterizer/rasterizer.cpp:115-186). */
+size_t cugs_b200_render_workspace_bytes(int64_t n, int64_t p_capacity);
+int cugs_b200_render_plan(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
+                          const float* positions, const float* rotations, const float* scales,
+                          const float* opacities, const float* sh_coeffs, float* means_2d,
+                          float* depths, float* cov_2d_inv, int32_t* radii, float* rgb,
+                          float* opacities_act, void* workspace, size_t workspace_bytes,
+                          int64_t* p_host);
+int cugs_b200_render_finish(cugs_handle_t* h, void* stream, int64_t n, int64_t p,
+                            const cugs_view_t* v, const float* means_2d, const float* depths,
+                            const float* cov_2d_inv, const int32_t* radii, const float* rgb,
+                            const float* opacities_act, int32_t* gaussian_idx, int32_t* tile_ranges,
+                            float* color, float* final_T, int32_t* n_contrib, void* workspace,
+                            size_t workspace_bytes);
+int cugs_b200_render_backward(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
+                              const float* positions, const float* rotations, const float* scales,
+                              const float* opacities, const float* sh_coeffs,
+                              const float* means_2d, const float* cov_2d_inv, const int32_t* radii,
+                              const float* rgb, const float* opacities_act,
+                              const int32_t* gaussian_idx, const int32_t* tile_ranges,
+                              const float* final_T, const int32_t* n_contrib,
+                              const float* dL_dcolor, float* dL_dpositions, float* dL_drotations,
+                              float* dL_dscales, float* dL_dopacities, float* dL_dsh_coeffs,
+                              float* dL_dmeans_2d, float* grad_accum, float* grad_count,
+                              float* max_radii, void* workspace, size_t workspace_bytes);
+
+/* ---- stage 7: fused L1 + SSIM loss and fused multi-tensor Adam ------------------------------
+ * loss: combined_loss (training/loss.cpp:131-135) value AND its gradient w.r.t. rendered (the
+ * reference gets the gradient from libtorch autograd, training/trainer.cpp:214-217).
+ * scalars3 (device) = {loss, l1, mean ssim}. workspace: cugs_b200_loss_workspace_bytes(w,h). */
+size_t cugs_b200_loss_workspace_bytes(int width, int height);
+int cugs_b200_loss_l1_ssim(cugs_handle_t* h, void* stream, int width, int height, float lambda,
+                           const float* rendered, const float* target, float* dL_dcolor,
+                           float* scalars3, void* workspace, size_t workspace_bytes);
+/* Adam: FusedAdam::step (optimizer/fused_adam.cu:140-164) + k_fused_adam (:44-76) for all five
+ * groups in ONE launch. Group order positions, sh_coeffs, opacities, scales, rotations
+ * (fused_adam.cu:94-97); counts[g] = number of floats. bc1/bc2 are computed by the caller in
+ * double exactly as fused_adam.cu:145-149. grad_scale multiplies every gradient first
+ * (1.0 = reference behaviour; 1/views for view-batched training). */
+int cugs_b200_adam_step(cugs_handle_t* h, void* stream, float* const params[5],
+                        const float* const grads[5], float* const m[5], float* const v[5],
+                        const int64_t counts[5], const float lr[5], float beta1, float beta2,
+                        float eps, float bc1, float bc2, float grad_scale);
+/* DensificationController::accumulate_gradients (optimizer/densification.cpp:59-88). */
+int cugs_b200_accumulate_stats(cugs_handle_t* h, void* stream, int64_t n,
+                               const float* dL_dmeans_2d, const int32_t* radii, float* grad_accum,
+                               float* grad_count, float* max_radii);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUGS_B200_H_ */

@@ -1,0 +1,192 @@
+// oracle/ref_harness.cpp — TEST INFRASTRUCTURE (not product code).
+//
+// A thin pybind11 module around the UNMODIFIED reference hot path, compiled from the sources
+// where they lie under /root/reference (see oracle/Makefile.ref; nothing is copied into this
+// repo). It exists for two reasons only:
+//   1. bit oracle: radii / tiles_touched / tile keys / sort order / tile ranges of the
+//      reference's own CUDA kernels, run on the same B200 as the new kernels;
+//   2. `bench.py --impl reference`: the reference's own render()/render_backward() timed
+//      through its public API (rasterizer.hpp:57-60, :88-93).
+// The product (cuda_gaussian_splatting_b200/) never imports this module.
+//
+// Camera is passed as 18 floats: W, H, fx, fy, cx, cy, R(row-major 3x3 world->camera), t(3).
+
+#include <torch/extension.h>
+
+#include <vector>
+
+#include "core/gaussian.hpp"
+#include "core/sh.hpp"
+#include "core/sh_backward.hpp"
+#include "core/types.hpp"
+#include "optimizer/fused_adam.hpp"
+#include "rasterizer/backward.hpp"
+#include "rasterizer/forward.hpp"
+#include "rasterizer/projection.hpp"
+#include "rasterizer/projection_backward.hpp"
+#include "rasterizer/rasterizer.hpp"
+#include "rasterizer/sorting.hpp"
+#include "training/loss.hpp"
+
+namespace {
+
+using T = torch::Tensor;
+
+cugs::CameraInfo make_camera(const std::vector<double>& c) {
+    TORCH_CHECK(c.size() == 18, "camera must be 18 numbers");
+    cugs::CameraInfo cam;
+    cam.width = static_cast<int>(c[0]);
+    cam.height = static_cast<int>(c[1]);
+    cam.intrinsics.fx = static_cast<float>(c[2]);
+    cam.intrinsics.fy = static_cast<float>(c[3]);
+    cam.intrinsics.cx = static_cast<float>(c[4]);
+    cam.intrinsics.cy = static_cast<float>(c[5]);
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k) cam.rotation(r, k) = static_cast<float>(c[6 + r * 3 + k]);
+    for (int r = 0; r < 3; ++r) cam.translation(r) = static_cast<float>(c[15 + r]);
+    return cam;
+}
+
+cugs::GaussianModel make_model(const T& pos, const T& sh, const T& opa, const T& rot, const T& scl) {
+    cugs::GaussianModel m;
+    m.positions = pos;
+    m.sh_coeffs = sh;
+    m.opacities = opa;
+    m.rotations = rot;
+    m.scales = scl;
+    return m;
+}
+
+cugs::RenderSettings make_settings(const std::vector<double>& bg, int deg, double scale_mod) {
+    cugs::RenderSettings s;
+    s.background[0] = static_cast<float>(bg[0]);
+    s.background[1] = static_cast<float>(bg[1]);
+    s.background[2] = static_cast<float>(bg[2]);
+    s.active_sh_degree = deg;
+    s.scale_modifier = static_cast<float>(scale_mod);
+    return s;
+}
+
+std::vector<T> pack(const cugs::RenderOutput& o) {
+    return {o.color, o.final_T, o.n_contrib, o.means_2d, o.depths, o.cov_2d_inv,
+            o.radii, o.rgb, o.opacities_act, o.gaussian_indices, o.tile_ranges};
+}
+
+cugs::RenderOutput unpack(const std::vector<T>& v) {
+    TORCH_CHECK(v.size() == 11, "render output must be 11 tensors");
+    return cugs::RenderOutput{v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10]};
+}
+
+std::vector<T> ref_project(const T& pos, const T& rot, const T& scl, const T& opa, const T& sh,
+                           const std::vector<double>& cam, int deg, double scale_mod) {
+    auto o = cugs::project_gaussians(pos, rot, scl, opa, sh, make_camera(cam), deg,
+                                     static_cast<float>(scale_mod));
+    return {o.means_2d, o.depths, o.cov_2d_inv, o.radii, o.tiles_touched, o.rgb, o.opacities_act};
+}
+
+std::vector<T> ref_sort(const T& means_2d, const T& depths, const T& radii, const T& tiles,
+                        int w, int h) {
+    auto o = cugs::sort_gaussians(means_2d, depths, radii, tiles, w, h);
+    auto p = torch::tensor({static_cast<int64_t>(o.total_pairs)}, torch::kInt64);
+    return {o.gaussian_keys_sorted, o.gaussian_values_sorted, o.tile_ranges, p};
+}
+
+std::vector<T> ref_rasterize_forward(const T& means_2d, const T& cov, const T& rgb, const T& opa,
+                                     const T& ranges, const T& idx, int w, int h,
+                                     const std::vector<double>& bg) {
+    float b[3] = {(float)bg[0], (float)bg[1], (float)bg[2]};
+    auto o = cugs::rasterize_forward(means_2d, cov, rgb, opa, ranges, idx, w, h, b);
+    return {o.color, o.final_T, o.n_contrib};
+}
+
+std::vector<T> ref_rasterize_backward(const T& dL_dcolor, const T& means_2d, const T& cov,
+                                      const T& rgb, const T& opa, const T& ranges, const T& idx,
+                                      const T& final_T, const T& n_contrib, int w, int h,
+                                      const std::vector<double>& bg, int n) {
+    float b[3] = {(float)bg[0], (float)bg[1], (float)bg[2]};
+    auto o = cugs::rasterize_backward(dL_dcolor, means_2d, cov, rgb, opa, ranges, idx, final_T,
+                                      n_contrib, w, h, b, n);
+    return {o.dL_drgb, o.dL_dopacity_act, o.dL_dmeans_2d, o.dL_dcov_2d_inv};
+}
+
+std::vector<T> ref_project_backward(const T& d_m2d, const T& d_cov, const T& d_rgb, const T& d_opa,
+                                    const T& pos, const T& rot, const T& scl, const T& opa,
+                                    const T& sh, const T& radii, const std::vector<double>& cam,
+                                    int deg, double scale_mod) {
+    auto o = cugs::project_backward(d_m2d, d_cov, d_rgb, d_opa, pos, rot, scl, opa, sh, radii,
+                                    make_camera(cam), deg, static_cast<float>(scale_mod));
+    return {o.dL_dpositions, o.dL_drotations, o.dL_dscales, o.dL_dopacities, o.dL_dsh_coeffs};
+}
+
+std::vector<T> ref_render(const T& pos, const T& sh, const T& opa, const T& rot, const T& scl,
+                          const std::vector<double>& cam, const std::vector<double>& bg, int deg,
+                          double scale_mod) {
+    return pack(cugs::render(make_model(pos, sh, opa, rot, scl), make_camera(cam),
+                             make_settings(bg, deg, scale_mod)));
+}
+
+std::vector<T> ref_render_backward(const T& dL_dcolor, const std::vector<T>& render_out,
+                                   const T& pos, const T& sh, const T& opa, const T& rot,
+                                   const T& scl, const std::vector<double>& cam,
+                                   const std::vector<double>& bg, int deg, double scale_mod) {
+    auto o = cugs::render_backward(dL_dcolor, unpack(render_out), make_model(pos, sh, opa, rot, scl),
+                                   make_camera(cam), make_settings(bg, deg, scale_mod));
+    return {o.dL_dpositions, o.dL_drotations, o.dL_dscales, o.dL_dopacities, o.dL_dsh_coeffs,
+            o.dL_dmeans_2d};
+}
+
+// loss value + autograd gradient, exactly as the trainer wires it (trainer.cpp:214-217).
+std::vector<T> ref_combined_loss_with_grad(const T& rendered, const T& target, double lambda) {
+    auto r = rendered.clone().detach().requires_grad_(true);
+    auto loss = cugs::combined_loss(r, target, static_cast<float>(lambda));
+    loss.backward();
+    auto l1 = cugs::l1_loss(rendered, target);
+    auto s = cugs::ssim(rendered, target).mean();
+    return {loss.detach(), l1, s, r.grad().clone()};
+}
+
+struct RefAdam {
+    cugs::GaussianModel model;
+    std::unique_ptr<cugs::FusedAdam> opt;
+    RefAdam(const T& pos, const T& sh, const T& opa, const T& rot, const T& scl)
+        : model(make_model(pos, sh, opa, rot, scl)) {
+        opt = std::make_unique<cugs::FusedAdam>(model, cugs::AdamConfig{});
+    }
+    // grads in BackwardOutput order: positions, rotations, scales, opacities, sh
+    void step(const std::vector<T>& g, int step_idx) {
+        torch::NoGradGuard ng;
+        cugs::BackwardOutput b{g[0], g[1], g[2], g[3], g[4], T()};
+        opt->update_lr(step_idx);
+        opt->zero_grad();
+        opt->apply_gradients(b);
+        opt->step();
+    }
+    std::vector<T> params() const {
+        return {model.positions, model.sh_coeffs, model.opacities, model.rotations, model.scales};
+    }
+};
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.doc() = "unmodified reference hot path (test oracle + reference bench arm)";
+    m.def("project_gaussians", &ref_project);
+    m.def("sort_gaussians", &ref_sort);
+    m.def("rasterize_forward", &ref_rasterize_forward);
+    m.def("rasterize_backward", &ref_rasterize_backward);
+    m.def("project_backward", &ref_project_backward);
+    m.def("render", &ref_render);
+    m.def("render_backward", &ref_render_backward);
+    m.def("combined_loss_with_grad", &ref_combined_loss_with_grad);
+    m.def("evaluate_sh_cuda", &cugs::evaluate_sh_cuda);
+    m.def("evaluate_sh_cpu", &cugs::evaluate_sh_cpu);
+    m.def("evaluate_sh_backward_cuda", &cugs::evaluate_sh_backward_cuda);
+    m.def("l1_loss", &cugs::l1_loss);
+    m.def("ssim", &cugs::ssim, py::arg("rendered"), py::arg("target"), py::arg("window_size") = 11);
+    m.def("combined_loss", &cugs::combined_loss, py::arg("rendered"), py::arg("target"),
+          py::arg("lambda_") = 0.2f);
+    py::class_<RefAdam>(m, "FusedAdam")
+        .def(py::init<const T&, const T&, const T&, const T&, const T&>())
+        .def("step", &RefAdam::step)
+        .def("params", &RefAdam::params);
+}
