@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native rasterizer hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload B]
+
+Metric (BASELINE.json): forward+backward throughput of the differentiable rasterizer at 3 M
+synthetic Gaussians / SH degree 3 / 1920x1080 (workload "B" = BASELINE.json configs[1]), as
+views/s (whole job) with ms/view beside it, plus the sort's GB/s.
+
+One "step" = `--views-per-gpu` views (default 1) rendered forward + backward on every GPU,
+parameter gradients summed in place; with N > 1 GPUs the step ends with ONE NCCL all-reduce(sum)
+of the gradient arena (59 N floats + 2 N densification statistics), as BASELINE.json config[3].
+Per-GPU work is fixed as N grows ("scaling": "weak").
+
+  value     : device-timed (CUDA events, max over ranks); everything resident in HBM.
+  e2e       : the same step through the public API with HOST per-view inputs: every view the
+              target image is copied host->device from pinned memory, the fused L1+SSIM loss
+              produces dL/dcolor, and the three loss scalars are read back device->host.
+              Gaussian parameters are model state (as in the reference's Trainer, which uploads
+              them once: training/trainer.cpp:83) and stay resident.
+  roofline  : the dominant kernel of the step, per-stage CUDA events recorded by the library on
+              the launching stream (cugs_b200_set_stage_timing) over a second pass of K steps.
+  cpu_baseline : the CPU oracle port (oracle/cugs_oracle.c, OpenMP, all host cores) on ONE full
+              view of the same workload (rank 0, N = 1 only).
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/cugs_ref*.so = its own CUDA
+kernels compiled for sm_100 from /root/reference by oracle/Makefile.ref) through its public
+render()/render_backward() API on the same scene; if that module cannot be loaded it falls back
+to the CPU oracle port. Nothing here reads /root/reference at run time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (N, W, H, seed, description)
+    "A": (100_000, 1280, 720, 1235, "A: 100k Gaussians SH3 1280x720 fwd+bwd"),
+    "B": (3_000_000, 1920, 1080, 1236, "B: 3M Gaussians SH3 1920x1080 fwd+bwd"),
+    "C": (1_000_000, 1920, 1080, 1237, "C: 1M Gaussians SH3 1920x1080 fwd+bwd"),
+    "E": (20_000_000, 3840, 2160, 1239, "E: 20M Gaussians SH3 3840x2160 fwd+bwd"),
+}
+METRIC = "fwd+bwd views/s at 3M Gaussians 1080p"
+STAGES = ["preprocess_fwd", "scan", "duplicate_with_keys", "sort", "tile_ranges", "blend_fwd", "blend_bwd",
+          "preprocess_bwd"]
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Polls nvidia-smi during the timed region (profiling recipe's clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks() -> tuple:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def sort_passes(P_bits_depth: int, num_tiles: int) -> int:
+    import math
+    tb = max(0, math.ceil(math.log2(num_tiles))) if num_tiles > 1 else 0
+    return max(1, (P_bits_depth + tb + 7) // 8)
+
+
+def algorithmic_bytes(n: int, p: int, w: int, h: int, passes: int) -> dict:
+    """ALGORITHMIC bytes per launch of each stage (SURVEY.md §8d / DESIGN.md): each distinct
+    input read once + each output written once."""
+    tiles = ((w + 15) // 16) * ((h + 15) // 16)
+    return {
+        "preprocess_fwd": 284 * n,
+        "scan": 8 * n,
+        "duplicate_with_keys": 20 * n + 12 * p,
+        "sort": (8 + 24 * passes) * p,
+        "tile_ranges": 8 * p + 8 * tiles,
+        "blend_fwd": 40 * p + 20 * w * h,
+        "blend_bwd": 40 * p + 32 * w * h + 36 * n,
+        "preprocess_bwd": 336 * n,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def bench_views(scene, count: int):
+    """View 0 = the scene's camera 0 (BASELINE config B's camera); further views = small jitters
+    around it (ring of 2 % of the median depth), so every view carries the same work."""
+    import cuda_gaussian_splatting_b200 as cugs
+    cams = [scene.camera]
+    if count > 1:
+        cams += cugs.ring_cameras(scene, count - 1, radius_frac=0.02)
+    return cams
+
+
+def run_b200(args) -> dict:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import cuda_gaussian_splatting_b200 as cugs
+    from cuda_gaussian_splatting_b200 import _lib
+
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a B200 (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, W, H, seed, desc = WORKLOADS[args.workload]
+    V = args.views_per_gpu
+    scene = cugs.synth(n, W, H, seed=seed)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    model = cugs.GaussianModel(t(scene.positions), t(scene.sh_coeffs), t(scene.opacities), t(scene.rotations),
+                               t(scene.scales))
+    cams = bench_views(scene, world * V)[rank * V:(rank + 1) * V]
+    settings = cugs.RenderSettings((0.0, 0.0, 0.0), 3, 1.0)
+    buf = cugs.FrameBuffers(n, W, H, 16, dev)
+    lib, h = _lib.load_library(), _lib.handle(local)
+
+    # synthetic targets (host, pinned) and the resident dL/dcolor of each view
+    rng = np.random.default_rng(4321 + rank)
+    targets_host = [torch.from_numpy(rng.uniform(size=(H, W, 3)).astype(np.float32)).pin_memory() for _ in range(V)]
+    target_dev = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    scal_host = torch.empty((3,), dtype=torch.float32).pin_memory()
+    dLs, Ps = [], []
+    for v in range(V):
+        out = cugs.render(model, cams[v], settings, buf)
+        Ps.append(int(out.gaussian_indices.numel()))
+        target_dev.copy_(targets_host[v], non_blocking=True)
+        _, g = cugs.combined_loss_with_grad(out.color, target_dev, 0.2)
+        dLs.append(g)
+    torch.cuda.synchronize()
+
+    def allreduce():
+        if world > 1:
+            dist.all_reduce(buf.grad_arena, op=dist.ReduceOp.SUM)
+
+    def step_resident():
+        for v in range(V):
+            out = cugs.render(model, cams[v], settings, buf)
+            cugs.render_backward(dLs[v], out, model, cams[v], settings, buf, accumulate=(v > 0))
+        allreduce()
+
+    def step_e2e():
+        for v in range(V):
+            target_dev.copy_(targets_host[v], non_blocking=True)              # H2D, pinned
+            out = cugs.render(model, cams[v], settings, buf)
+            sc, g = cugs.combined_loss_with_grad(out.color, target_dev, 0.2)
+            cugs.render_backward(g, out, model, cams[v], settings, buf, accumulate=(v > 0))
+            scal_host.copy_(sc, non_blocking=True)                            # D2H of {loss, l1, ssim}
+        allreduce()
+        torch.cuda.current_stream().synchronize()                             # the loss is on the host now
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = int(lib.cugs_b200_launch_count(h))
+    total_ms = timed(step_resident, args.steps)
+    launches = int(lib.cugs_b200_launch_count(h)) - l0
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # second pass: per-stage device timing (events recorded by the library on the launching stream)
+    import ctypes as C
+    stage_sum = [0.0] * len(STAGES)
+    stage_cnt = 0
+    lib.cugs_b200_set_stage_timing(h, 1)
+    ms8 = (C.c_float * 8)()
+    for _ in range(args.steps):
+        for v in range(V):
+            out = cugs.render(model, cams[v], settings, buf)
+            cugs.render_backward(dLs[v], out, model, cams[v], settings, buf, accumulate=(v > 0))
+            lib.cugs_b200_get_stage_ms(h, ms8)
+            for k in range(8):
+                stage_sum[k] += max(float(ms8[k]), 0.0)
+            stage_cnt += 1
+    lib.cugs_b200_set_stage_timing(h, 0)
+    stages_ms = {nm: stage_sum[k] / max(stage_cnt, 1) for k, nm in enumerate(STAGES)}
+
+    for _ in range(3):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+
+    views = world * V * args.steps
+    value = views / (total_ms * 1e-3)
+    e2e_value = views / (e2e_ms * 1e-3)
+
+    res = None
+    if rank == 0:
+        P = Ps[0]
+        c_passes, c_bits = C.c_int(0), C.c_int(0)
+        lib.cugs_b200_last_sort_plan(h, C.byref(c_passes), C.byref(c_bits))
+        passes, key_bits = int(c_passes.value), int(c_bits.value)
+        alg = algorithmic_bytes(n, P, W, H, passes)
+        peak, peak_src = measured_peaks()
+        hbm_stages = ["preprocess_fwd", "scan", "duplicate_with_keys", "sort", "tile_ranges", "preprocess_bwd"]
+        rl_all = {}
+        for nm in STAGES:
+            ms = stages_ms[nm]
+            gbs = alg[nm] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            rl_all[nm] = {"ms": round(ms, 4), "algorithmic_bytes": alg[nm], "achieved_gbs": round(gbs, 1),
+                          "frac_of_hbm_peak": round(gbs / peak, 4),
+                          "bound": "hbm" if nm in hbm_stages else "fp32-issue/L2-atomics (not HBM)"}
+        dom = max(hbm_stages, key=lambda k: stages_ms[k])
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": rl_all[dom]["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": rl_all[dom]["frac_of_hbm_peak"], "traffic": TRAFFIC.get(dom),
+                    "peak_source": peak_src, "ms": rl_all[dom]["ms"]}
+        res = {
+            "metric": METRIC, "value": round(value, 3), "unit": "views/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4),
+            "ms_per_view": round(total_ms / args.steps / V, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "views_per_gpu_per_step": V, "P_pairs_view0": P, "sort_passes": passes,
+                       "sort_key_bits": key_bits,
+                       "collective": "none" if world == 1 else "one NCCL all-reduce(sum) of 61N floats per step",
+                       "l2": "no flush needed: per-step inputs (708 MB of Gaussian parameters at 3M) exceed the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "ms_per_view": round(e2e_ms / args.steps / V, 4),
+                    "h2d_bytes_per_step": V * H * W * 3 * 4, "d2h_bytes_per_step": V * 12,
+                    "what": "per view: H2D target (pinned) -> render -> fused L1+SSIM loss+grad -> render_backward -> D2H loss"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "stages_ms": {k: round(v_, 4) for k, v_ in stages_ms.items()},
+            "stages_sum_ms": round(sum(stages_ms.values()), 4),
+            "roofline_all": rl_all,
+            "sort_gbs": rl_all["sort"]["achieved_gbs"],
+            "sort_mpairs_per_s": round(P / (stages_ms["sort"] * 1e-3) / 1e6, 1) if stages_ms["sort"] > 0 else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res["cpu_baseline"] = cpu_baseline(scene, args.workload)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return res
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+# captures (profiles/), filled in per round; None = not captured yet.
+TRAFFIC = {}
+try:
+    TRAFFIC = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+except Exception:
+    TRAFFIC = {}
+
+
+def cpu_baseline(scene, workload: str, views: int = 1) -> dict:
+    """The CPU oracle port (same math, OpenMP over all host cores) on `views` full views."""
+    import numpy as np
+    from oracle import oracle_py  # checker / baseline only
+    H, W = scene.camera.height, scene.camera.width
+    g = np.random.default_rng(1).uniform(-1, 1, size=(H, W, 3)).astype(np.float32)
+    t0 = time.perf_counter()
+    for _ in range(views):
+        fwd = oracle_py.render_forward(scene, deg=3)
+        oracle_py.render_backward(scene, fwd, g, deg=3)
+    dt = time.perf_counter() - t0
+    return {"value": round(views / dt, 5), "unit": "views/s", "ms_per_view": round(dt / views * 1e3, 1),
+            "cores": oracle_py.num_threads(), "kind": "port",
+            "sample": f"{views} full view(s) of workload {workload} fwd+bwd (oracle/cugs_oracle.c, OpenMP)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args) -> dict:
+    rank, world, local = dist_env()
+    if rank != 0:
+        return None
+    import numpy as np
+    import torch
+
+    import cuda_gaussian_splatting_b200 as cugs  # synth() only: the scene generator, no kernels
+    n, W, H, seed, desc = WORKLOADS[args.workload]
+    scene = cugs.synth(n, W, H, seed=seed)
+    base = {"impl": "reference", "metric": METRIC, "unit": "views/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "views_per_gpu_per_step": 1}}
+    ref = None
+    why = ""
+    try:
+        sys.path.insert(0, str(ROOT / "oracle" / "_ref"))
+        import cugs_ref as ref  # the unmodified reference, compiled from /root/reference for sm_100
+        assert torch.cuda.is_available()
+    except Exception as e:  # noqa: BLE001
+        ref, why = None, f"{type(e).__name__}: {e}"
+    if ref is None:
+        cb = cpu_baseline(scene, args.workload, views=max(1, min(args.steps, 2)))
+        cb["sample"] += f"; compiled reference unavailable ({why})"
+        base.update({"value": cb["value"], "ms_per_step": cb["ms_per_view"], "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return base
+
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pos, sh, opa, rot, scl = t(scene.positions), t(scene.sh_coeffs), t(scene.opacities), t(scene.rotations), t(scene.scales)
+    cam, bg = scene.camera.as_ref_list(), [0.0, 0.0, 0.0]
+    target_host = torch.from_numpy(np.random.default_rng(4321).uniform(size=(H, W, 3)).astype(np.float32)).pin_memory()
+    target = target_host.to(dev)
+    out = ref.render(pos, sh, opa, rot, scl, cam, bg, 3, 1.0)
+    _, _, _, dL = ref.combined_loss_with_grad(out[0], target, 0.2)
+
+    def step_resident():
+        o = ref.render(pos, sh, opa, rot, scl, cam, bg, 3, 1.0)
+        ref.render_backward(dL, o, pos, sh, opa, rot, scl, cam, bg, 3, 1.0)
+
+    def step_e2e():
+        tg = target_host.to(dev, non_blocking=True)
+        o = ref.render(pos, sh, opa, rot, scl, cam, bg, 3, 1.0)
+        loss, _, _, g = ref.combined_loss_with_grad(o[0], tg, 0.2)   # trainer.cpp:214-225
+        ref.render_backward(g, o, pos, sh, opa, rot, scl, cam, bg, 3, 1.0)
+        loss.item()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop()
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+    value = args.steps / (ms * 1e-3)
+    base.update({
+        "value": round(value, 3), "ms_per_step": round(ms / args.steps, 4), "ms_per_view": round(ms / args.steps, 4),
+        "clocks": clocks,
+        "cpu_baseline": {"value": round(value, 3), "unit": "views/s", "cores": 0, "kind": "reference",
+                         "sample": "the unmodified reference's own CUDA render()+render_backward() (oracle/_ref, built "
+                                   "for sm_100), full workload, run on the GPU: the reference has no CPU rasterizer"},
+        "e2e": {"value": round(args.steps / (e2e_ms * 1e-3), 3), "unit": "views/s",
+                "ms_per_view": round(e2e_ms / args.steps, 4),
+                "h2d_bytes_per_step": H * W * 3 * 4, "d2h_bytes_per_step": 4,
+                "what": "H2D target (pinned) -> ref render -> ref combined_loss + autograd -> ref render_backward -> loss.item()"},
+        "P_pairs": int(out[9].numel()),
+    })
+    return base
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
+    ap.add_argument("--views-per-gpu", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    res = run_reference(args) if args.impl == "reference" else run_b200(args)
+    if res is not None:
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,7 @@ SIGNATURES = {
     "cugs_b200_last_error": (C.c_char_p, [_P]),
     "cugs_b200_abi_version": (_INT, []),
     "cugs_b200_sm_count": (_INT, [_P]),
+    "cugs_b200_launch_count": (C.c_uint64, [_P]),
     "cugs_b200_preprocess_fwd": (_INT, [_P, _P, _I64, _VP] + [_P] * 14),
     "cugs_b200_sh_forward": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P]),
     "cugs_b200_sh_backward": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P, _P]),
@@ -61,7 +62,10 @@ SIGNATURES = {
     "cugs_b200_render_workspace_bytes": (_SZ, [_I64, _I64]),
     "cugs_b200_render_plan": (_INT, [_P, _P, _I64, _VP] + [_P] * 11 + [_P, _SZ, C.POINTER(_I64)]),
     "cugs_b200_render_finish": (_INT, [_P, _P, _I64, _I64, _VP] + [_P] * 11 + [_P, _SZ]),
-    "cugs_b200_render_backward": (_INT, [_P, _P, _I64, _VP] + [_P] * 24 + [_P, _SZ]),
+    "cugs_b200_render_backward": (_INT, [_P, _P, _I64, _VP] + [_P] * 24 + [_INT, _P, _SZ]),
+    "cugs_b200_last_sort_plan": (_INT, [_P, C.POINTER(_INT), C.POINTER(_INT)]),
+    "cugs_b200_set_stage_timing": (_INT, [_P, _INT]),
+    "cugs_b200_get_stage_ms": (_INT, [_P, C.POINTER(_F)]),
     "cugs_b200_loss_workspace_bytes": (_SZ, [_INT, _INT]),
     "cugs_b200_loss_l1_ssim": (_INT, [_P, _P, _INT, _INT, _F, _P, _P, _P, _P, _P, _SZ]),
     "cugs_b200_adam_step": (_INT, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),

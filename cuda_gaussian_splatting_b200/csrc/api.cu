@@ -25,7 +25,8 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
                                const float* dL_drgb, const float* dL_dopacity_act, float* dL_dpositions,
                                float* dL_drotations, float* dL_dscales, float* dL_dopacities,
                                float* dL_dsh_coeffs, float* grad_accum, float* grad_count,
-                               float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out);
+                               float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out,
+                               bool accumulate);
 extern "C" int cugs_b200_sort_num_passes(int depth_bits, int tile_bits);
 extern "C" int cugs_b200_sort_pairs_pingpong(cugs_handle_t* h, void* stream, int64_t p, int depth_bits,
                                              int tile_bits, uint64_t* keys_a, int32_t* vals_a,
@@ -54,6 +55,11 @@ extern "C" int cugs_b200_create(int device, cugs_handle_t** out) {
     e = cudaHostAlloc(reinterpret_cast<void**>(&h->pinned), 64, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete h; return (int)e; }
     std::memset(h->pinned, 0, 64);
+    h->timing = false;
+    h->launches = 0;
+    h->last_sort_passes = 0;
+    h->last_sort_key_bits = 0;
+    for (int i = 0; i < 12; ++i) { h->ev[i] = nullptr; h->ev_recorded[i] = false; }
     *out = h;
     return CUGS_OK;
 }
@@ -61,11 +67,58 @@ extern "C" int cugs_b200_create(int device, cugs_handle_t** out) {
 extern "C" void cugs_b200_destroy(cugs_handle_t* h) {
     if (!h) return;
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (int i = 0; i < 12; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// optional stage timing (events on the caller's stream at the stage boundaries)
+// ------------------------------------------------------------------------------------------------
+extern "C" int cugs_b200_set_stage_timing(cugs_handle_t* h, int enable) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    if (enable) {
+        for (int i = 0; i < 12; ++i)
+            if (!h->ev[i]) CUGS_CUDA_TRY(h, cudaEventCreate(&h->ev[i]));
+    }
+    for (int i = 0; i < 12; ++i) h->ev_recorded[i] = false;
+    h->timing = enable != 0;
+    return CUGS_OK;
+}
+
+static inline void mark(cugs_handle_t* h, int i, cudaStream_t s) {
+    if (h->timing) {
+        cudaEventRecord(h->ev[i], s);
+        h->ev_recorded[i] = true;
+    }
+}
+
+extern "C" int cugs_b200_last_sort_plan(const cugs_handle_t* h, int* passes, int* key_bits) {
+    if (!h) return CUGS_ERR_INVALID_ARG;
+    if (passes) *passes = h->last_sort_passes;
+    if (key_bits) *key_bits = h->last_sort_key_bits;
+    return CUGS_OK;
+}
+
+extern "C" int cugs_b200_get_stage_ms(cugs_handle_t* h, float* ms8) {
+    CUGS_REQUIRE(h, h != nullptr && ms8 != nullptr, "null pointer");
+    // {first event, last event} of each stage; events 0-2 plan, 3-7 finish, 8-10 backward
+    static const int span[CUGS_NUM_STAGES][2] = {{0, 1}, {1, 2}, {3, 4}, {4, 5}, {5, 6}, {6, 7}, {8, 9}, {9, 10}};
+    for (int k = 0; k < CUGS_NUM_STAGES; ++k) {
+        ms8[k] = -1.0f;
+        const int a = span[k][0], b = span[k][1];
+        if (!h->timing || !h->ev_recorded[a] || !h->ev_recorded[b]) continue;
+        CUGS_CUDA_TRY(h, cudaEventSynchronize(h->ev[b]));
+        float ms = 0.0f;
+        CUGS_CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]));
+        ms8[k] = ms;
+    }
+    return CUGS_OK;
 }
 
 extern "C" const char* cugs_b200_last_error(const cugs_handle_t* h) { return h ? h->err : "null handle"; }
 extern "C" int cugs_b200_sm_count(const cugs_handle_t* h) { return h ? h->sm_count : 0; }
+extern "C" uint64_t cugs_b200_launch_count(const cugs_handle_t* h) { return h ? h->launches : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // workspace layout of one frame
@@ -152,13 +205,16 @@ extern "C" int cugs_b200_render_plan(cugs_handle_t* h, void* stream, int64_t n, 
     const FrameWorkspace w = carve(workspace, n, 0);
     CUGS_CUDA_TRY(h, cudaMemsetAsync(w.depth_minmax, 0xff, 4, s));
     CUGS_CUDA_TRY(h, cudaMemsetAsync(w.depth_minmax + 1, 0, 4, s));
+    mark(h, 0, s);
     if (int e = cugs_b200_preprocess_fwd(h, stream, n, v, positions, rotations, scales, opacities, sh_coeffs,
                                          means_2d, depths, cov_2d_inv, radii, w.tiles_touched, rgb,
                                          opacities_act, w.packed, w.depth_minmax))
         return e;
+    mark(h, 1, s);
     if (int e = cugs_scan_launch(h, s, n, w.tiles_touched, w.offsets, w.total_dev, true, w.scan_temp,
                                  w.depth_minmax))
         return e;
+    mark(h, 2, s);
     CUGS_CUDA_TRY(h, cudaStreamSynchronize(s));  // the one blocking read (reference: sorting.cu:146)
     *p_host = h->pinned[0];
     return CUGS_OK;
@@ -187,6 +243,7 @@ extern "C" int cugs_b200_render_finish(cugs_handle_t* h, void* stream, int64_t n
                              cugs_b200_render_workspace_bytes(n, p));
         w = carve(workspace, n, p);
     }
+    mark(h, 3, s);
     if (p > 0) {
         // key bits that can differ: tile bits + depth bits below the highest differing one
         const uint64_t mm = (uint64_t)h->pinned[1];
@@ -198,6 +255,8 @@ extern "C" int cugs_b200_render_finish(cugs_handle_t* h, void* stream, int64_t n
         }
         const int tile_bits = ceil_log2(num_tiles);
         const int passes = cugs_b200_sort_num_passes(depth_bits, tile_bits);
+        h->last_sort_passes = passes;
+        h->last_sort_key_bits = depth_bits + tile_bits;
         // choose where the unsorted pairs go so that the sorted VALUES land in gaussian_idx
         uint64_t* ka; int32_t* va; uint64_t* kb; int32_t* vb;
         if (passes & 1) { ka = w.keys_y; va = w.vals_y; kb = w.keys_x; vb = gaussian_idx; }
@@ -205,17 +264,23 @@ extern "C" int cugs_b200_render_finish(cugs_handle_t* h, void* stream, int64_t n
         if (int e = cugs_b200_duplicate_with_keys(h, stream, n, v->width, v->height, means_2d, depths, radii,
                                                   w.tiles_touched, w.offsets, p, ka, va))
             return e;
+        mark(h, 4, s);
         int in_b = 0;
         if (int e = cugs_b200_sort_pairs_pingpong(h, stream, p, depth_bits, tile_bits, ka, va, kb, vb,
                                                   w.sort_temp, w.sort_temp_bytes, &in_b))
             return e;
+        mark(h, 5, s);
+    } else {
+        mark(h, 4, s);
+        mark(h, 5, s);
     }
     if (int e = cugs_b200_tile_ranges(h, stream, p, w.keys_x, num_tiles, tile_ranges)) return e;
+    mark(h, 6, s);
     if (int e = cugs_b200_blend_fwd(h, stream, v, tile_ranges, gaussian_idx, means_2d, cov_2d_inv, rgb,
                                     opacities_act, n > 0 ? w.packed : nullptr, color, final_T, n_contrib)) {
         return e;
     }
-    (void)s;
+    mark(h, 7, s);
     return CUGS_OK;
 }
 
@@ -226,8 +291,8 @@ extern "C" int cugs_b200_render_backward(
     const float* opacities_act, const int32_t* gaussian_idx, const int32_t* tile_ranges,
     const float* final_T, const int32_t* n_contrib, const float* dL_dcolor, float* dL_dpositions,
     float* dL_drotations, float* dL_dscales, float* dL_dopacities, float* dL_dsh_coeffs,
-    float* dL_dmeans_2d, float* grad_accum, float* grad_count, float* max_radii, void* workspace,
-    size_t workspace_bytes) {
+    float* dL_dmeans_2d, float* grad_accum, float* grad_count, float* max_radii, int accumulate,
+    void* workspace, size_t workspace_bytes) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, n >= 0, "n must be >= 0");
     if (n == 0) return CUGS_OK;
@@ -245,12 +310,17 @@ extern "C" int cugs_b200_render_backward(
     cudaStream_t s = (cudaStream_t)stream;
     const FrameWorkspace w = carve(workspace, n, 0);
     // stage 1 (rasterizer.cpp:146-158): pixel gradients -> packed per-Gaussian 2-D gradients
+    mark(h, 8, s);
     if (int e = cugs_blend_bwd_accumulate(h, s, n, v, tile_ranges, gaussian_idx, means_2d, cov_2d_inv, rgb,
                                           opacities_act, w.packed, dL_dcolor, final_T, n_contrib, w.grad_acc))
         return e;
+    mark(h, 9, s);
     // stage 2 (rasterizer.cpp:163-176): 2-D gradients -> parameter gradients (+ SH backward, + stats)
-    return cugs_preprocess_bwd_launch(h, s, n, v, positions, rotations, scales, opacities, sh_coeffs, radii,
-                                      rgb, nullptr, nullptr, nullptr, nullptr, dL_dpositions, dL_drotations,
-                                      dL_dscales, dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count,
-                                      max_radii, w.grad_acc, dL_dmeans_2d);
+    if (int e = cugs_preprocess_bwd_launch(h, s, n, v, positions, rotations, scales, opacities, sh_coeffs,
+                                           radii, rgb, nullptr, nullptr, nullptr, nullptr, dL_dpositions,
+                                           dL_drotations, dL_dscales, dL_dopacities, dL_dsh_coeffs, grad_accum,
+                                           grad_count, max_radii, w.grad_acc, dL_dmeans_2d, accumulate != 0))
+        return e;
+    mark(h, 10, s);
+    return CUGS_OK;
 }

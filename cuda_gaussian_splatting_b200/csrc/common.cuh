@@ -15,6 +15,12 @@ struct cugs_handle {
     int sm_count;
     int64_t* pinned;      // mapped pinned host words {P, depth_min|depth_max<<32, ...}
     char err[512];
+    // optional per-stage timing of the fused entry points (cugs_b200_set_stage_timing)
+    bool timing;
+    cudaEvent_t ev[12];
+    bool ev_recorded[12];
+    int last_sort_passes, last_sort_key_bits;  // plan of the most recent render_finish
+    unsigned long long launches;  // kernels launched through this handle (cugs_b200_launch_count)
 };
 
 namespace cugs {
@@ -46,6 +52,7 @@ inline int set_error(cugs_handle* h, int code, const char* fmt, ...) {
         if (_e != cudaSuccess)                                                                  \
             return cugs::set_error((h), (int)_e, "launch %s failed: %s", (name),                \
                                    cudaGetErrorString(_e));                                     \
+        ++(h)->launches;                                                                        \
     } while (0)
 
 #define CUGS_REQUIRE(h, cond, msg)                                                              \

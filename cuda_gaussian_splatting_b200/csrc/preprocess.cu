@@ -302,7 +302,8 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                  float* __restrict__ dL_dsh, float* __restrict__ grad_accum,
                  float* __restrict__ grad_count, float* __restrict__ max_radii,
                  const float4* __restrict__ gacc /* [N,3] packed blend gradients or null */,
-                 float* __restrict__ dL_dmeans_2d_out /* written when gacc != null */) {
+                 float* __restrict__ dL_dmeans_2d_out /* written when gacc != null */,
+                 bool accumulate /* add to the five parameter-gradient outputs instead of overwriting */) {
     __shared__ __align__(16) float sY[kPreWarps][32 * kYStride];
     __shared__ float sG[kPreWarps][96];  // gated dL/drgb per (Gaussian, channel)
 
@@ -468,6 +469,13 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
         }
     }
     if (valid) {
+        if (accumulate) {
+            g_pos[0] += dL_dpos[i * 3 + 0]; g_pos[1] += dL_dpos[i * 3 + 1]; g_pos[2] += dL_dpos[i * 3 + 2];
+            const float4 r4 = reinterpret_cast<const float4*>(dL_drot)[i];
+            g_rot[0] += r4.x; g_rot[1] += r4.y; g_rot[2] += r4.z; g_rot[3] += r4.w;
+            g_scl[0] += dL_dscl[i * 3 + 0]; g_scl[1] += dL_dscl[i * 3 + 1]; g_scl[2] += dL_dscl[i * 3 + 2];
+            g_opa += dL_dopa[i];
+        }
         dL_dpos[i * 3 + 0] = g_pos[0]; dL_dpos[i * 3 + 1] = g_pos[1]; dL_dpos[i * 3 + 2] = g_pos[2];
         reinterpret_cast<float4*>(dL_drot)[i] = make_float4(g_rot[0], g_rot[1], g_rot[2], g_rot[3]);
         dL_dscl[i * 3 + 0] = g_scl[0]; dL_dscl[i * 3 + 1] = g_scl[1]; dL_dscl[i * 3 + 2] = g_scl[2];
@@ -499,14 +507,22 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
             o.y = (k0 + 1 < na) ? gd * y4.y : 0.0f;
             o.z = (k0 + 2 < na) ? gd * y4.z : 0.0f;
             o.w = (k0 + 3 < na) ? gd * y4.w : 0.0f;
+            if (accumulate) {
+                const float4 old = __ldcs(out4 + q);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
             __stcs(out4 + q, o);
         }
     } else if (valid) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             float* o = dL_dsh + (i * 3 + ch) * vp.C;
-            for (int k = 0; k < na; ++k) o[k] = gate_g[ch] * Y[k];
-            for (int k = na; k < vp.C; ++k) o[k] = 0.0f;
+            if (accumulate) {
+                for (int k = 0; k < na; ++k) o[k] += gate_g[ch] * Y[k];
+            } else {
+                for (int k = 0; k < na; ++k) o[k] = gate_g[ch] * Y[k];
+                for (int k = na; k < vp.C; ++k) o[k] = 0.0f;
+            }
         }
     }
 }
@@ -604,7 +620,8 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
                                const float* dL_drgb, const float* dL_dopacity_act, float* dL_dpositions,
                                float* dL_drotations, float* dL_dscales, float* dL_dopacities,
                                float* dL_dsh_coeffs, float* grad_accum, float* grad_count,
-                               float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out) {
+                               float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out,
+                               bool accumulate) {
     const ViewParams vp = make_view_params(v);
     const unsigned grid = (unsigned)((n + kPreBlock - 1) / kPreBlock);
     if (v->num_coeffs == 16)
@@ -612,13 +629,13 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
             n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
             dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
             dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
-            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out);
+            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate);
     else
         k_preprocess_bwd<false><<<grid, kPreBlock, 0, s>>>(
             n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
             dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
             dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
-            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out);
+            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate);
     CUGS_LAUNCH_CHECK(h, "k_preprocess_bwd");
     return CUGS_OK;
 }
@@ -650,7 +667,7 @@ extern "C" int cugs_b200_preprocess_bwd(cugs_handle_t* h, void* stream, int64_t 
                                       opacities, sh_coeffs, radii, rgb, dL_dmeans_2d, dL_dcov_2d_inv,
                                       dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
                                       dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
-                                      nullptr, nullptr);
+                                      nullptr, nullptr, false);
 }
 
 extern "C" int cugs_b200_sh_forward(cugs_handle_t* h, void* stream, int64_t n, int degree,

@@ -445,12 +445,25 @@ class FrameBuffers:
         self.workspace = torch.empty((1,), dtype=torch.uint8, device=device)
         self.p_capacity = 0
         self.ensure_capacity(max(p_capacity, 1))
-        # gradients
-        self.dL_dpositions = torch.empty((n, 3), **f)
-        self.dL_drotations = torch.empty((n, 4), **f)
-        self.dL_dscales = torch.empty((n, 3), **f)
-        self.dL_dopacities = torch.empty((n, 1), **f)
-        self.dL_dsh_coeffs = torch.empty((n, 3, num_coeffs), **f)
+        # gradients: ONE contiguous arena laid out as the five Adam groups (fused_adam.cu:94-97:
+        # positions, sh_coeffs, opacities, scales, rotations) followed by the two additive
+        # densification statistics of the step, so that view-parallel training needs exactly one
+        # all-reduce(sum) per step. Segment starts are 256-byte aligned (float4 accesses).
+        sizes = [3 * n, 3 * num_coeffs * n, n, 3 * n, 4 * n, n, n]
+        starts, off = [], 0
+        for sz in sizes:
+            starts.append(off)
+            off += (sz + 63) // 64 * 64
+        self.grad_arena = torch.zeros((max(off, 64),), **f)
+        seg = lambda k: self.grad_arena[starts[k]:starts[k] + sizes[k]]
+        self.dL_dpositions = seg(0).view(n, 3)
+        self.dL_dsh_coeffs = seg(1).view(n, 3, num_coeffs)
+        self.dL_dopacities = seg(2).view(n, 1)
+        self.dL_dscales = seg(3).view(n, 3)
+        self.dL_drotations = seg(4).view(n, 4)
+        self.step_grad_accum = seg(5)   # sum over the step's views of ||dL/dmeans_2d|| (visible only)
+        self.step_grad_count = seg(6)   # number of the step's views in which the Gaussian was visible
+        self.step_max_radii = torch.zeros((n,), **f)  # needs a max-reduction, kept outside the arena
         self.dL_dmeans_2d = torch.empty((n, 2), **f)
 
     def ensure_capacity(self, p: int) -> None:
@@ -514,9 +527,11 @@ def render(model: GaussianModel, camera: CameraInfo, settings: RenderSettings,
 
 def render_backward(dL_dcolor: torch.Tensor, render_out: RenderOutput, model: GaussianModel,
                     camera: CameraInfo, settings: RenderSettings, buffers: Optional[FrameBuffers] = None,
-                    stats: Optional[Sequence[torch.Tensor]] = None) -> BackwardOutput:
+                    stats: Optional[Sequence[torch.Tensor]] = None, accumulate: bool = False) -> BackwardOutput:
     """rasterizer.hpp:88-93 / rasterizer.cpp:115-186. ``stats`` = (grad_accum, grad_count,
-    max_radii) fuses DensificationController::accumulate_gradients into the same launch."""
+    max_radii) fuses DensificationController::accumulate_gradients into the same launch;
+    ``accumulate`` adds the parameter gradients to ``buffers`` instead of overwriting them
+    (gradient of a batch of views)."""
     _check(dL_dcolor.is_cuda, "dL_dcolor must be on CUDA device")
     _check(dL_dcolor.dim() == 3 and dL_dcolor.shape[2] == 3, "dL_dcolor must be [H, W, 3]")
     dev = dL_dcolor.device
@@ -532,6 +547,7 @@ def render_backward(dL_dcolor: torch.Tensor, render_out: RenderOutput, model: Ga
     v = make_view(camera, settings, active, sh.shape[2])
     ws = render_out._workspace
     _check(ws is not None, "render_out does not come from render() of this library")
+    _check(not accumulate or buffers is not None, "accumulate=True needs persistent FrameBuffers")
     if buffers is not None:
         g = (buffers.dL_dpositions, buffers.dL_drotations, buffers.dL_dscales, buffers.dL_dopacities,
              buffers.dL_dsh_coeffs, buffers.dL_dmeans_2d)
@@ -544,6 +560,6 @@ def render_backward(dL_dcolor: torch.Tensor, render_out: RenderOutput, model: Ga
         h, _stream(dev), n, C.byref(v), _ptr(pos), _ptr(rot), _ptr(scl), _ptr(opa), _ptr(sh), _ptr(r.means_2d),
         _ptr(r.cov_2d_inv), _ptr(r.radii), _ptr(r.rgb), _ptr(r.opacities_act), _ptr(r.gaussian_indices),
         _ptr(r.tile_ranges), _ptr(r.final_T), _ptr(r.n_contrib), _ptr(dL_dcolor.contiguous()),
-        *[_ptr(t) for t in g], *sp, _ptr(ws), ws.numel())
+        *[_ptr(t) for t in g], *sp, int(bool(accumulate)), _ptr(ws), ws.numel())
     _lib.check(h, st, "cugs_b200_render_backward")
     return BackwardOutput(*g)

@@ -62,6 +62,8 @@ void cugs_b200_destroy(cugs_handle_t* h);
 const char* cugs_b200_last_error(const cugs_handle_t* h);
 int cugs_b200_abi_version(void);
 int cugs_b200_sm_count(const cugs_handle_t* h);
+/* number of CUDA kernels this handle has launched so far (memsets / copies not counted) */
+uint64_t cugs_b200_launch_count(const cugs_handle_t* h);
 
 /* ---- stage 1: preprocess forward ---------------------------------------------------------
  * Replaces project_gaussians (rasterizer/projection.cu:195-289): k_project_gaussians (:55-189),
@@ -159,7 +161,11 @@ int cugs_b200_preprocess_bwd(cugs_handle_t* h, void* stream, int64_t n, const cu
  * render_finish = duplicateWithKeys + sort + tile ranges + blend; gaussian_idx must hold P
  * entries. workspace: cugs_b200_render_workspace_bytes(n, p_capacity) bytes; the SAME workspace
  * must be passed to plan, finish and render_backward of one frame (it carries the packed
- * records). render_backward = blend_bwd + preprocess_bwd (rasterizer/rasterizer.cpp:115-186). */
+ * records). render_backward = blend_bwd + preprocess_bwd (rasterizer/rasterizer.cpp:115-186).
+ * accumulate = 0: the five parameter gradients are overwritten (reference behaviour);
+ * accumulate = 1: they are added to what the buffers hold (view-batched training: the gradient
+ * of a batch of views is summed in place, no separate axpy pass). dL_dmeans_2d is always
+ * overwritten (it is a per-view quantity, optimizer/densification.cpp:77). */
 size_t cugs_b200_render_workspace_bytes(int64_t n, int64_t p_capacity);
 int cugs_b200_render_plan(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
                           const float* positions, const float* rotations, const float* scales,
@@ -183,7 +189,19 @@ int cugs_b200_render_backward(cugs_handle_t* h, void* stream, int64_t n, const c
                               const float* dL_dcolor, float* dL_dpositions, float* dL_drotations,
                               float* dL_dscales, float* dL_dopacities, float* dL_dsh_coeffs,
                               float* dL_dmeans_2d, float* grad_accum, float* grad_count,
-                              float* max_radii, void* workspace, size_t workspace_bytes);
+                              float* max_radii, int accumulate, void* workspace,
+                              size_t workspace_bytes);
+
+/* Optional per-stage device timing of the three fused entry points above: when enabled, CUDA
+ * events are recorded on the caller's stream at the stage boundaries (a few microseconds per
+ * frame); get_stage_ms synchronises on the last recorded event and returns the durations in ms
+ * of {preprocess_fwd, scan, duplicate_with_keys, sort, tile_ranges, blend_fwd, blend_bwd,
+ * preprocess_bwd} of the most recent frame (-1 for a stage that did not run). */
+/* Sort plan of the most recent render_finish: number of onesweep passes and sorted key bits. */
+int cugs_b200_last_sort_plan(const cugs_handle_t* h, int* passes, int* key_bits);
+#define CUGS_NUM_STAGES 8
+int cugs_b200_set_stage_timing(cugs_handle_t* h, int enable);
+int cugs_b200_get_stage_ms(cugs_handle_t* h, float* ms8);
 
 /* ---- stage 7: fused L1 + SSIM loss and fused multi-tensor Adam ------------------------------
  * loss: combined_loss (training/loss.cpp:131-135) value AND its gradient w.r.t. rendered (the

@@ -1,0 +1,545 @@
+"""GPU parity tests: the sm_100a CUDA path (through the C ABI) against
+
+  (1) the UNMODIFIED reference CUDA kernels compiled for sm_100 (oracle/_ref/cugs_ref*.so, the
+      bit oracle: run on the same B200, same inputs) and
+  (2) the CPU oracle oracle/cugs_oracle.c (the tolerance oracle; bit oracle for the pure
+      integer stages).
+
+Bars (BASELINE.json north_star): tile keys, sort order, tile ranges, radii and tile counts
+BIT-EXACT; images max-abs <= 1e-4; gradients within rel 1e-3 (norm-wise, see `grad_close`).
+Nothing here reads /root/reference at run time.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import cuda_gaussian_splatting_b200 as cugs
+from cuda_gaussian_splatting_b200 import CameraInfo, Scene
+from conftest import to_torch
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-4       # max abs on images (north_star)
+GRAD_REL = 1e-3      # relative tolerance on gradients (north_star)
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    if not t.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return t
+
+
+def grad_close(mine, ref, rel=GRAD_REL):
+    """Gradient bar. The reference accumulates with float atomics in arbitrary order, so its own
+    result is only defined up to summation-order noise; element-wise relative error is therefore
+    meaningless for elements that are sums with cancellation. We require
+      * norm-wise:    ||mine - ref||_2 <= rel * ||ref||_2
+      * element-wise: |mine - ref| <= rel * |ref| + rel * rms(ref)   (rms = scale of the tensor)
+    """
+    mine = np.asarray(mine, np.float64).reshape(-1)
+    ref = np.asarray(ref, np.float64).reshape(-1)
+    assert mine.shape == ref.shape
+    assert np.isfinite(mine).all()
+    nref = np.linalg.norm(ref)
+    err = np.linalg.norm(mine - ref)
+    rms = nref / math.sqrt(max(ref.size, 1))
+    if nref == 0:
+        return bool(err == 0), f"ref is zero, |err| = {err}"
+    el = np.abs(mine - ref) - (rel * np.abs(ref) + rel * rms)
+    ok = err <= rel * nref and (el <= 0).all()
+    return bool(ok), f"norm-rel {err / nref:.3e}, worst element excess {el.max():.3e} (rms {rms:.3e})"
+
+
+def scenes():
+    return {
+        "small": (cugs.synth(5000, 320, 240, seed=11), 3),
+        "ragged": (cugs.synth(3001, 333, 211, seed=12), 3),            # N % 32 != 0, W,H % 16 != 0
+        "adversarial": (cugs.synth(20000, 640, 360, seed=13, adversarial=True), 3),  # culls + A.2 quirk
+        "deg0_c1": (cugs.synth(4000, 256, 256, seed=14, num_coeffs=1), 0),
+        "deg1_c4": (cugs.synth(4000, 256, 192, seed=15, num_coeffs=4), 1),
+        "deg2_c16": (cugs.synth(4000, 256, 192, seed=16, num_coeffs=16), 2),  # allocated 16, active 9
+        "dense_big_splats": (cugs.synth(3000, 160, 120, seed=17, sigma_px=12.0), 3),  # saturating pixels
+        "config_A": (cugs.synth(100_000, 1280, 720, seed=1235), 3),
+    }
+
+
+SCENES = None
+
+
+def get_scene(name):
+    global SCENES
+    if SCENES is None:
+        SCENES = scenes()
+    return SCENES[name]
+
+
+NAMES = ["small", "ragged", "adversarial", "deg0_c1", "deg1_c4", "deg2_c16", "dense_big_splats", "config_A"]
+
+
+def ref_render(ref, torch, scene, deg, bg=(0.0, 0.0, 0.0), scale_mod=1.0, camera=None):
+    m = to_torch(scene)
+    cam = (camera or scene.camera).as_ref_list()
+    out = ref.render(m.positions, m.sh_coeffs, m.opacities, m.rotations, m.scales, cam, list(bg), deg, scale_mod)
+    torch.cuda.synchronize()
+    return m, out
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+# ================================================================================================
+# 1. preprocess: bit-exact integers and screen-space floats versus the compiled reference
+# ================================================================================================
+@pytest.mark.parametrize("name", NAMES)
+def test_preprocess_vs_reference(ref, torch, name):
+    scene, deg = get_scene(name)
+    m = to_torch(scene)
+    r = ref.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs,
+                              scene.camera.as_ref_list(), deg, 1.0)
+    o = cugs.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs, scene.camera, deg)
+    r_m2d, r_dep, r_cov, r_rad, r_tiles, r_rgb, r_opa = [np_(t) for t in r]
+    assert np.array_equal(np_(o.radii), r_rad), "radii must be bit-exact"
+    assert np.array_equal(np_(o.tiles_touched), r_tiles), "tiles_touched must be bit-exact"
+    assert np.array_equal(np_(o.depths).view(np.uint32), r_dep.view(np.uint32)), "depth bits feed the sort key"
+    assert np.array_equal(np_(o.means_2d).view(np.uint32), r_m2d.view(np.uint32)), "means_2d feed the tile rect"
+    assert np.array_equal(np_(o.opacities_act).view(np.uint32), r_opa.view(np.uint32))
+    assert np.array_equal(np_(o.cov_2d_inv).view(np.uint32), r_cov.view(np.uint32))
+    assert np.abs(np_(o.rgb) - r_rgb).max() <= 2e-6  # SH: different summation order only
+
+
+def test_preprocess_scale_modifier_and_ring_camera(ref, torch):
+    scene, deg = get_scene("small")
+    cam = cugs.ring_cameras(scene, 3)[1]
+    m = to_torch(scene)
+    for sm in (0.5, 2.0):
+        r = ref.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs, cam.as_ref_list(), deg, sm)
+        o = cugs.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs, cam, deg, sm)
+        assert np.array_equal(np_(o.radii), np_(r[3]))
+        assert np.array_equal(np_(o.tiles_touched), np_(r[4]))
+        assert np.array_equal(np_(o.depths).view(np.uint32), np_(r[1]).view(np.uint32))
+        assert np.array_equal(np_(o.means_2d).view(np.uint32), np_(r[0]).view(np.uint32))
+        assert np.abs(np_(o.rgb) - np_(r[5])).max() <= 2e-6
+
+
+# ================================================================================================
+# 2-4. scan + duplicateWithKeys + sort + ranges: bit-exact
+# ================================================================================================
+@pytest.mark.parametrize("name", NAMES)
+def test_sort_stage_bit_exact_vs_reference(ref, torch, name):
+    scene, deg = get_scene(name)
+    m = to_torch(scene)
+    r = ref.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs,
+                              scene.camera.as_ref_list(), deg, 1.0)
+    W, H = scene.camera.width, scene.camera.height
+    rk, rv, rr, rp = ref.sort_gaussians(r[0], r[1], r[3], r[4], W, H)
+    for depth_bits in (32,):
+        s = cugs.sort_gaussians(r[0], r[1], r[3], r[4], W, H, depth_bits=depth_bits)
+        assert s.total_pairs == int(rp.item())
+        assert np.array_equal(np_(s.gaussian_keys_sorted), np_(rk)), "sorted keys"
+        assert np.array_equal(np_(s.gaussian_values_sorted), np_(rv)), "sort order (values)"
+        assert np.array_equal(np_(s.tile_ranges), np_(rr)), "tile ranges"
+    # sorting on all 64 bits (the reference's CUB call) gives the same permutation
+    s64 = cugs.sort_gaussians(r[0], r[1], r[3], r[4], W, H, depth_bits=32, tile_bits=32)
+    assert np.array_equal(np_(s64.gaussian_values_sorted), np_(rv))
+
+
+@pytest.mark.parametrize("name", ["small", "adversarial", "ragged"])
+def test_binning_vs_cpu_oracle(oracle, torch, name):
+    """Integer stages against the CPU restatement (no compiled reference needed)."""
+    scene, deg = get_scene(name)
+    m = to_torch(scene)
+    o = cugs.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs, scene.camera, deg)
+    W, H = scene.camera.width, scene.camera.height
+    s = cugs.sort_gaussians(o.means_2d, o.depths, o.radii, o.tiles_touched, W, H)
+    tiles = np_(o.tiles_touched)
+    off, P = oracle.scan(tiles)
+    assert s.total_pairs == P
+    keys, vals = oracle.fill_keys(np_(o.means_2d), np_(o.depths), np_(o.radii), off, W, H, P)
+    ks, vs = oracle.sort_pairs(keys, vals)
+    assert np.array_equal(np_(s.gaussian_keys_sorted).view(np.uint64), ks)
+    assert np.array_equal(np_(s.gaussian_values_sorted), vs)
+    nt = cugs.rasterizer.num_tiles(W, H)
+    assert np.array_equal(np_(s.tile_ranges), oracle.tile_ranges(ks, nt))
+
+
+def test_sort_random_keys_all_bit_plans(oracle, torch):
+    """The onesweep sort on raw random pairs for several (depth_bits, tile_bits) plans, incl. ragged
+    sizes around the 4608-pair tile and duplicate keys (stability)."""
+    import ctypes as C
+    from cuda_gaussian_splatting_b200 import _lib
+    lib, h = _lib.load_library(), _lib.handle(0)
+    rng = np.random.default_rng(5)
+    for p in (1, 31, 4607, 4608, 4609, 100_003, 1_000_000):
+        for db, tb in ((32, 13), (20, 13), (32, 32), (7, 1), (0, 9), (32, 0)):
+            depth = rng.integers(0, 1 << db, size=p, dtype=np.uint64) if db else np.zeros(p, np.uint64)
+            tile = rng.integers(0, 1 << tb, size=p, dtype=np.uint64) if tb else np.zeros(p, np.uint64)
+            if p > 1000:  # many duplicates: stability must hold
+                depth[: p // 2] = depth[0]
+            keys = (tile << np.uint64(32)) | depth
+            vals = np.arange(p, dtype=np.int32)
+            k_in, v_in = torch.from_numpy(keys.view(np.int64)).cuda(), torch.from_numpy(vals).cuda()
+            k_out, v_out = torch.empty_like(k_in), torch.empty_like(v_in)
+            tmp = torch.empty((lib.cugs_b200_sort_temp_bytes(p),), dtype=torch.uint8, device="cuda")
+            st = lib.cugs_b200_sort_pairs(h, torch.cuda.current_stream().cuda_stream, p, db, tb, k_in.data_ptr(),
+                                          v_in.data_ptr(), k_out.data_ptr(), v_out.data_ptr(), tmp.data_ptr(), tmp.numel())
+            _lib.check(h, st, "sort")
+            order = np.argsort(keys, kind="stable")
+            assert np.array_equal(np_(k_out).view(np.uint64), keys[order]), (p, db, tb)
+            assert np.array_equal(np_(v_out), vals[order]), (p, db, tb)
+
+
+# ================================================================================================
+# 5. full forward through render(): integers bit-exact, image <= 1e-4
+# ================================================================================================
+@pytest.mark.parametrize("name", NAMES)
+def test_render_forward_vs_reference(ref, torch, name):
+    scene, deg = get_scene(name)
+    bg = (0.1, 0.2, 0.3)
+    m, r = ref_render(ref, torch, scene, deg, bg)
+    out = cugs.render(m, scene.camera, cugs.RenderSettings(bg, deg, 1.0))
+    torch.cuda.synchronize()
+    r_color, r_T, r_n, _, _, _, r_rad, _, _, r_idx, r_ranges = [np_(t) for t in r]
+    assert np.array_equal(np_(out.radii), r_rad)
+    assert np.array_equal(np_(out.tile_ranges), r_ranges), "tile ranges must be bit-exact"
+    assert np.array_equal(np_(out.gaussian_indices), r_idx), "sort order must be bit-exact"
+    assert np.array_equal(np_(out.n_contrib), r_n), "n_contrib must be bit-exact (backward consumes it)"
+    assert np.abs(np_(out.color) - r_color).max() <= IMG_TOL
+    assert np.abs(np_(out.final_T) - r_T).max() <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["small", "dense_big_splats", "adversarial"])
+def test_render_forward_vs_cpu_oracle(oracle, torch, name):
+    scene, deg = get_scene(name)
+    bg = (0.3, 0.5, 0.7)
+    o = oracle.render_forward(scene, deg=deg, bg=bg)
+    out = cugs.render(to_torch(scene), scene.camera, cugs.RenderSettings(bg, deg, 1.0))
+    assert np.array_equal(np_(out.radii), o["radii"])
+    assert np.array_equal(np_(out.tile_ranges), o["tile_ranges"])
+    assert np.array_equal(np_(out.gaussian_indices), o["gaussian_indices"])
+    # the CPU expf differs from the GPU's in the last ulp, so a handful of threshold decisions may flip
+    mismatch = (np_(out.n_contrib) != o["n_contrib"]).mean()
+    assert mismatch <= 1e-3, f"n_contrib mismatch fraction {mismatch}"
+    d = np.abs(np_(out.color) - o["color"])
+    assert np.quantile(d, 0.999) <= IMG_TOL and d.max() <= 1e-2
+
+
+def test_stage_rasterize_forward_matches_render(ref, torch):
+    """Public stage function (un-packed gather path) == fused path."""
+    scene, deg = get_scene("small")
+    bg = (0.0, 0.5, 1.0)
+    m, r = ref_render(ref, torch, scene, deg, bg)
+    W, H = scene.camera.width, scene.camera.height
+    f = cugs.rasterize_forward(r[3], r[5], r[7], r[8], r[10], r[9], W, H, bg)
+    assert np.array_equal(np_(f.n_contrib), np_(r[2]))
+    assert np.abs(np_(f.color) - np_(r[0])).max() <= IMG_TOL
+    assert np.abs(np_(f.final_T) - np_(r[1])).max() <= 1e-6
+
+
+# ================================================================================================
+# 6. backward
+# ================================================================================================
+def _dL(torch, scene, seed=4321):
+    H, W = scene.camera.height, scene.camera.width
+    rng = np.random.default_rng(seed)
+    return torch.from_numpy(rng.uniform(-1, 1, size=(H, W, 3)).astype(np.float32)).cuda()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_render_backward_vs_reference(ref, torch, name):
+    scene, deg = get_scene(name)
+    bg = (0.1, 0.2, 0.3)
+    m, r = ref_render(ref, torch, scene, deg, bg)
+    g = _dL(torch, scene)
+    rb = ref.render_backward(g, r, m.positions, m.sh_coeffs, m.opacities, m.rotations, m.scales,
+                             scene.camera.as_ref_list(), list(bg), deg, 1.0)
+    settings = cugs.RenderSettings(bg, deg, 1.0)
+    out = cugs.render(m, scene.camera, settings)
+    b = cugs.render_backward(g, out, m, scene.camera, settings)
+    torch.cuda.synchronize()
+    names = ["dL_dpositions", "dL_drotations", "dL_dscales", "dL_dopacities", "dL_dsh_coeffs", "dL_dmeans_2d"]
+    for nm, rt in zip(names, rb):
+        ok, msg = grad_close(np_(getattr(b, nm)), np_(rt))
+        assert ok, f"{name}.{nm}: {msg}"
+        assert getattr(b, nm).shape == rt.shape
+
+
+@pytest.mark.parametrize("name", ["small", "dense_big_splats"])
+def test_stage_backward_functions_vs_reference(ref, torch, name):
+    """rasterize_backward / project_backward stage functions on the reference's own intermediates."""
+    scene, deg = get_scene(name)
+    bg = (0.2, 0.2, 0.2)
+    m, r = ref_render(ref, torch, scene, deg, bg)
+    W, H, n = scene.camera.width, scene.camera.height, scene.n
+    g = _dL(torch, scene, 7)
+    rr = ref.rasterize_backward(g, r[3], r[5], r[7], r[8], r[10], r[9], r[1], r[2], W, H, list(bg), n)
+    mine = cugs.rasterize_backward(g, r[3], r[5], r[7], r[8], r[10], r[9], r[1], r[2], W, H, bg, n)
+    for nm, rt in zip(["dL_drgb", "dL_dopacity_act", "dL_dmeans_2d", "dL_dcov_2d_inv"], rr):
+        ok, msg = grad_close(np_(getattr(mine, nm)), np_(rt))
+        assert ok, f"{nm}: {msg}"
+    # project_backward on identical incoming gradients: deterministic per-Gaussian math
+    rp = ref.project_backward(rr[2], rr[3], rr[0], rr[1], m.positions, m.rotations, m.scales, m.opacities,
+                              m.sh_coeffs, r[6], scene.camera.as_ref_list(), deg, 1.0)
+    mp = cugs.project_backward(rr[2], rr[3], rr[0], rr[1], m.positions, m.rotations, m.scales, m.opacities,
+                               m.sh_coeffs, r[6], scene.camera, deg, 1.0, rgb=r[7])
+    for nm, rt in zip(["dL_dpositions", "dL_drotations", "dL_dscales", "dL_dopacities", "dL_dsh_coeffs"], rp):
+        ok, msg = grad_close(np_(getattr(mp, nm)), np_(rt), rel=1e-4)
+        assert ok, f"{nm}: {msg}"
+
+
+@pytest.mark.parametrize("name", ["small", "dense_big_splats"])
+def test_render_backward_vs_cpu_oracle(oracle, torch, name):
+    scene, deg = get_scene(name)
+    m = to_torch(scene)
+    settings = cugs.RenderSettings((0.0, 0.0, 0.0), deg, 1.0)
+    out = cugs.render(m, scene.camera, settings)
+    g = _dL(torch, scene, 3)
+    b = cugs.render_backward(g, out, m, scene.camera, settings)
+    # feed the oracle the GPU's forward outputs so both walk identical (n_contrib, final_T)
+    fwd = dict(tile_ranges=np_(out.tile_ranges), gaussian_indices=np_(out.gaussian_indices),
+               means_2d=np_(out.means_2d), cov_2d_inv=np_(out.cov_2d_inv), rgb=np_(out.rgb),
+               opacities_act=np_(out.opacities_act), final_T=np_(out.final_T), n_contrib=np_(out.n_contrib),
+               radii=np_(out.radii))
+    ob = oracle.render_backward(scene, fwd, np_(g), deg=deg)
+    for nm in ["dL_dpositions", "dL_drotations", "dL_dscales", "dL_dopacities", "dL_dsh_coeffs", "dL_dmeans_2d"]:
+        ok, msg = grad_close(np_(getattr(b, nm)), ob[nm], rel=2e-3)  # CPU expf / summation order
+        assert ok, f"{nm}: {msg}"
+
+
+def test_culled_gaussian_has_exactly_zero_gradients(torch):  # test_backward.cpp:181-201
+    f = np.float32
+    cam = CameraInfo(64, 48, 200.0, 200.0, 32.0, 24.0)
+    s = Scene(np.array([[0, 0, -5]], f), np.ones((1, 3, 1), f), np.full((1, 1), 5.0, f), np.array([[1, 0, 0, 0]], f),
+              np.full((1, 3), -2.0, f), cam)
+    m = to_torch(s)
+    st = cugs.RenderSettings((0, 0, 0), 0, 1.0)
+    out = cugs.render(m, cam, st)
+    b = cugs.render_backward(_dL(torch, s), out, m, cam, st)
+    for nm in ["dL_dpositions", "dL_drotations", "dL_dscales", "dL_dopacities", "dL_dsh_coeffs"]:
+        assert float(getattr(b, nm).abs().sum()) == 0.0
+
+
+# ================================================================================================
+# reference known-answer tests, run on the product (tests/test_rasterizer.cpp, test_projection.cpp)
+# ================================================================================================
+def _single(x, y, z, cam, opa=0.0, sh_dc=1.0, log_s=-2.0):
+    f = np.float32
+    return Scene(np.array([[x, y, z]], f), np.full((1, 3, 1), sh_dc, f), np.array([[opa]], f),
+                 np.array([[1, 0, 0, 0]], f), np.full((1, 3), log_s, f), cam)
+
+
+def test_known_answers_projection(torch):  # test_projection.cpp:64-149
+    cam = CameraInfo(640, 480, 500.0, 500.0, 320.0, 240.0)
+    s = _single(0, 0, 5, cam)
+    m = to_torch(s)
+    o = cugs.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs, cam, 0)
+    assert int(o.radii[0]) > 0 and int(o.tiles_touched[0]) > 0
+    assert abs(float(o.means_2d[0, 0]) - 320) <= 1 and abs(float(o.means_2d[0, 1]) - 240) <= 1
+    assert abs(float(o.depths[0]) - 5) <= 0.01 and abs(float(o.opacities_act[0]) - 0.5) <= 0.01
+    s = _single(1, 0, 5, cam)
+    m = to_torch(s)
+    o = cugs.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs, cam, 0)
+    assert abs(float(o.means_2d[0, 0]) - 420) <= 1
+    s = _single(0, 0, -5, cam)
+    m = to_torch(s)
+    o = cugs.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs, cam, 0)
+    assert int(o.radii[0]) == 0 and int(o.tiles_touched[0]) == 0
+
+
+def test_known_answers_rasterizer(torch):  # test_rasterizer.cpp:72-325
+    cam = CameraInfo(320, 240, 200.0, 200.0, 160.0, 120.0)
+    z = np.zeros
+    empty = Scene(z((0, 3), np.float32), z((0, 3, 1), np.float32), z((0, 1), np.float32), z((0, 4), np.float32),
+                  z((0, 3), np.float32), cam)
+    out = cugs.render(to_torch(empty), cam, cugs.RenderSettings((0.3, 0.5, 0.7), 0, 1.0))
+    assert tuple(out.color.shape) == (240, 320, 3) and tuple(out.final_T.shape) == (240, 320)
+    assert np.allclose(np_(out.color)[120, 160], [0.3, 0.5, 0.7], atol=0.01)
+    s = _single(0, 0, 5, cam, opa=5.0, log_s=-1.5)
+    out = cugs.render(to_torch(s), cam, cugs.RenderSettings((1.0, 0.0, 1.0), 0, 1.0))
+    c = np_(out.color)
+    assert c[120, 160, 1] > 0.1 and c[120, 160, 1] > c[0, 0, 1]
+    assert np.allclose(c[0, 0], [1.0, 0.0, 1.0], atol=0.05)
+    assert float(out.final_T[120, 160]) < 0.5 and int(out.n_contrib[120, 160]) >= 1
+    # all Gaussians culled: P == 0 path
+    s = _single(0, 0, -5, cam)
+    out = cugs.render(to_torch(s), cam, cugs.RenderSettings((0.3, 0.5, 0.7), 0, 1.0))
+    assert np.allclose(np_(out.color), np.array([0.3, 0.5, 0.7], np.float32)[None, None], atol=1e-6)
+    assert int(out.gaussian_indices.numel()) == 0 and int(out.tile_ranges.abs().sum()) == 0
+
+
+def test_sh_stage_functions_vs_reference(ref, torch):  # test_sh.cpp:161-216
+    rng = np.random.default_rng(3)
+    for deg in range(4):
+        n = 10_000 if deg == 3 else 257
+        sh = torch.from_numpy(rng.normal(0, 0.7, size=(n, 3, 16)).astype(np.float32)).cuda()
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        d = torch.from_numpy(d).cuda()
+        g = torch.from_numpy(rng.normal(size=(n, 3)).astype(np.float32)).cuda()
+        assert np.abs(np_(cugs.evaluate_sh_cuda(deg, sh, d)) - np_(ref.evaluate_sh_cuda(deg, sh, d))).max() <= 1e-5
+        assert np.abs(np_(cugs.evaluate_sh_backward_cuda(deg, sh, d, g)) -
+                      np_(ref.evaluate_sh_backward_cuda(deg, sh, d, g))).max() <= 1e-5
+    with pytest.raises(RuntimeError):  # test_sh.cpp:127-143
+        cugs.evaluate_sh_cuda(4, sh, d)
+    with pytest.raises(RuntimeError):
+        cugs.evaluate_sh_cuda(3, sh[:, :, :4].contiguous(), d)
+
+
+# ================================================================================================
+# 7. loss, Adam, stats
+# ================================================================================================
+@pytest.mark.parametrize("shape", [(48, 64), (123, 77), (720, 1280)])
+def test_loss_vs_reference_autograd(ref, torch, shape):
+    rng = np.random.default_rng(8)
+    H, W = shape
+    x = torch.from_numpy(rng.uniform(size=(H, W, 3)).astype(np.float32)).cuda()
+    y = torch.from_numpy(rng.uniform(size=(H, W, 3)).astype(np.float32)).cuda()
+    rl, rl1, rs, rg = ref.combined_loss_with_grad(x, y, 0.2)
+    sc, g = cugs.combined_loss_with_grad(x, y, 0.2)
+    sc = np_(sc)
+    assert abs(sc[0] - float(rl)) <= 1e-5 and abs(sc[1] - float(rl1)) <= 1e-6 and abs(sc[2] - float(rs)) <= 1e-5
+    rgn = np_(rg)
+    assert np.abs(np_(g) - rgn).max() <= 1e-3 * np.abs(rgn).max()
+    ok, msg = grad_close(np_(g), rgn)
+    assert ok, msg
+
+
+def test_loss_vs_cpu_oracle_and_known_answers(oracle, torch):  # test_loss.cpp:39-137
+    rng = np.random.default_rng(2)
+    x = rng.uniform(size=(50, 70, 3)).astype(np.float32)
+    y = rng.uniform(size=(50, 70, 3)).astype(np.float32)
+    sc, g = cugs.combined_loss_with_grad(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), 0.2)
+    osc, og = oracle.loss(x, y, 0.2)
+    assert np.allclose(np_(sc), osc, atol=1e-5)
+    assert np.abs(np_(g) - og).max() <= 1e-3 * np.abs(og).max()
+    xt = torch.from_numpy(x).cuda()
+    assert abs(float(cugs.l1_loss(xt, xt))) < 1e-7 and abs(float(cugs.ssim_mean(xt, xt)) - 1.0) < 1e-4
+    a = torch.full((16, 16, 3), 0.8, device="cuda")
+    b = torch.full((16, 16, 3), 0.3, device="cuda")
+    assert abs(float(cugs.l1_loss(a, b)) - 0.5) < 1e-5
+    with pytest.raises(RuntimeError):  # test_loss.cpp:143-170
+        cugs.combined_loss(xt[:, :, :2], xt[:, :, :2])
+    with pytest.raises(RuntimeError):
+        cugs.combined_loss(xt, xt[:10])
+    with pytest.raises(RuntimeError):
+        cugs.combined_loss(xt.double(), xt.double())
+
+
+def test_adam_vs_reference_and_torch_optim(ref, torch):  # test_fused_adam.cpp:95-225
+    scene = cugs.synth(1003, 64, 48, seed=21)
+    mine, theirs = to_torch(scene), to_torch(scene)
+    tparams = [p.clone().requires_grad_(True) for p in (mine.positions, mine.sh_coeffs, mine.opacities, mine.scales,
+                                                        mine.rotations)]
+    cfg = cugs.AdamConfig()
+    lrs = [cfg.position_lr_config.lr_init, cfg.lr_sh_coeffs, cfg.lr_opacities, cfg.lr_scales, cfg.lr_rotations]
+    topt = torch.optim.Adam([dict(params=[p], lr=lr) for p, lr in zip(tparams, lrs)], betas=(0.9, 0.999), eps=1e-15)
+    opt = cugs.FusedAdam(mine, cfg)
+    ropt = ref.FusedAdam(theirs.positions, theirs.sh_coeffs, theirs.opacities, theirs.rotations, theirs.scales)
+    rng = np.random.default_rng(1)
+    for step in range(10):
+        g = {k: torch.from_numpy(rng.normal(size=tuple(getattr(mine, k).shape)).astype(np.float32)).cuda()
+             for k in ("positions", "rotations", "scales", "opacities", "sh_coeffs")}
+        b = cugs.BackwardOutput(g["positions"], g["rotations"], g["scales"], g["opacities"], g["sh_coeffs"], None)
+        opt.update_lr(0)
+        opt.zero_grad()
+        opt.apply_gradients(b)
+        opt.step()
+        ropt.step([g["positions"], g["rotations"], g["scales"], g["opacities"], g["sh_coeffs"]], 0)
+        for p, k in zip(tparams, ("positions", "sh_coeffs", "opacities", "scales", "rotations")):
+            p.grad = g[k].clone()
+        topt.step()
+    rp = ropt.params()  # positions, sh, opacities, rotations, scales
+    for a, b_ in zip((mine.positions, mine.sh_coeffs, mine.opacities, mine.rotations, mine.scales), rp):
+        assert np.array_equal(np_(a).view(np.uint32), np_(b_).view(np.uint32)), "Adam must match k_fused_adam bit for bit"
+    for a, t in zip((mine.positions, mine.sh_coeffs, mine.opacities, mine.scales, mine.rotations), tparams):
+        assert np.allclose(np_(a), np_(t), rtol=1e-4, atol=1e-5)
+    # zero gradient with zero state leaves the parameters bit-identical (test_fused_adam.cpp:202-225)
+    fresh = to_torch(scene)
+    before = [np_(p).copy() for p in (fresh.positions, fresh.sh_coeffs)]
+    o2 = cugs.FusedAdam(fresh, cfg)
+    z = lambda t: torch.zeros_like(t)
+    o2.apply_gradients(cugs.BackwardOutput(z(fresh.positions), z(fresh.rotations), z(fresh.scales), z(fresh.opacities),
+                                           z(fresh.sh_coeffs), None))
+    o2.step()
+    assert np.array_equal(np_(fresh.positions), before[0]) and np.array_equal(np_(fresh.sh_coeffs), before[1])
+
+
+def test_accumulate_stats_vs_oracle(oracle, torch):  # test_densification.cpp:134-161
+    rng = np.random.default_rng(6)
+    n = 10_007
+    g = rng.normal(size=(n, 2)).astype(np.float32)
+    r = rng.integers(0, 4, size=n).astype(np.int32)
+    st = cugs.DensificationStats(n, "cuda")
+    acc, cnt, mx = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for _ in range(3):
+        st.accumulate_gradients(torch.from_numpy(g).cuda(), torch.from_numpy(r).cuda())
+        oracle.accumulate_stats(g, r, acc, cnt, mx)
+    assert np.allclose(np_(st.grad_accum), acc, rtol=1e-6) and np.array_equal(np_(st.grad_count), cnt)
+    assert np.array_equal(np_(st.max_radii_2d), mx)
+
+
+def test_fused_stats_in_render_backward_match_separate_kernel(torch):
+    scene, deg = get_scene("small")
+    m = to_torch(scene)
+    settings = cugs.RenderSettings((0, 0, 0), deg, 1.0)
+    out = cugs.render(m, scene.camera, settings)
+    g = _dL(torch, scene)
+    fused = cugs.DensificationStats(scene.n, "cuda")
+    b = cugs.render_backward(g, out, m, scene.camera, settings, stats=fused.as_tuple())
+    sep = cugs.DensificationStats(scene.n, "cuda")
+    sep.accumulate_gradients(b.dL_dmeans_2d, out.radii)
+    assert np.array_equal(np_(fused.grad_accum), np_(sep.grad_accum))
+    assert np.array_equal(np_(fused.grad_count), np_(sep.grad_count))
+    assert np.array_equal(np_(fused.max_radii_2d), np_(sep.max_radii_2d))
+
+
+# ================================================================================================
+# full-size (BASELINE config B: 3M Gaussians, 1080p) — versus the reference on the same GPU and
+# through size-independent properties
+# ================================================================================================
+def test_config_B_full_size(ref, torch):
+    scene = cugs.synth(3_000_000, 1920, 1080, seed=1236)
+    deg, bg = 3, (0.0, 0.0, 0.0)
+    m, r = ref_render(ref, torch, scene, deg, bg)
+    settings = cugs.RenderSettings(bg, deg, 1.0)
+    out = cugs.render(m, scene.camera, settings)
+    keys_ok = torch.equal(out.gaussian_indices, r[9]) and torch.equal(out.tile_ranges, r[10])
+    assert keys_ok, "sort order / tile ranges must be bit-exact at 3M"
+    assert torch.equal(out.radii, r[6]) and torch.equal(out.n_contrib, r[2])
+    assert float((out.color - r[0]).abs().max()) <= IMG_TOL
+    # properties: ranges partition [0,P), pairs inside a tile are depth-sorted
+    P = int(out.gaussian_indices.numel())
+    rg = out.tile_ranges.long()
+    assert int((rg[:, 1] - rg[:, 0]).sum()) == P
+    d = out.depths[out.gaussian_indices.long()]
+    tile_of = torch.repeat_interleave(torch.arange(rg.shape[0], device="cuda"), (rg[:, 1] - rg[:, 0]))
+    same = tile_of[1:] == tile_of[:-1]
+    assert bool(((d[1:] >= d[:-1]) | ~same).all())
+    g = _dL(torch, scene)
+    rb = ref.render_backward(g, r, m.positions, m.sh_coeffs, m.opacities, m.rotations, m.scales,
+                             scene.camera.as_ref_list(), list(bg), deg, 1.0)
+    b = cugs.render_backward(g, out, m, scene.camera, settings)
+    for nm, rt in zip(["dL_dpositions", "dL_drotations", "dL_dscales", "dL_dopacities", "dL_dsh_coeffs", "dL_dmeans_2d"], rb):
+        mine_t = getattr(b, nm).double()
+        ref_t = rt.double()
+        rel = float((mine_t - ref_t).norm() / ref_t.norm())
+        assert rel <= GRAD_REL, f"{nm}: norm-rel {rel:.3e}"
+
+
+def test_full_size_properties_without_reference(torch):
+    """Size-independent properties at 1M / 1080p that need no oracle."""
+    scene = cugs.synth(1_000_000, 1920, 1080, seed=1237)
+    m = to_torch(scene)
+    out = cugs.render(m, scene.camera, cugs.RenderSettings((0, 0, 0), 3, 1.0))
+    P = int(out.gaussian_indices.numel())
+    rg = out.tile_ranges.long()
+    assert int((rg[:, 1] - rg[:, 0]).sum()) == P
+    assert bool((out.final_T >= 0).all()) and bool((out.final_T <= 1).all())
+    assert bool(torch.isfinite(out.color).all())
+    # idempotence: rendering twice gives bit-identical images (the forward has no atomics)
+    c1 = out.color.clone()
+    out2 = cugs.render(m, scene.camera, cugs.RenderSettings((0, 0, 0), 3, 1.0))
+    assert torch.equal(c1, out2.color)
