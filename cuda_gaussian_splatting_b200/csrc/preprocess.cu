@@ -54,7 +54,9 @@ __device__ __forceinline__ void quat_rotation(float w, float x, float y, float z
     const float n2 = add_rn(fma_rn(z, z, fma_rn(y, y, fma_rn(w, w, mul_rn(x, x)))), 1e-12f);
     inv_norm = rsqrtf(n2);
     w = mul_rn(w, inv_norm); x = mul_rn(x, inv_norm); y = mul_rn(y, inv_norm); z = mul_rn(z, inv_norm);
-    R[0] = fma_rn(-2.0f, dot2c(y, y, z, z), 1.0f);
+    // nvcc shares y*y and z*z with R[4] / R[8]: in R[0] BOTH products are rounded (sm_100 SASS of
+    // k_project_gaussians: FMUL yy, FMUL zz, FADD), in R[4] / R[8] the x*x product is fused.
+    R[0] = fma_rn(-2.0f, add_rn(mul_rn(y, y), mul_rn(z, z)), 1.0f);
     R[1] = mul_rn(2.0f, fma_rn(x, y, -mul_rn(w, z)));
     R[2] = mul_rn(2.0f, dot2c(x, z, w, y));
     R[3] = mul_rn(2.0f, dot2c(x, y, w, z));
@@ -75,9 +77,10 @@ __device__ __forceinline__ void covariance_chain(const ViewParams& vp, const flo
 #pragma unroll
         for (int j = 0; j < 3; ++j) f.M[i * 3 + j] = mul_rn(f.R[i * 3 + j], f.s[j]);
     const float* M = f.M;
-    f.cov3[0] = dot3c(M[0], M[0], M[1], M[1], M[2], M[2]);
+    // which product of each 3-term sum is rounded separately is read off the reference's SASS
+    f.cov3[0] = dot3c(M[1], M[1], M[0], M[0], M[2], M[2]);
     f.cov3[1] = dot3c(M[0], M[3], M[1], M[4], M[2], M[5]);
-    f.cov3[2] = dot3c(M[0], M[6], M[1], M[7], M[2], M[8]);
+    f.cov3[2] = dot3c(M[1], M[7], M[0], M[6], M[2], M[8]);
     f.cov3[3] = dot3c(M[3], M[3], M[4], M[4], M[5], M[5]);
     f.cov3[4] = dot3c(M[3], M[6], M[4], M[7], M[5], M[8]);
     f.cov3[5] = dot3c(M[6], M[6], M[7], M[7], M[8], M[8]);

@@ -213,9 +213,10 @@ struct AdamGroups {
 
 __device__ __forceinline__ void adam_element(float& p, float g, float& m, float& v, float lr, float b1,
                                              float b2, float eps, float bc1, float bc2) {
-    // fused_adam.cu:57-75 with nvcc's contraction spelled out
-    const float mi = fma_rn(b1, m, mul_rn(add_rn(1.0f, -b1), g));
-    const float vi = fma_rn(b2, v, mul_rn(mul_rn(add_rn(1.0f, -b2), g), g));
+    // fused_adam.cu:57-75 with the contraction nvcc 12.9 applies to the reference spelled out
+    // (SASS of k_fused_adam for sm_100: FMUL b1*m, FFMA g*(1-b1)+.; FMUL (1-b2)*g, FMUL b2*v, FFMA)
+    const float mi = fma_rn(g, add_rn(1.0f, -b1), mul_rn(b1, m));
+    const float vi = fma_rn(g, mul_rn(add_rn(1.0f, -b2), g), mul_rn(b2, v));
     m = mi;
     v = vi;
     const float m_hat = mul_rn(mi, bc1), v_hat = mul_rn(vi, bc2);

@@ -64,7 +64,8 @@ static void quat_to_rotation(float w, float x, float y, float z, float R[9], flo
     float inv_norm = 1.0f / sqrtf(n2); /* GPU: rsqrtf (approx, <=1ulp off) */
     w *= inv_norm; x *= inv_norm; y *= inv_norm; z *= inv_norm;
     if (inv_norm_out) *inv_norm_out = inv_norm;
-    R[0] = fmaf(-2.0f, dot2c(y, y, z, z), 1.0f);
+    /* nvcc shares y*y and z*z with R[4], R[8]: here both products are rounded (sm_100 SASS) */
+    R[0] = fmaf(-2.0f, y * y + z * z, 1.0f);
     R[1] = 2.0f * fmaf(x, y, -(w * z));
     R[2] = 2.0f * dot2c(x, z, w, y);
     R[3] = 2.0f * dot2c(x, y, w, z);
@@ -82,9 +83,9 @@ static void compute_cov3d(const float ls[3], const float q[4], float cov[6], flo
     quat_to_rotation(q[0], q[1], q[2], q[3], R, inv_norm);
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) M[i * 3 + j] = R[i * 3 + j] * s[j];
-    cov[0] = dot3c(M[0], M[0], M[1], M[1], M[2], M[2]);
+    cov[0] = dot3c(M[1], M[1], M[0], M[0], M[2], M[2]); /* M0*M0 is the rounded product (SASS) */
     cov[1] = dot3c(M[0], M[3], M[1], M[4], M[2], M[5]);
-    cov[2] = dot3c(M[0], M[6], M[1], M[7], M[2], M[8]);
+    cov[2] = dot3c(M[1], M[7], M[0], M[6], M[2], M[8]); /* M0*M6 is the rounded product (SASS) */
     cov[3] = dot3c(M[3], M[3], M[4], M[4], M[5], M[5]);
     cov[4] = dot3c(M[3], M[6], M[4], M[7], M[5], M[8]);
     cov[5] = dot3c(M[6], M[6], M[7], M[7], M[8], M[8]);
@@ -741,9 +742,10 @@ void oracle_adam(int64_t n, float* p, const float* g, float* m, float* v, float 
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
         float gi = g[i];
-        float mi = fmaf(b1, m[i], (1.0f - b1) * gi);
+        /* contraction nvcc 12.9 applies to fused_adam.cu:62-67 (read off the sm_100 SASS) */
+        float mi = fmaf(gi, 1.0f - b1, b1 * m[i]);
         m[i] = mi;
-        float vi = fmaf(b2, v[i], (1.0f - b2) * gi * gi);
+        float vi = fmaf(gi, (1.0f - b2) * gi, b2 * v[i]);
         v[i] = vi;
         float mh = mi * bc1, vh = vi * bc2;
         p[i] -= lr * mh / (sqrtf(vh) + eps);

@@ -177,7 +177,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("project_backward", &ref_project_backward);
     m.def("render", &ref_render);
     m.def("render_backward", &ref_render_backward);
-    m.def("combined_loss_with_grad", &ref_combined_loss_with_grad);
+    m.def("combined_loss_with_grad", &ref_combined_loss_with_grad,
+          py::call_guard<py::gil_scoped_release>());  // autograd must not run under the GIL
     m.def("evaluate_sh_cuda", &cugs::evaluate_sh_cuda);
     m.def("evaluate_sh_cpu", &cugs::evaluate_sh_cpu);
     m.def("evaluate_sh_backward_cuda", &cugs::evaluate_sh_backward_cuda);
