@@ -3,30 +3,33 @@
 // Forward  replaces k_rasterize_forward  (reference rasterizer/forward.cu:48-174).
 // Backward replaces k_rasterize_backward (reference rasterizer/backward.cu:31-233).
 //
-// Design (B200):
-//  * one CTA (256 threads) per tile; a warp owns a compact 8x4 pixel patch (not 2 rows of 16), so
-//    that the lanes of a warp reject / accept the same Gaussians and finish together;
-//  * Gaussians are staged in batches of 256 through a 2-deep shared-memory ring. Each thread
-//    gathers ONE 48-byte packed record {x,y,a,b | c,thr,op,r | g,b,-,-} (written by preprocess)
-//    with three 16-byte cp.async (LDGSTS) copies — no register staging, one or two sectors per
-//    Gaussian instead of nine scalar loads from four arrays — and the gather of batch k+1 overlaps
-//    the blending of batch k;
-//  * per evaluation the hot path is 2 broadcast LDS + 9 FP32 ops + 2 compares: `power` is computed
-//    with the reference's exact rounding, and compared against a per-Gaussian conservative bound
-//    thr = -log(255*op) - 1e-4 so that the accurate expf (11 instructions + MUFU) only runs for
-//    evaluations that can contribute. Those take the exact path: same expf, same comparisons, same
-//    rounding of T as the reference, so n_contrib and final_T are bit-identical;
-//  * early termination: per-warp vote on `done`, per-CTA __syncthreads_and between batches;
-//  * backward: the warp walks the range back to front in lock step, sums the nine per-Gaussian
-//    gradient terms across its 32 pixels with shuffles, and lane 0 issues two 128-bit vector
-//    reductions + one scalar reduction (red.global.add.v4.f32) per (warp, Gaussian) — instead of
-//    nine scalar atomics per (pixel, Gaussian).
+// Both kernels are instruction-issue bound (ncu: >80 % issue-active, <5 % DRAM), so the design
+// minimises instructions per (pixel, Gaussian) evaluation:
+//  * one CTA of 64 threads (2 warps) per tile; a thread owns FOUR horizontally adjacent pixels, a
+//    warp a 16x8 patch. The Gaussian record is read from shared memory once per thread (2
+//    broadcast LDS.128) for four evaluations, the dy-terms of `power` are shared by the four
+//    pixels, and the four independent dependency chains give the ILP a 2-warp CTA needs;
+//  * Gaussians are staged in batches of 128 through a 2-deep shared-memory ring of 48-byte packed
+//    records {x,y,a,b | c,thr,op,r | g,b,-,-} (written by preprocess) with 16-byte cp.async
+//    (LDGSTS) copies; the gather of batch k+1 overlaps the blending of batch k;
+//  * `power` is computed with the reference's exact rounding and compared against a per-Gaussian
+//    conservative bound thr = -log(255*op) - 1e-4: the accurate expf (11 instructions + MUFU) only
+//    runs for evaluations that can reach alpha >= 1/255. Those take the exact path (same expf,
+//    same comparisons, same rounding of T as the reference), so n_contrib / final_T are
+//    bit-identical to the reference;
+//  * early termination: per-warp vote every 8 Gaussians, per-CTA __syncthreads_and per batch;
+//  * backward: a thread first sums the nine per-Gaussian gradient terms over its own four pixels
+//    in registers, then the warp reduces them with a multi-value butterfly (8 values in 7
+//    shuffle steps + 1 value in 5, instead of 9 x 5), and 9 lanes issue ONE coalesced
+//    red.global.add.f32 to the 9 consecutive floats of the Gaussian's packed gradient record —
+//    instead of the reference's nine scalar atomics per (pixel, Gaussian).
 #include "common.cuh"
 
 namespace cugs {
 
-constexpr int kBlendThreads = 256;
-constexpr int kBatch = 256;  // Gaussians per staged batch (one per thread)
+constexpr int kBlendThreads = 64;
+constexpr int kPix = 4;      // pixels per thread (one row segment)
+constexpr int kBatch = 128;  // Gaussians per staged batch (two per thread)
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kTMin = 1.0f / 255.0f;  // forward.cuh:25-31 kTransmittanceThreshold
 
@@ -44,20 +47,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c),
-                 "f"(d)
-                 : "memory");
-}
-
-// The reference's `power`, rounding for rounding (SURVEY A.10; forward.cu:131-132 and
-// backward.cu:132-133 compile to the same sequence).
-__device__ __forceinline__ float blend_power(float dx, float dy, float a, float b, float c) {
-    const float s1 = fma_rn(dx, a, mul_rn(dy, b));
-    const float s2 = fma_rn(dx, b, mul_rn(dy, c));
-    return mul_rn(fma_rn(dx, s1, mul_rn(dy, s2)), -0.5f);
 }
 
 // Stage one Gaussian of the batch into shared memory.
@@ -82,10 +71,22 @@ __device__ __forceinline__ void stage_gaussian(StagedGaussian* dst, int g, const
     }
 }
 
-__device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px, int& py) {
+// thread -> its four pixels: lane = (row-in-warp << 2) | column-group; warp w covers rows 8w..8w+7
+__device__ __forceinline__ void pixels_of_thread(int tile_x, int tile_y, int& px0, int& py) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    px = tile_x * kTile + (warp & 1) * 8 + (lane & 7);
-    py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
+    px0 = tile_x * kTile + (lane & 3) * kPix;
+    py = tile_y * kTile + warp * 8 + (lane >> 2);
+}
+
+// The reference's `power`, rounding for rounding (SURVEY A.10; forward.cu:131-132 and
+// backward.cu:132-133 compile to the same sequence):
+//   s1 = fma(dx, a, dy*b); s2 = fma(dx, b, dy*c); power = (fma(dx, s1, dy*s2)) * -0.5
+// dyb = rn(dy*b) and dyc = rn(dy*c) are shared by the four pixels of a thread (same row).
+__device__ __forceinline__ float blend_power4(float dx, float dy, float a, float b, float dyb, float dyc,
+                                              float& s1, float& s2) {
+    s1 = fma_rn(dx, a, dyb);
+    s2 = fma_rn(dx, b, dyc);
+    return mul_rn(fma_rn(dx, s1, mul_rn(dy, s2)), -0.5f);
 }
 
 // ================================================================================================
@@ -103,37 +104,54 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
 
     const int tile = blockIdx.x;
     const int tile_x = tile % ntx, tile_y = tile / ntx;
-    int px, py;
-    pixel_of_thread(tile_x, tile_y, px, py);
-    const bool inside = (px < width) && (py < height);
-    const float pxf = (float)px + 0.5f, pyf = (float)py + 0.5f;  // forward.cu:72-73
+    int px0, py;
+    pixels_of_thread(tile_x, tile_y, px0, py);
+    const float pyf = (float)py + 0.5f;  // forward.cu:72-73
+    float pxf[kPix];
+    bool done[kPix];
+#pragma unroll
+    for (int k = 0; k < kPix; ++k) {
+        pxf[k] = (float)(px0 + k) + 0.5f;
+        done[k] = !((px0 + k < width) && (py < height));
+    }
 
     const int2 range = reinterpret_cast<const int2*>(tile_ranges)[tile];
     const int count = range.y - range.x;
     const int nb = (count + kBatch - 1) / kBatch;
 
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    int contrib = 0;
-    bool done = !inside;
+    float T[kPix], C0[kPix], C1[kPix], C2[kPix];
+    int contrib[kPix];
+#pragma unroll
+    for (int k = 0; k < kPix; ++k) { T[k] = 1.0f; C0[k] = C1[k] = C2[k] = 0.0f; contrib[k] = 0; }
 
-    // prologue: gather batch 0, prefetch the index of batch 1
-    int next_idx = -1;
+    // prologue: gather batch 0, prefetch the indices of batch 1
+    int next_idx[2] = {-1, -1};
     if (nb > 0) {
-        const int li = range.x + threadIdx.x;
-        if (li < range.y) stage_gaussian<kPacked>(&s_g[0][threadIdx.x], gaussian_idx[li], packed, means_2d, conic, rgb, opa);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int li = range.x + threadIdx.x + u * kBlendThreads;
+            if (li < range.y)
+                stage_gaussian<kPacked>(&s_g[0][threadIdx.x + u * kBlendThreads], gaussian_idx[li], packed,
+                                        means_2d, conic, rgb, opa);
+            const int li1 = li + kBatch;
+            if (li1 < range.y) next_idx[u] = gaussian_idx[li1];
+        }
         cp_async_commit();
-        const int li1 = li + kBatch;
-        if (li1 < range.y) next_idx = gaussian_idx[li1];
     }
 
     for (int b = 0; b < nb; ++b) {
         // issue the gather of batch b+1 into the other buffer (its previous reader, batch b-1,
         // finished before the __syncthreads_and at the end of the previous iteration)
         if (b + 1 < nb) {
-            if (next_idx >= 0) stage_gaussian<kPacked>(&s_g[(b + 1) & 1][threadIdx.x], next_idx, packed, means_2d, conic, rgb, opa);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (next_idx[u] >= 0)
+                    stage_gaussian<kPacked>(&s_g[(b + 1) & 1][threadIdx.x + u * kBlendThreads], next_idx[u],
+                                            packed, means_2d, conic, rgb, opa);
+                const int li2 = range.x + (b + 2) * kBatch + threadIdx.x + u * kBlendThreads;
+                next_idx[u] = (li2 < range.y) ? gaussian_idx[li2] : -1;
+            }
             cp_async_commit();
-            const int li2 = range.x + (b + 2) * kBatch + threadIdx.x;
-            next_idx = (li2 < range.y) ? gaussian_idx[li2] : -1;
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
@@ -142,53 +160,97 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
 
         const StagedGaussian* sg = s_g[b & 1];
         const int bc = min(kBatch, count - b * kBatch);
-        for (int j0 = 0; j0 < bc; j0 += 16) {
-            if (__all_sync(kFull, done)) break;
-            const int j1 = min(j0 + 16, bc);
+        for (int j0 = 0; j0 < bc; j0 += 8) {
+            if (__all_sync(kFull, done[0] && done[1] && done[2] && done[3])) break;
+            const int j1 = min(j0 + 8, bc);
             for (int j = j0; j < j1; ++j) {
                 const float4 q0 = sg[j].q0;
                 const float2 ct = *reinterpret_cast<const float2*>(&sg[j].q1);
-                const float dx = pxf - q0.x, dy = pyf - q0.y;
-                const float power = blend_power(dx, dy, q0.z, q0.w, ct.x);
-                // cheap reject: cannot reach alpha >= 1/255 (NaNs fall through to the exact path)
-                if (done || power < ct.y || power > 0.0f) continue;
+                const float dy = pyf - q0.y;
+                const float dyb = mul_rn(dy, q0.w), dyc = mul_rn(dy, ct.x);
+                float power[kPix];
+                bool pass[kPix];
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < kPix; ++k) {
+                    float s1, s2;
+                    power[k] = blend_power4(pxf[k] - q0.x, dy, q0.z, q0.w, dyb, dyc, s1, s2);
+                    // cheap reject: cannot reach alpha >= 1/255 (NaNs fall through to the exact path)
+                    pass[k] = !(done[k] || power[k] < ct.y || power[k] > 0.0f);
+                    any |= pass[k];
+                }
+                if (!any) continue;
                 const float2 orr = *reinterpret_cast<const float2*>(&sg[j].q1.z);  // opacity, r
-                const float alpha = fminf(mul_rn(orr.x, expf(power)), 0.99f);       // forward.cu:137-140
-                if (alpha < kAlphaMin) continue;
                 const float2 gb = *reinterpret_cast<const float2*>(&sg[j].q2);
-                const float w = mul_rn(alpha, T);
-                C0 = fma_rn(w, orr.y, C0);
-                C1 = fma_rn(w, gb.x, C1);
-                C2 = fma_rn(w, gb.y, C2);
-                T = mul_rn(T, add_rn(1.0f, -alpha));
-                ++contrib;
-                if (T < kTMin) done = true;  // the crossing Gaussian is composited (forward.cu:153)
+#pragma unroll
+                for (int k = 0; k < kPix; ++k) {
+                    if (!pass[k]) continue;
+                    const float alpha = fminf(mul_rn(orr.x, expf(power[k])), 0.99f);  // forward.cu:137-140
+                    if (alpha < kAlphaMin) continue;
+                    const float w = mul_rn(alpha, T[k]);
+                    C0[k] = fma_rn(w, orr.y, C0[k]);
+                    C1[k] = fma_rn(w, gb.x, C1[k]);
+                    C2[k] = fma_rn(w, gb.y, C2[k]);
+                    T[k] = mul_rn(T[k], add_rn(1.0f, -alpha));
+                    ++contrib[k];
+                    if (T[k] < kTMin) done[k] = true;  // the crossing Gaussian is composited (forward.cu:153)
+                }
             }
         }
-        if (__syncthreads_and(done)) break;
+        if (__syncthreads_and(done[0] && done[1] && done[2] && done[3])) break;
     }
     cp_async_wait<0>();
 
-    if (inside) {
-        const int64_t pi = (int64_t)py * width + px;
-        out_color[pi * 3 + 0] = fma_rn(T, bg_r, C0);  // forward.cu:166-168
-        out_color[pi * 3 + 1] = fma_rn(T, bg_g, C1);
-        out_color[pi * 3 + 2] = fma_rn(T, bg_b, C2);
-        out_T[pi] = T;
-        out_n[pi] = contrib;
+    if (py < height) {
+#pragma unroll
+        for (int k = 0; k < kPix; ++k) {
+            if (px0 + k >= width) continue;
+            const int64_t pi = (int64_t)py * width + px0 + k;
+            out_color[pi * 3 + 0] = fma_rn(T[k], bg_r, C0[k]);  // forward.cu:166-168
+            out_color[pi * 3 + 1] = fma_rn(T[k], bg_g, C1[k]);
+            out_color[pi * 3 + 2] = fma_rn(T[k], bg_b, C2[k]);
+            out_T[pi] = T[k];
+            out_n[pi] = contrib[k];
+        }
     }
 }
 
 // ================================================================================================
 // backward
 // ================================================================================================
-__device__ __forceinline__ float warp_sum(float v) {
-    v += __shfl_xor_sync(kFull, v, 16);
-    v += __shfl_xor_sync(kFull, v, 8);
-    v += __shfl_xor_sync(kFull, v, 4);
-    v += __shfl_xor_sync(kFull, v, 2);
-    v += __shfl_xor_sync(kFull, v, 1);
-    return v;
+// Sum v[0..8] over the 32 lanes of the warp. On return lane 4*i (i = 0..7) holds the total of
+// v[i] in `r`, and every lane holds the total of v[8] in `r8`.
+__device__ __forceinline__ void warp_reduce9(const float (&v)[9], int lane, float& r, float& r8) {
+    // 8 values: after the xor-16 / xor-8 / xor-4 exchanges a lane keeps 4, 2, 1 partial sums
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float w4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = b4 ? v[i + 4] : v[i];
+        const float send = b4 ? v[i] : v[i + 4];
+        w4[i] = keep + __shfl_xor_sync(kFull, send, 16);
+    }
+    float w2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = b3 ? w4[i + 2] : w4[i];
+        const float send = b3 ? w4[i] : w4[i + 2];
+        w2[i] = keep + __shfl_xor_sync(kFull, send, 8);
+    }
+    {
+        const float keep = b2 ? w2[1] : w2[0];
+        const float send = b2 ? w2[0] : w2[1];
+        r = keep + __shfl_xor_sync(kFull, send, 4);
+    }
+    r += __shfl_xor_sync(kFull, r, 2);
+    r += __shfl_xor_sync(kFull, r, 1);
+    // now lanes with (b4,b3,b2) = bits hold value index 4*b4 + 2*b3 + b2
+    r8 = v[8];
+    r8 += __shfl_xor_sync(kFull, r8, 16);
+    r8 += __shfl_xor_sync(kFull, r8, 8);
+    r8 += __shfl_xor_sync(kFull, r8, 4);
+    r8 += __shfl_xor_sync(kFull, r8, 2);
+    r8 += __shfl_xor_sync(kFull, r8, 1);
 }
 
 template <bool kPacked>
@@ -205,10 +267,9 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
 
     const int tile = blockIdx.x;
     const int tile_x = tile % ntx, tile_y = tile / ntx;
-    int px, py;
-    pixel_of_thread(tile_x, tile_y, px, py);
-    const bool inside = (px < width) && (py < height);
-    const float pxf = (float)px + 0.5f, pyf = (float)py + 0.5f;
+    int px0, py;
+    pixels_of_thread(tile_x, tile_y, px0, py);
+    const float pyf = (float)py + 0.5f;
     const int lane = threadIdx.x & 31;
 
     const int2 range = reinterpret_cast<const int2*>(tile_ranges)[tile];
@@ -216,39 +277,50 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
     const int nb = (count + kBatch - 1) / kBatch;
 
     // per-pixel forward outputs (backward.cu:65-87)
-    float T = 0.0f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    int maxc = 0;
-    if (inside) {
-        const int64_t pi = (int64_t)py * width + px;
-        T = final_T[pi];
-        maxc = n_contrib[pi];
-        g0 = dL_dcolor[pi * 3 + 0];
-        g1 = dL_dcolor[pi * 3 + 1];
-        g2 = dL_dcolor[pi * 3 + 2];
+    float pxf[kPix], T[kPix], g0[kPix], g1[kPix], g2[kPix], S0[kPix], S1[kPix], S2[kPix];
+    int left[kPix];  // contributors still to process; <= 0 means the pixel is done
+#pragma unroll
+    for (int k = 0; k < kPix; ++k) {
+        pxf[k] = (float)(px0 + k) + 0.5f;
+        T[k] = 0.0f; g0[k] = g1[k] = g2[k] = 0.0f; left[k] = 0;
+        if (px0 + k < width && py < height) {
+            const int64_t pi = (int64_t)py * width + px0 + k;
+            T[k] = final_T[pi];
+            left[k] = n_contrib[pi];
+            g0[k] = dL_dcolor[pi * 3 + 0];
+            g1[k] = dL_dcolor[pi * 3 + 1];
+            g2[k] = dL_dcolor[pi * 3 + 2];
+        }
+        S0[k] = T[k] * bg_r; S1[k] = T[k] * bg_g; S2[k] = T[k] * bg_b;
     }
-    float S0 = T * bg_r, S1 = T * bg_g, S2 = T * bg_b;
-    int found = 0;
-    bool done = !inside || maxc <= 0;
 
     // batches are visited last to first; batch b covers [range.x + b*kBatch, ...)
-    int next_idx = -1;
+    int next_idx[2] = {-1, -1};
     if (nb > 0) {
-        const int li = range.x + (nb - 1) * kBatch + threadIdx.x;
-        if (li < range.y) {
-            const int g = gaussian_idx[li];
-            s_idx[(nb - 1) & 1][threadIdx.x] = g;
-            stage_gaussian<kPacked>(&s_g[(nb - 1) & 1][threadIdx.x], g, packed, means_2d, conic, rgb, opa);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int t = threadIdx.x + u * kBlendThreads;
+            const int li = range.x + (nb - 1) * kBatch + t;
+            if (li < range.y) {
+                const int g = gaussian_idx[li];
+                s_idx[(nb - 1) & 1][t] = g;
+                stage_gaussian<kPacked>(&s_g[(nb - 1) & 1][t], g, packed, means_2d, conic, rgb, opa);
+            }
+            if (nb > 1) next_idx[u] = gaussian_idx[li - kBatch];  // batch nb-2 is always full
         }
         cp_async_commit();
-        if (nb > 1) next_idx = gaussian_idx[li - kBatch];  // batch nb-2 is always full
     }
 
     for (int b = nb - 1; b >= 0; --b) {
         if (b > 0) {
-            s_idx[(b - 1) & 1][threadIdx.x] = next_idx;
-            stage_gaussian<kPacked>(&s_g[(b - 1) & 1][threadIdx.x], next_idx, packed, means_2d, conic, rgb, opa);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int t = threadIdx.x + u * kBlendThreads;
+                s_idx[(b - 1) & 1][t] = next_idx[u];
+                stage_gaussian<kPacked>(&s_g[(b - 1) & 1][t], next_idx[u], packed, means_2d, conic, rgb, opa);
+                if (b > 1) next_idx[u] = gaussian_idx[range.x + (b - 2) * kBatch + t];
+            }
             cp_async_commit();
-            if (b > 1) next_idx = gaussian_idx[range.x + (b - 2) * kBatch + threadIdx.x];
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
@@ -259,59 +331,79 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
         const int* sid = s_idx[b & 1];
         const int bc = min(kBatch, count - b * kBatch);
         for (int j = bc - 1; j >= 0; --j) {
-            if ((j & 7) == 7 && __all_sync(kFull, done)) break;
+            if ((j & 7) == 7 && __all_sync(kFull, (left[0] <= 0) && (left[1] <= 0) && (left[2] <= 0) && (left[3] <= 0)))
+                break;
             const float4 q0 = sg[j].q0;
             const float4 q1 = sg[j].q1;
-            const float dx = pxf - q0.x, dy = pyf - q0.y;
             const float a = q0.z, bq = q0.w, c = q1.x;
-            const float power = blend_power(dx, dy, a, bq, c);
-            bool hit = false;
-            float ex = 0.f, alpha = 0.f;
-            if (!(done || power < q1.y || power > 0.0f)) {
-                ex = expf(power);
-                alpha = fminf(mul_rn(q1.z, ex), 0.99f);
-                hit = !(alpha < kAlphaMin);
+            const float dy = pyf - q0.y;
+            const float dyb = mul_rn(dy, bq), dyc = mul_rn(dy, c);
+            float power[kPix], dx[kPix], s1[kPix], s2[kPix];
+            bool pass[kPix];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < kPix; ++k) {
+                dx[k] = pxf[k] - q0.x;
+                power[k] = blend_power4(dx[k], dy, a, bq, dyb, dyc, s1[k], s2[k]);
+                pass[k] = !(left[k] <= 0 || power[k] < q1.y || power[k] > 0.0f);
+                any |= pass[k];
             }
-            if (hit) {
-                ++found;
-                if (found > maxc) { done = true; hit = false; }  // backward.cu:141-145
-            }
-            if (!__any_sync(kFull, hit)) continue;
+            if (!__any_sync(kFull, any)) continue;
 
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f;
-            if (hit) {
+            float v[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) v[q] = 0.0f;
+            if (any) {
                 const float2 gb = *reinterpret_cast<const float2*>(&sg[j].q2);
                 const float cr = q1.w, cg = gb.x, cb = gb.y;
-                const float oma = fmaxf(1.0f - alpha, 1e-5f);  // backward.cu:150-151
-                T = T / oma;
-                const float w = alpha * T;
-                v0 = g0 * w; v1 = g1 * w; v2 = g2 * w;
-                float dLa = 0.0f;
-                dLa += g0 * (T * cr - S0 / oma);
-                dLa += g1 * (T * cg - S1 / oma);
-                dLa += g2 * (T * cb - S2 / oma);
-                S0 += w * cr; S1 += w * cg; S2 += w * cb;
-                const bool clamped = (q1.z * ex >= 0.99f);
-                const float dLp = clamped ? 0.0f : dLa * alpha;
-                v3 = clamped ? 0.0f : dLa * ex;
-                v4 = dLp * (a * dx + bq * dy);
-                v5 = dLp * (bq * dx + c * dy);
-                v6 = dLp * (-0.5f * dx * dx);
-                v7 = dLp * (-dx * dy);
-                v8 = dLp * (-0.5f * dy * dy);
-                if (found == maxc) done = true;  // nothing left for this pixel
+                float m_dx = 0.f, m_xx = 0.f;  // sum dLp*dx, sum dLp*dx*dx ; dy is common to the 4 pixels
+                float m_p = 0.f;               // sum dLp
+#pragma unroll
+                for (int k = 0; k < kPix; ++k) {
+                    if (!pass[k]) continue;
+                    const float ex = expf(power[k]);
+                    const float oe = mul_rn(q1.z, ex);
+                    const float alpha = fminf(oe, 0.99f);
+                    if (alpha < kAlphaMin) continue;       // backward.cu:137-139
+                    --left[k];                              // found++ ; found > n_contrib -> stop (:141-145)
+                    const float oma = fmaxf(1.0f - alpha, 1e-5f);  // backward.cu:150-151
+                    const float inv = 1.0f / oma;
+                    T[k] = T[k] * inv;
+                    const float w = alpha * T[k];
+                    v[0] = fmaf(g0[k], w, v[0]);
+                    v[1] = fmaf(g1[k], w, v[1]);
+                    v[2] = fmaf(g2[k], w, v[2]);
+                    // dL/dalpha = sum_c dL/dC_c * (T*rgb_c - S_c/oma)   (backward.cu:166-168)
+                    const float gc = g0[k] * cr + g1[k] * cg + g2[k] * cb;
+                    const float gs = g0[k] * S0[k] + g1[k] * S1[k] + g2[k] * S2[k];
+                    const float dLa = T[k] * gc - inv * gs;
+                    S0[k] = fmaf(w, cr, S0[k]);
+                    S1[k] = fmaf(w, cg, S1[k]);
+                    S2[k] = fmaf(w, cb, S2[k]);
+                    const bool clamped = (oe >= 0.99f);      // backward.cu:178-190
+                    const float dLp = clamped ? 0.0f : dLa * alpha;
+                    v[3] += clamped ? 0.0f : dLa * ex;
+                    v[4] = fmaf(dLp, s1[k], v[4]);           // a*dx + b*dy
+                    v[5] = fmaf(dLp, s2[k], v[5]);           // b*dx + c*dy
+                    const float pdx = dLp * dx[k];
+                    m_p += dLp;
+                    m_dx += pdx;
+                    m_xx = fmaf(pdx, dx[k], m_xx);
+                }
+                v[6] = -0.5f * m_xx;            // sum dLp * (-0.5 dx^2)
+                v[7] = -(m_dx * dy);            // sum dLp * (-dx dy)
+                v[8] = -0.5f * (m_p * dy * dy); // sum dLp * (-0.5 dy^2)
             }
-            v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
-            v3 = warp_sum(v3); v4 = warp_sum(v4); v5 = warp_sum(v5);
-            v6 = warp_sum(v6); v7 = warp_sum(v7); v8 = warp_sum(v8);
-            if (lane == 0) {
-                float* acc = grad_acc + (int64_t)sid[j] * 12;
-                red_add_v4(acc, v0, v1, v2, v3);
-                red_add_v4(acc + 4, v4, v5, v6, v7);
-                atomicAdd(acc + 8, v8);
+            float r, r8;
+            warp_reduce9(v, lane, r, r8);
+            // lanes 0,4,...,28 hold v0..v7; lane 1 takes v8: nine lanes, nine consecutive floats
+            const bool writer = ((lane & 3) == 0) || (lane == 1);
+            if (writer) {
+                const int slot = (lane == 1) ? 8 : (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1));
+                atomicAdd(grad_acc + (int64_t)sid[j] * 12 + slot, (lane == 1) ? r8 : r);
             }
         }
-        if (__syncthreads_and(done)) break;
+        if (__syncthreads_and((left[0] <= 0) && (left[1] <= 0) && (left[2] <= 0) && (left[3] <= 0))) break;
     }
     cp_async_wait<0>();
 }
