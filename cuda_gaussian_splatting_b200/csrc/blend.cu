@@ -17,6 +17,11 @@
 //    runs for evaluations that can reach alpha >= 1/255. Those take the exact path (same expf,
 //    same comparisons, same rounding of T as the reference), so n_contrib / final_T are
 //    bit-identical to the reference;
+//  * per-warp list compaction: at the start of a batch every warp tests the 128 staged Gaussians
+//    against ITS 16x8 pixel patch (conservative footprint box {hx,hy} carried in the record) with
+//    four ballots and keeps an ordered list of the survivors in shared memory; the inner loop
+//    only visits those (44 % of the (patch, Gaussian) pairs are dropped on the synthetic scenes)
+//    — dropping a Gaussian that cannot pass the cheap reject anywhere in the patch changes nothing;
 //  * early termination: per-warp vote every 8 Gaussians, per-CTA __syncthreads_and per batch;
 //  * backward: a thread first sums the nine per-Gaussian gradient terms over its own four pixels
 //    in registers, then the warp reduces them with a multi-value butterfly (8 values in 7
@@ -36,7 +41,7 @@ constexpr float kTMin = 1.0f / 255.0f;  // forward.cuh:25-31 kTransmittanceThres
 struct __align__(16) StagedGaussian {
     float4 q0;  // x, y, a, b
     float4 q1;  // c, thr, opacity, r
-    float4 q2;  // g, b, -, -
+    float4 q2;  // g, b, hx, hy (conservative footprint half-extents, common.cuh blend_extents)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -44,6 +49,11 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ float exp2f_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
@@ -65,17 +75,50 @@ __device__ __forceinline__ void stage_gaussian(StagedGaussian* dst, int g, const
         const float2 m = reinterpret_cast<const float2*>(means_2d)[g];
         const float a = conic[(int64_t)g * 3], b = conic[(int64_t)g * 3 + 1], c = conic[(int64_t)g * 3 + 2];
         const float o = opa[g];
+        const float thr = blend_reject_threshold(o);
+        const float inv_det = 1.0f / (a * c - b * b);  // Sigma' = conic^-1: Sigma'_xx = c/det, Sigma'_yy = a/det
+        float hx, hy;
+        blend_extents(thr, c * inv_det, a * inv_det, hx, hy);
         dst->q0 = make_float4(m.x, m.y, a, b);
-        dst->q1 = make_float4(c, blend_reject_threshold(o), o, rgb[(int64_t)g * 3]);
-        dst->q2 = make_float4(rgb[(int64_t)g * 3 + 1], rgb[(int64_t)g * 3 + 2], 0.f, 0.f);
+        dst->q1 = make_float4(c, thr, o, rgb[(int64_t)g * 3]);
+        dst->q2 = make_float4(rgb[(int64_t)g * 3 + 1], rgb[(int64_t)g * 3 + 2], hx, hy);
     }
 }
 
-// thread -> its four pixels: lane = (row-in-warp << 2) | column-group; warp w covers rows 8w..8w+7
+// thread -> its four pixels: lane = (row-in-warp << 2) | c; warp w covers rows 8w..8w+7; pixel slot
+// k of the thread is column 4k + c, so slot k of a warp is the 4-column band [4k, 4k+3] x 8 rows:
+// a Gaussian that does not reach a band fails the cheap reject in ALL lanes of that slot and the
+// slot's exact path is skipped by a uniform branch.
+constexpr int kPixStride = 4;
 __device__ __forceinline__ void pixels_of_thread(int tile_x, int tile_y, int& px0, int& py) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    px0 = tile_x * kTile + (lane & 3) * kPix;
+    px0 = tile_x * kTile + (lane & 3);
     py = tile_y * kTile + warp * 8 + (lane >> 2);
+}
+
+// Ordered list of the batch's Gaussians whose footprint box can reach this warp's 16x8 patch.
+__device__ __forceinline__ int build_warp_list(const void* sg_void, int bc, float x0, float y0,
+                                               unsigned char* list) {
+    struct Rec { float4 q0, q1, q2; };
+    const Rec* sg = reinterpret_cast<const Rec*>(sg_void);
+    const int lane = threadIdx.x & 31;
+    const float x1 = x0 + 15.0f, y1 = y0 + 7.0f;  // pixel centres of the patch corners
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int jj = u * 32 + lane;
+        bool keep = false;
+        if (jj < bc) {
+            const float2 xy = *reinterpret_cast<const float2*>(&sg[jj].q0);
+            const float2 h = *reinterpret_cast<const float2*>(&sg[jj].q2.z);
+            keep = !((x0 - xy.x > h.x) || (xy.x - x1 > h.x) || (y0 - xy.y > h.y) || (xy.y - y1 > h.y));
+        }
+        const unsigned m = __ballot_sync(kFull, keep);
+        if (keep) list[cnt + __popc(m & ((1u << lane) - 1))] = (unsigned char)jj;
+        cnt += __popc(m);
+    }
+    __syncwarp();
+    return cnt;
 }
 
 // The reference's `power`, rounding for rounding (forward.cu:131-132 and
@@ -101,18 +144,21 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             const float* __restrict__ opa, float* __restrict__ out_color,
             float* __restrict__ out_T, int* __restrict__ out_n) {
     __shared__ StagedGaussian s_g[2][kBatch];
+    __shared__ unsigned char s_list[2][kBatch];
 
     const int tile = blockIdx.x;
     const int tile_x = tile % ntx, tile_y = tile / ntx;
     int px0, py;
     pixels_of_thread(tile_x, tile_y, px0, py);
     const float pyf = (float)py + 0.5f;  // forward.cu:72-73
+    const int warp = threadIdx.x >> 5;
+    const float patch_x0 = (float)(tile_x * kTile) + 0.5f, patch_y0 = (float)(tile_y * kTile + warp * 8) + 0.5f;
     float pxf[kPix];
     bool done[kPix];
 #pragma unroll
     for (int k = 0; k < kPix; ++k) {
-        pxf[k] = (float)(px0 + k) + 0.5f;
-        done[k] = !((px0 + k < width) && (py < height));
+        pxf[k] = (float)(px0 + k * kPixStride) + 0.5f;
+        done[k] = !((px0 + k * kPixStride < width) && (py < height));
     }
 
     const int2 range = reinterpret_cast<const int2*>(tile_ranges)[tile];
@@ -160,10 +206,13 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
 
         const StagedGaussian* sg = s_g[b & 1];
         const int bc = min(kBatch, count - b * kBatch);
-        for (int j0 = 0; j0 < bc; j0 += 8) {
+        const unsigned char* list = s_list[warp];
+        const int cnt = build_warp_list(sg, bc, patch_x0, patch_y0, s_list[warp]);
+        for (int i0 = 0; i0 < cnt; i0 += 8) {
             if (__all_sync(kFull, done[0] && done[1] && done[2] && done[3])) break;
-            const int j1 = min(j0 + 8, bc);
-            for (int j = j0; j < j1; ++j) {
+            const int i1 = min(i0 + 8, cnt);
+            for (int i = i0; i < i1; ++i) {
+                const int j = list[i];
                 const float4 q0 = sg[j].q0;
                 const float2 ct = *reinterpret_cast<const float2*>(&sg[j].q1);
                 const float dy = pyf - q0.y;
@@ -204,8 +253,8 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
     if (py < height) {
 #pragma unroll
         for (int k = 0; k < kPix; ++k) {
-            if (px0 + k >= width) continue;
-            const int64_t pi = (int64_t)py * width + px0 + k;
+            if (px0 + k * kPixStride >= width) continue;
+            const int64_t pi = (int64_t)py * width + px0 + k * kPixStride;
             out_color[pi * 3 + 0] = fma_rn(T[k], bg_r, C0[k]);  // forward.cu:166-168
             out_color[pi * 3 + 1] = fma_rn(T[k], bg_g, C1[k]);
             out_color[pi * 3 + 2] = fma_rn(T[k], bg_b, C2[k]);
@@ -264,13 +313,15 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             float* __restrict__ grad_acc /* [N,12] */) {
     __shared__ StagedGaussian s_g[2][kBatch];
     __shared__ int s_idx[2][kBatch];
+    __shared__ unsigned char s_list[2][kBatch];
 
     const int tile = blockIdx.x;
     const int tile_x = tile % ntx, tile_y = tile / ntx;
     int px0, py;
     pixels_of_thread(tile_x, tile_y, px0, py);
     const float pyf = (float)py + 0.5f;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float patch_x0 = (float)(tile_x * kTile) + 0.5f, patch_y0 = (float)(tile_y * kTile + warp * 8) + 0.5f;
 
     const int2 range = reinterpret_cast<const int2*>(tile_ranges)[tile];
     const int count = range.y - range.x;
@@ -281,10 +332,10 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
     int left[kPix];  // contributors still to process; <= 0 means the pixel is done
 #pragma unroll
     for (int k = 0; k < kPix; ++k) {
-        pxf[k] = (float)(px0 + k) + 0.5f;
+        pxf[k] = (float)(px0 + k * kPixStride) + 0.5f;
         T[k] = 0.0f; g0[k] = g1[k] = g2[k] = 0.0f; left[k] = 0;
-        if (px0 + k < width && py < height) {
-            const int64_t pi = (int64_t)py * width + px0 + k;
+        if (px0 + k * kPixStride < width && py < height) {
+            const int64_t pi = (int64_t)py * width + px0 + k * kPixStride;
             T[k] = final_T[pi];
             left[k] = n_contrib[pi];
             g0[k] = dL_dcolor[pi * 3 + 0];
@@ -330,9 +381,12 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
         const StagedGaussian* sg = s_g[b & 1];
         const int* sid = s_idx[b & 1];
         const int bc = min(kBatch, count - b * kBatch);
-        for (int j = bc - 1; j >= 0; --j) {
-            if ((j & 7) == 7 && __all_sync(kFull, (left[0] <= 0) && (left[1] <= 0) && (left[2] <= 0) && (left[3] <= 0)))
+        const unsigned char* list = s_list[warp];
+        const int cnt = build_warp_list(sg, bc, patch_x0, patch_y0, s_list[warp]);
+        for (int i = cnt - 1; i >= 0; --i) {
+            if ((i & 7) == 7 && __all_sync(kFull, (left[0] <= 0) && (left[1] <= 0) && (left[2] <= 0) && (left[3] <= 0)))
                 break;
+            const int j = list[i];
             const float4 q0 = sg[j].q0;
             const float4 q1 = sg[j].q1;
             const float a = q0.z, bq = q0.w, c = q1.x;
@@ -361,13 +415,19 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
 #pragma unroll
                 for (int k = 0; k < kPix; ++k) {
                     if (!pass[k]) continue;
-                    const float ex = expf(power[k]);
-                    const float oe = mul_rn(q1.z, ex);
+                    // ex2.approx (rel. error < 1e-6) unless alpha lands within a guard band of one of the
+                    // two thresholds the forward pass decided on with the accurate expf
+                    float ex = exp2f_fast(power[k] * 1.4426950408889634f);
+                    float oe = q1.z * ex;
+                    if (fabsf(oe - kAlphaMin) < 4e-8f || fabsf(oe - 0.99f) < 1e-5f) {
+                        ex = expf(power[k]);
+                        oe = mul_rn(q1.z, ex);
+                    }
                     const float alpha = fminf(oe, 0.99f);
                     if (alpha < kAlphaMin) continue;       // backward.cu:137-139
                     --left[k];                              // found++ ; found > n_contrib -> stop (:141-145)
                     const float oma = fmaxf(1.0f - alpha, 1e-5f);  // backward.cu:150-151
-                    const float inv = 1.0f / oma;
+                    const float inv = __fdividef(1.0f, oma);
                     T[k] = T[k] * inv;
                     const float w = alpha * T[k];
                     v[0] = fmaf(g0[k], w, v[0]);

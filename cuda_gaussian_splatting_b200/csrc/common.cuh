@@ -149,6 +149,19 @@ __device__ __forceinline__ float blend_reject_threshold(float op) {
     return -__logf(255.0f * op) - 1e-4f;
 }
 
+// Conservative axis-aligned half-extents of the region where a Gaussian can pass the cheap reject
+// (power >= thr): the ellipse d^T Q d <= t, t = -2 thr, Q = Sigma'^-1, spans |dx| <= sqrt(t Sigma'_xx),
+// |dy| <= sqrt(t Sigma'_yy). Inflated by 1e-4 relative + 1e-3 px against rounding. The blend kernels
+// drop a Gaussian from a warp's list when this box misses the warp's pixel patch, which cannot
+// change any result. thr > 0 (opacity below 1/255): nothing can pass -> -inf (always dropped);
+// NaN inputs give NaN extents, whose comparisons are false -> never dropped (exact path decides).
+__device__ __forceinline__ void blend_extents(float thr, float sxx, float syy, float& hx, float& hy) {
+    const float t = -2.0f * thr;
+    if (t < 0.0f) { hx = -INFINITY; hy = -INFINITY; return; }
+    hx = sqrtf(t * sxx) * 1.0001f + 1e-3f;
+    hy = sqrtf(t * syy) * 1.0001f + 1e-3f;
+}
+
 // Per-launch constants shared by the per-Gaussian kernels (passed by value: lives in the
 // constant bank, so the 16-entry view matrix is not re-read from global by every thread).
 struct ViewParams {

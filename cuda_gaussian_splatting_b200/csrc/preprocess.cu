@@ -173,6 +173,7 @@ k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
 
     // ---- phase A: projection ----
     float o_x = 0.f, o_y = 0.f, o_depth = 0.f, o_op = 0.f, o_a = 0.f, o_b = 0.f, o_c = 0.f;
+    float o_sxx = 0.f, o_syy = 0.f;  // Sigma'_xx, Sigma'_yy (footprint extents for the blend kernels)
     int o_radius = 0, o_tiles = 0;
     bool quirk = false;
     if (valid) {
@@ -195,6 +196,8 @@ k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                 o_a = mul_rn(f.c2[2], inv_det);
                 o_b = mul_rn(-f.c2[1], inv_det);
                 o_c = mul_rn(f.c2[0], inv_det);
+                o_sxx = f.c2[0];
+                o_syy = f.c2[2];
                 int radius = radius_from_cov(f.c2, f.det);
                 if (radius > 0) {
                     radius = min(radius, max(vp.width, vp.height));  // :165-166
@@ -280,12 +283,15 @@ k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
         c_r = col[0]; c_g = col[1]; c_b = col[2];
     }
 
-    // ---- packed blend record {x,y,a,b | c,thr,op,r | g,b,0,0} ----
+    // ---- packed blend record {x,y,a,b | c,thr,op,r | g,b,hx,hy} ----
     if (packed != nullptr && valid) {
         float4* rec = packed + i * 3;
+        const float thr = blend_reject_threshold(o_op);
+        float hx, hy;
+        blend_extents(thr, o_sxx, o_syy, hx, hy);
         rec[0] = make_float4(o_x, o_y, o_a, o_b);
-        rec[1] = make_float4(o_c, blend_reject_threshold(o_op), o_op, c_r);
-        rec[2] = make_float4(c_g, c_b, 0.0f, 0.0f);
+        rec[1] = make_float4(o_c, thr, o_op, c_r);
+        rec[2] = make_float4(c_g, c_b, hx, hy);
     }
 }
 

@@ -70,7 +70,7 @@ uint64_t cugs_b200_launch_count(const cugs_handle_t* h);
  * the libtorch view-direction ops (:273-280), evaluate_sh_cuda (core/sh.cu:81-123) and
  * clamp_min(0) (:284), fused into one launch. Every output element is written (zeros where the
  * reference leaves its torch::zeros untouched), so outputs may be uninitialised.
- * packed (optional, may be NULL): [N,12] f32 private record {x,y,a,b | c,thr,op,r | g,b,0,0}
+ * packed (optional, may be NULL): [N,12] f32 private record {x,y,a,b | c,thr,op,r | g,b,hx,hy}
  * consumed by the blend kernels. depth_minmax (optional): 2 x u32 device words, pre-set by the
  * caller to {0xFFFFFFFF, 0}; receives min / max of float_bits(depth) over Gaussians with
  * tiles_touched > 0 (used to trim the sort's key bits). */
