@@ -12,7 +12,20 @@ using namespace cugs;
 // internal launchers implemented in the other translation units
 int cugs_scan_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, const int32_t* tiles_touched,
                      int32_t* offsets, int64_t* total_dev, bool to_pinned, void* scan_temp,
-                     const unsigned* aux_pair);
+                     const unsigned* aux_pair, const uint64_t* gather);
+int cugs_preprocess_fwd_launch(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
+                               const float* positions, const float* rotations, const float* scales,
+                               const float* opacities, const float* sh_coeffs, float* means_2d, float* depths,
+                               float* cov_2d_inv, int32_t* radii, int32_t* tiles_touched, float* rgb,
+                               float* opacities_act, float* packed, uint32_t* depth_minmax, uint64_t* gsort);
+// tile_binning.cu
+size_t cugs_packed_sort_temp_bytes(int64_t n, int passes, int num_tiles);
+int cugs_packed_passes(int key_bits);
+int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, uint64_t* a, uint64_t* b,
+                     int* out32_last, int num_tiles, int* tile_ranges, void* temp, size_t temp_bytes);
+int cugs_duplicate_sorted(cugs_handle_t* h, cudaStream_t s, int64_t n, int width, int height,
+                          const uint64_t* sorted_elts, const float* means_2d, const int32_t* radii,
+                          const int32_t* tiles_touched, const int32_t* offsets_sorted, int64_t p, uint64_t* pairs);
 int cugs_blend_bwd_accumulate(cugs_handle_t* h, cudaStream_t s, int64_t n, const cugs_view_t* v,
                               const int32_t* tile_ranges, const int32_t* gaussian_idx,
                               const float* means_2d, const float* cov_2d_inv, const float* rgb,
@@ -103,7 +116,10 @@ extern "C" int cugs_b200_last_sort_plan(const cugs_handle_t* h, int* passes, int
 extern "C" int cugs_b200_get_stage_ms(cugs_handle_t* h, float* ms8) {
     CUGS_REQUIRE(h, h != nullptr && ms8 != nullptr, "null pointer");
     // {first event, last event} of each stage; events 0-2 plan, 3-7 finish, 8-10 backward
-    static const int span[CUGS_NUM_STAGES][2] = {{0, 1}, {1, 2}, {3, 4}, {4, 5}, {5, 6}, {6, 7}, {8, 9}, {9, 10}};
+    // stages: preprocess, scan (gather-scan in depth order), duplicate, sort (depth sort of the N
+    // Gaussians [1->11] + tile sort of the P pairs incl. histogram/ranges [4->5]), tile_ranges (now
+    // part of the sort: 0), blend_fwd, blend_bwd, preprocess_bwd
+    static const int span[CUGS_NUM_STAGES][2] = {{0, 1}, {11, 2}, {3, 4}, {4, 5}, {5, 6}, {6, 7}, {8, 9}, {9, 10}};
     for (int k = 0; k < CUGS_NUM_STAGES; ++k) {
         ms8[k] = -1.0f;
         const int a = span[k][0], b = span[k][1];
@@ -112,6 +128,12 @@ extern "C" int cugs_b200_get_stage_ms(cugs_handle_t* h, float* ms8) {
         float ms = 0.0f;
         CUGS_CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]));
         ms8[k] = ms;
+    }
+    if (h->timing && h->ev_recorded[1] && h->ev_recorded[11] && ms8[3] >= 0.0f) {  // add the depth sort to "sort"
+        float ms = 0.0f;
+        CUGS_CUDA_TRY(h, cudaEventSynchronize(h->ev[11]));
+        CUGS_CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[1], h->ev[11]));
+        ms8[3] += ms;
     }
     return CUGS_OK;
 }
@@ -126,20 +148,24 @@ extern "C" uint64_t cugs_b200_launch_count(const cugs_handle_t* h) { return h ? 
 namespace {
 
 struct FrameWorkspace {
-    float* packed;          // [N,12]
+    float* packed;          // [N,12]  blend records
     int32_t* tiles_touched; // [N]
-    int32_t* offsets;       // [N]
+    int32_t* offsets;       // [N]     pair offsets in DEPTH order
     void* scan_temp;
-    unsigned* depth_minmax; // 2 words (+ int64 total)
     int64_t* total_dev;
-    uint64_t* keys_x;       // [Pcap]  (sorted keys end up here)
-    uint64_t* keys_y;       // [Pcap]
-    int32_t* vals_y;        // [Pcap]
-    void* sort_temp;
-    size_t sort_temp_bytes;
+    uint64_t* gsort_a;      // [N]     depth_key << 32 | index; sorted result ends up here (4 passes)
+    uint64_t* gsort_b;      // [N]
+    void* gsort_temp;
+    size_t gsort_temp_bytes;
     float* grad_acc;        // [N,12]
+    uint64_t* pairs_a;      // [Pcap]  tile << 32 | index
+    uint64_t* pairs_b;      // [Pcap]
+    void* psort_temp;
+    size_t psort_temp_bytes;
     size_t total_bytes;
 };
+
+constexpr int kMaxTilesForWorkspace = 48 * 1024;  // tile histogram lives in shared memory (<= 192 KB)
 
 FrameWorkspace carve(void* base, int64_t n, int64_t pcap) {
     FrameWorkspace w{};
@@ -156,15 +182,17 @@ FrameWorkspace carve(void* base, int64_t n, int64_t pcap) {
     w.tiles_touched = static_cast<int32_t*>(take(nn * 4));
     w.offsets = static_cast<int32_t*>(take(nn * 4));
     w.scan_temp = take(cugs_b200_scan_temp_bytes(n));
-    w.depth_minmax = static_cast<unsigned*>(take(64));
-    w.total_dev = reinterpret_cast<int64_t*>(w.depth_minmax ? w.depth_minmax + 4 : nullptr);
+    w.total_dev = static_cast<int64_t*>(take(64));
+    w.gsort_a = static_cast<uint64_t*>(take(nn * 8));
+    w.gsort_b = static_cast<uint64_t*>(take(nn * 8));
+    w.gsort_temp_bytes = cugs_packed_sort_temp_bytes(n, 4, 0);
+    w.gsort_temp = take(w.gsort_temp_bytes);
     w.grad_acc = static_cast<float*>(take(nn * 48));
     // P-sized scratch, live only inside render_finish
-    w.keys_x = static_cast<uint64_t*>(take(pp * 8));
-    w.keys_y = static_cast<uint64_t*>(take(pp * 8));
-    w.vals_y = static_cast<int32_t*>(take(pp * 4));
-    w.sort_temp_bytes = cugs_b200_sort_temp_bytes(pcap);
-    w.sort_temp = take(w.sort_temp_bytes);
+    w.pairs_a = static_cast<uint64_t*>(take(pp * 8));
+    w.pairs_b = static_cast<uint64_t*>(take(pp * 8));
+    w.psort_temp_bytes = cugs_packed_sort_temp_bytes(pcap, 4, kMaxTilesForWorkspace);
+    w.psort_temp = take(w.psort_temp_bytes);
     w.total_bytes = off;
     return w;
 }
@@ -203,16 +231,20 @@ extern "C" int cugs_b200_render_plan(cugs_handle_t* h, void* stream, int64_t n, 
     cudaStream_t s = (cudaStream_t)stream;
     // the N-sized regions come first in the layout, so carving with pcap = 0 addresses them
     const FrameWorkspace w = carve(workspace, n, 0);
-    CUGS_CUDA_TRY(h, cudaMemsetAsync(w.depth_minmax, 0xff, 4, s));
-    CUGS_CUDA_TRY(h, cudaMemsetAsync(w.depth_minmax + 1, 0, 4, s));
     mark(h, 0, s);
-    if (int e = cugs_b200_preprocess_fwd(h, stream, n, v, positions, rotations, scales, opacities, sh_coeffs,
-                                         means_2d, depths, cov_2d_inv, radii, w.tiles_touched, rgb,
-                                         opacities_act, w.packed, w.depth_minmax))
+    if (int e = cugs_preprocess_fwd_launch(h, stream, n, v, positions, rotations, scales, opacities, sh_coeffs,
+                                           means_2d, depths, cov_2d_inv, radii, w.tiles_touched, rgb,
+                                           opacities_act, w.packed, nullptr, w.gsort_a))
         return e;
     mark(h, 1, s);
-    if (int e = cugs_scan_launch(h, s, n, w.tiles_touched, w.offsets, w.total_dev, true, w.scan_temp,
-                                 w.depth_minmax))
+    // depth sort of the N Gaussians (the depth-bit passes of the reference's 64-bit sort, hoisted
+    // in front of duplicateWithKeys), then the scan of tiles_touched in depth order
+    if (int e = cugs_packed_sort(h, s, n, 32, w.gsort_a, w.gsort_b, nullptr, 0, nullptr, w.gsort_temp,
+                                 w.gsort_temp_bytes))
+        return e;
+    mark(h, 11, s);
+    if (int e = cugs_scan_launch(h, s, n, w.tiles_touched, w.offsets, w.total_dev, true, w.scan_temp, nullptr,
+                                 w.gsort_a))
         return e;
     mark(h, 2, s);
     CUGS_CUDA_TRY(h, cudaStreamSynchronize(s));  // the one blocking read (reference: sorting.cu:146)
@@ -244,37 +276,31 @@ extern "C" int cugs_b200_render_finish(cugs_handle_t* h, void* stream, int64_t n
         w = carve(workspace, n, p);
     }
     mark(h, 3, s);
+    if (num_tiles > kMaxTilesForWorkspace)
+        return set_error(h, CUGS_ERR_UNSUPPORTED, "%d tiles > %d is not supported by the fused path", num_tiles,
+                         kMaxTilesForWorkspace);
     if (p > 0) {
-        // key bits that can differ: tile bits + depth bits below the highest differing one
-        const uint64_t mm = (uint64_t)h->pinned[1];
-        const unsigned dmin = (unsigned)(mm & 0xffffffffu), dmax = (unsigned)(mm >> 32);
-        int depth_bits = 32;
-        if (h->pinned[0] == p && dmin <= dmax) {
-            const unsigned x = dmin ^ dmax;
-            depth_bits = x ? 32 - __builtin_clz(x) : 0;
-        }
-        const int tile_bits = ceil_log2(num_tiles);
-        const int passes = cugs_b200_sort_num_passes(depth_bits, tile_bits);
-        h->last_sort_passes = passes;
-        h->last_sort_key_bits = depth_bits + tile_bits;
-        // choose where the unsorted pairs go so that the sorted VALUES land in gaussian_idx
-        uint64_t* ka; int32_t* va; uint64_t* kb; int32_t* vb;
-        if (passes & 1) { ka = w.keys_y; va = w.vals_y; kb = w.keys_x; vb = gaussian_idx; }
-        else            { ka = w.keys_x; va = gaussian_idx; kb = w.keys_y; vb = w.vals_y; }
-        if (int e = cugs_b200_duplicate_with_keys(h, stream, n, v->width, v->height, means_2d, depths, radii,
-                                                  w.tiles_touched, w.offsets, p, ka, va))
+        if (h->pinned[0] != p)
+            return set_error(h, CUGS_ERR_INVALID_ARG, "p = %lld does not match the plan of this frame (%lld)",
+                             (long long)p, (long long)h->pinned[0]);
+        if (int e = cugs_duplicate_sorted(h, s, n, v->width, v->height, w.gsort_a, means_2d, radii, w.tiles_touched,
+                                          w.offsets, p, w.pairs_a))
             return e;
         mark(h, 4, s);
-        int in_b = 0;
-        if (int e = cugs_b200_sort_pairs_pingpong(h, stream, p, depth_bits, tile_bits, ka, va, kb, vb,
-                                                  w.sort_temp, w.sort_temp_bytes, &in_b))
+        const int tile_bits = ceil_log2(num_tiles);
+        h->last_sort_passes = 4 + cugs_packed_passes(tile_bits);
+        h->last_sort_key_bits = 32 + tile_bits;
+        // tile histogram -> tile ranges, and the stable sort of the pairs by tile id; the last pass
+        // writes the Gaussian indices straight into the caller's buffer
+        if (int e = cugs_packed_sort(h, s, p, tile_bits, w.pairs_a, w.pairs_b, gaussian_idx, num_tiles, tile_ranges,
+                                     w.psort_temp, w.psort_temp_bytes))
             return e;
         mark(h, 5, s);
     } else {
         mark(h, 4, s);
         mark(h, 5, s);
+        CUGS_CUDA_TRY(h, cudaMemsetAsync(tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(int), s));
     }
-    if (int e = cugs_b200_tile_ranges(h, stream, p, w.keys_x, num_tiles, tile_ranges)) return e;
     mark(h, 6, s);
     if (int e = cugs_b200_blend_fwd(h, stream, v, tile_ranges, gaussian_idx, means_2d, cov_2d_inv, rgb,
                                     opacities_act, n > 0 ? w.packed : nullptr, color, final_T, n_contrib)) {

@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(kScanBlock)
 k_scan_exclusive(int64_t n, const int* __restrict__ in, int* __restrict__ out,
                  unsigned* __restrict__ ticket, volatile uint64_t* __restrict__ status,
                  int64_t* __restrict__ total_dev, int64_t* __restrict__ total_pinned,
-                 const unsigned* __restrict__ aux_pair /* e.g. depth min/max, copied to pinned[1] */) {
+                 const unsigned* __restrict__ aux_pair /* e.g. depth min/max, copied to pinned[1] */,
+                 const uint64_t* __restrict__ gather /* optional: item i is in[(u32)gather[i]] */) {
     __shared__ unsigned s_block;
     __shared__ int64_t s_warp[kScanBlock / 32];
     __shared__ int64_t s_prefix;
@@ -39,7 +40,10 @@ k_scan_exclusive(int64_t n, const int* __restrict__ in, int* __restrict__ out,
     const int64_t base = (int64_t)bid * kScanTile + (int64_t)threadIdx.x * kScanItems;
 
     int v[kScanItems];
-    if (base + kScanItems <= n) {
+    if (gather != nullptr) {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) v[k] = (base + k < n) ? in[(unsigned)gather[base + k]] : 0;
+    } else if (base + kScanItems <= n) {
         const int4 a = *reinterpret_cast<const int4*>(in + base);
         const int4 b = *reinterpret_cast<const int4*>(in + base + 4);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
@@ -214,14 +218,14 @@ extern "C" size_t cugs_b200_scan_temp_bytes(int64_t n) {
 
 int cugs_scan_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, const int32_t* tiles_touched,
                      int32_t* offsets, int64_t* total_dev, bool to_pinned, void* scan_temp,
-                     const unsigned* aux_pair) {
+                     const unsigned* aux_pair, const uint64_t* gather) {
     const int64_t blocks = (n + kScanTile - 1) / kScanTile;
     CUGS_CUDA_TRY(h, cudaMemsetAsync(scan_temp, 0, cugs_b200_scan_temp_bytes(n), s));
     unsigned* ticket = reinterpret_cast<unsigned*>(scan_temp);
     uint64_t* status = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(scan_temp) + 16);
     k_scan_exclusive<<<(unsigned)blocks, kScanBlock, 0, s>>>(n, tiles_touched, offsets, ticket, status,
                                                              total_dev, to_pinned ? h->pinned : nullptr,
-                                                             aux_pair);
+                                                             aux_pair, gather);
     CUGS_LAUNCH_CHECK(h, "k_scan_exclusive");
     return CUGS_OK;
 }
@@ -242,7 +246,7 @@ extern "C" int cugs_b200_scan(cugs_handle_t* h, void* stream, int64_t n, const i
         return set_error(h, CUGS_ERR_WORKSPACE, "scan_temp too small: %zu < %zu", scan_temp_bytes,
                          cugs_b200_scan_temp_bytes(n));
     if (int e = cugs_scan_launch(h, s, n, tiles_touched, offsets, total_dev, total_host != nullptr,
-                                 scan_temp, nullptr))
+                                 scan_temp, nullptr, nullptr))
         return e;
     if (total_host) {
         CUGS_CUDA_TRY(h, cudaStreamSynchronize(s));  // the one blocking read (sorting.cu:146)

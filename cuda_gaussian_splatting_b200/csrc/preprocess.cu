@@ -137,7 +137,7 @@ k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                  float* __restrict__ cov_2d_inv, int* __restrict__ radii,
                  int* __restrict__ tiles_touched, float* __restrict__ rgb,
                  float* __restrict__ opa_act, float4* __restrict__ packed,
-                 unsigned* __restrict__ depth_minmax) {
+                 unsigned* __restrict__ depth_minmax, uint64_t* __restrict__ gsort) {
     __shared__ __align__(16) float sY[kPreWarps][32 * kYStride];
     __shared__ float sRGB[kPreWarps][96];
 
@@ -217,6 +217,12 @@ k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
         radii[i] = o_radius;
         tiles_touched[i] = o_tiles;
         opa_act[i] = o_op;
+        // element of the depth sort (tile_binning.cu): depth bits << 32 | index; key 0 for the
+        // filler entries of quirk A.2, 0xffffffff (sorts last) when the Gaussian emits no pair
+        if (gsort != nullptr) {
+            const unsigned key = (o_tiles > 0) ? (quirk ? 0u : __float_as_uint(o_depth)) : 0xffffffffu;
+            gsort[i] = ((uint64_t)key << 32) | (uint64_t)(unsigned)i;
+        }
     }
 
     if (depth_minmax != nullptr) {
@@ -592,6 +598,12 @@ static int check_view(cugs_handle_t* h, const cugs_view_t* v) {
     return CUGS_OK;
 }
 
+int cugs_preprocess_fwd_launch(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
+                               const float* positions, const float* rotations, const float* scales,
+                               const float* opacities, const float* sh_coeffs, float* means_2d, float* depths,
+                               float* cov_2d_inv, int32_t* radii, int32_t* tiles_touched, float* rgb,
+                               float* opacities_act, float* packed, uint32_t* depth_minmax, uint64_t* gsort);
+
 extern "C" int cugs_b200_preprocess_fwd(cugs_handle_t* h, void* stream, int64_t n,
                                         const cugs_view_t* v, const float* positions,
                                         const float* rotations, const float* scales,
@@ -599,6 +611,16 @@ extern "C" int cugs_b200_preprocess_fwd(cugs_handle_t* h, void* stream, int64_t 
                                         float* means_2d, float* depths, float* cov_2d_inv,
                                         int32_t* radii, int32_t* tiles_touched, float* rgb,
                                         float* opacities_act, float* packed, uint32_t* depth_minmax) {
+    return cugs_preprocess_fwd_launch(h, stream, n, v, positions, rotations, scales, opacities, sh_coeffs, means_2d,
+                                      depths, cov_2d_inv, radii, tiles_touched, rgb, opacities_act, packed,
+                                      depth_minmax, nullptr);
+}
+
+int cugs_preprocess_fwd_launch(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
+                               const float* positions, const float* rotations, const float* scales,
+                               const float* opacities, const float* sh_coeffs, float* means_2d, float* depths,
+                               float* cov_2d_inv, int32_t* radii, int32_t* tiles_touched, float* rgb,
+                               float* opacities_act, float* packed, uint32_t* depth_minmax, uint64_t* gsort) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, n >= 0, "n must be >= 0");
     if (int e = check_view(h, v)) return e;
@@ -612,11 +634,11 @@ extern "C" int cugs_b200_preprocess_fwd(cugs_handle_t* h, void* stream, int64_t 
     if (v->num_coeffs == 16)
         k_preprocess_fwd<true><<<grid, kPreBlock, 0, s>>>(
             n, vp, positions, rotations, scales, opacities, sh_coeffs, means_2d, depths, cov_2d_inv,
-            radii, tiles_touched, rgb, opacities_act, reinterpret_cast<float4*>(packed), depth_minmax);
+            radii, tiles_touched, rgb, opacities_act, reinterpret_cast<float4*>(packed), depth_minmax, gsort);
     else
         k_preprocess_fwd<false><<<grid, kPreBlock, 0, s>>>(
             n, vp, positions, rotations, scales, opacities, sh_coeffs, means_2d, depths, cov_2d_inv,
-            radii, tiles_touched, rgb, opacities_act, reinterpret_cast<float4*>(packed), depth_minmax);
+            radii, tiles_touched, rgb, opacities_act, reinterpret_cast<float4*>(packed), depth_minmax, gsort);
     CUGS_LAUNCH_CHECK(h, "k_preprocess_fwd");
     return CUGS_OK;
 }

@@ -1,0 +1,452 @@
+// tile_binning.cu — the binning pipeline of the fused render path (render_plan / render_finish).
+//
+// Produces exactly what the reference's sort_gaussians produces (rasterizer/sorting.cu:115-227:
+// stable ascending sort of the 64-bit keys tile<<32 | depth_bits with CUB over all 64 bits, then
+// k_compute_tile_ranges): the sorted Gaussian indices and the tile ranges, bit for bit — but as an
+// LSD radix sort whose passes over the DEPTH bits are hoisted in front of duplicateWithKeys:
+// every (tile, Gaussian) pair of one Gaussian carries the same depth digits, so the low 32 key
+// bits are sorted once per Gaussian (N elements) instead of once per pair (P ~ 6 N elements), and
+// only the tile bits are sorted on the pairs:
+//
+//   1. preprocess writes one packed element per Gaussian: depth_key << 32 | index, depth_key =
+//      float bits of the depth (0 for the filler entries of quirk A.2, 0xffffffff if the Gaussian
+//      emits no pair)                                                       [preprocess.cu]
+//   2. stable LSD sort of the N packed elements by depth_key              (4 onesweep passes x 8 bits)
+//   3. exclusive scan of tiles_touched in depth order -> pair offsets, P  [binning.cu, gather-scan]
+//   4. duplicateWithKeys in depth order: packed pair = tile_id << 32 | gaussian index
+//   5. tile histogram (-> tile ranges by an exclusive scan, no pass over sorted keys) and stable
+//      LSD sort of the P pairs by tile id                                  (ceil(tile_bits/8) passes)
+//
+// Order of the result: tile ascending; inside a tile the emission order of step 4 = (depth bits
+// ascending, Gaussian index ascending) — the order of the reference's stable 64-bit sort.
+// HBM traffic: 8 B/pair per pass instead of 12, 2 passes over the pairs instead of 6 (1080p).
+#include "common.cuh"
+
+namespace cugs {
+
+constexpr int kPkRadixBits = 8;
+constexpr int kPkRadix = 256;
+constexpr int kPkThreads = 512;
+constexpr int kPkItems = 8;
+constexpr int kPkTile = kPkThreads * kPkItems;  // 4096 elements per block
+constexpr int kPkWarps = kPkThreads / 32;
+constexpr int kPkMaxPasses = 4;
+
+constexpr unsigned kPkAggregate = 1u << 30;
+constexpr unsigned kPkPrefix = 2u << 30;
+constexpr unsigned kPkValue = (1u << 30) - 1;
+
+struct PackedPlan {
+    int passes;
+    int shift[kPkMaxPasses];  // bit offset inside the HIGH 32 bits of the element
+    int bits[kPkMaxPasses];
+};
+
+inline PackedPlan make_packed_plan(int key_bits) {
+    PackedPlan pl{};
+    pl.passes = (key_bits + kPkRadixBits - 1) / kPkRadixBits;
+    if (pl.passes < 1) pl.passes = 1;
+    if (pl.passes > kPkMaxPasses) pl.passes = kPkMaxPasses;
+    int shift = 0;
+    for (int i = 0; i < pl.passes; ++i) {  // spread the bits evenly: 13 -> 7,6
+        const int left = key_bits - shift, passes_left = pl.passes - i;
+        int b = (left + passes_left - 1) / passes_left;
+        if (b < 1) b = 1;
+        if (b > kPkRadixBits) b = kPkRadixBits;
+        pl.shift[i] = shift;
+        pl.bits[i] = b;
+        shift += b;
+    }
+    return pl;
+}
+
+__device__ __forceinline__ unsigned pk_digit(uint64_t e, int shift, unsigned mask) {
+    return ((unsigned)(e >> 32) >> shift) & mask;
+}
+
+// ------------------------------------------------------------------------------------------------
+// histograms: digit histograms of every pass (+ optionally the full per-tile histogram) in ONE read
+// ------------------------------------------------------------------------------------------------
+constexpr int kPkHistThreads = 512;
+constexpr int kPkHistItems = 8;
+
+template <bool kTileHist>
+__global__ void __launch_bounds__(kPkHistThreads)
+k_packed_histogram(int64_t n, const uint64_t* __restrict__ elts, PackedPlan plan,
+                   unsigned* __restrict__ digit_hist /* [passes][256] */, int num_tiles,
+                   unsigned* __restrict__ tile_hist /* [num_tiles] */) {
+    extern __shared__ unsigned s_hist[];  // [passes*256] (+ [num_tiles])
+    unsigned* s_tile = s_hist + plan.passes * kPkRadix;
+    const int total_bins = plan.passes * kPkRadix + (kTileHist ? num_tiles : 0);
+    for (int b = threadIdx.x; b < total_bins; b += kPkHistThreads) s_hist[b] = 0;
+    __syncthreads();
+    const int64_t tile = (int64_t)kPkHistThreads * kPkHistItems;
+    for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile) {
+        uint64_t e[kPkHistItems];
+#pragma unroll
+        for (int i = 0; i < kPkHistItems; ++i) {
+            const int64_t idx = base + (int64_t)i * kPkHistThreads + threadIdx.x;
+            e[i] = (idx < n) ? __ldcs(elts + idx) : 0ull;
+        }
+#pragma unroll
+        for (int i = 0; i < kPkHistItems; ++i) {
+            const int64_t idx = base + (int64_t)i * kPkHistThreads + threadIdx.x;
+            if (idx < n) {
+                const unsigned key = (unsigned)(e[i] >> 32);
+                for (int ps = 0; ps < plan.passes; ++ps)
+                    atomicAdd(&s_hist[ps * kPkRadix + ((key >> plan.shift[ps]) & ((1u << plan.bits[ps]) - 1))], 1u);
+                if (kTileHist && key < (unsigned)num_tiles) atomicAdd(&s_tile[key], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < plan.passes * kPkRadix; b += kPkHistThreads) {
+        const unsigned c = s_hist[b];
+        if (c) atomicAdd(&digit_hist[b], c);
+    }
+    if (kTileHist)
+        for (int b = threadIdx.x; b < num_tiles; b += kPkHistThreads) {
+            const unsigned c = s_tile[b];
+            if (c) atomicAdd(&tile_hist[b], c);
+        }
+}
+
+// exclusive scan of each pass's 256 bins, in place
+__global__ void __launch_bounds__(kPkRadix) k_packed_scan_bins(unsigned* __restrict__ hist) {
+    __shared__ unsigned swarp[kPkRadix / 32];
+    unsigned* hp = hist + blockIdx.x * kPkRadix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned c = hp[threadIdx.x];
+    unsigned incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) swarp[warp] = incl;
+    __syncthreads();
+    unsigned off = 0;
+    for (int w = 0; w < warp; ++w) off += swarp[w];
+    hp[threadIdx.x] = off + incl - c;
+}
+
+// tile histogram -> tile ranges [start, end) (rasterizer/sorting.cu:82-109 semantics: tiles
+// without pairs stay {0, 0}). One block; num_tiles is at most a few ten thousand.
+__global__ void __launch_bounds__(1024)
+k_tile_hist_to_ranges(int num_tiles, const unsigned* __restrict__ tile_hist, int* __restrict__ ranges) {
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < num_tiles; base += 1024) {
+        const int t = base + threadIdx.x;
+        const unsigned c = (t < num_tiles) ? tile_hist[t] : 0u;
+        unsigned incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned off = s_carry;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        const unsigned start = off + incl - c;
+        if (t < num_tiles) {
+            ranges[2 * t + 0] = c ? (int)start : 0;
+            ranges[2 * t + 1] = c ? (int)(start + c) : 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = off + incl;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one onesweep pass over packed 64-bit elements (digit taken from the high word). kLast: write
+// only the low word (the Gaussian index) of each element to out32.
+// ------------------------------------------------------------------------------------------------
+constexpr size_t kPkSmemBytes = (size_t)kPkTile * 8 + (size_t)kPkRadix * 8 + (size_t)kPkWarps * kPkRadix * 4 +
+                                (size_t)kPkRadix * 4 + 64;
+
+template <bool kLast>
+__global__ void __launch_bounds__(kPkThreads)
+k_onesweep_packed(int64_t n, const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                  int* __restrict__ out32, const unsigned* __restrict__ bin_base,
+                  volatile unsigned* __restrict__ lookback, unsigned* __restrict__ ticket, int shift, int bits) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint64_t* s_elts = reinterpret_cast<uint64_t*>(s_raw);                   // [kPkTile]
+    int64_t* s_bin_global = reinterpret_cast<int64_t*>(s_elts + kPkTile);     // global index = [d] + slot
+    unsigned(*s_warp_hist)[kPkRadix] = reinterpret_cast<unsigned(*)[kPkRadix]>(s_bin_global + kPkRadix);
+    unsigned* s_bin_start = &s_warp_hist[kPkWarps][0];
+    unsigned* s_scan = s_bin_start + kPkRadix;
+    __shared__ unsigned s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int b = lane; b < kPkRadix; b += 32) s_warp_hist[warp][b] = 0;
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int64_t tile_base = (int64_t)tile * kPkTile;
+    const int valid = (int)min((int64_t)kPkTile, n - tile_base);
+    const int64_t seg = tile_base + (int64_t)warp * (32 * kPkItems);
+    const unsigned mask = (1u << bits) - 1;
+    const unsigned lt_mask = (1u << lane) - 1;
+
+    uint64_t e[kPkItems];
+#pragma unroll
+    for (int i = 0; i < kPkItems; ++i) {
+        const int64_t idx = seg + i * 32 + lane;
+        e[i] = (idx < n) ? __ldcs(in + idx) : ~0ull;
+    }
+
+    // stable ranking inside the warp: match peers with the same digit, per-warp counters
+    unsigned short rank[kPkItems];
+#pragma unroll
+    for (int i = 0; i < kPkItems; ++i) {
+        const unsigned d = pk_digit(e[i], shift, mask);
+        const unsigned peers = __match_any_sync(kFull, d);
+        const int leader = __ffs(peers) - 1;
+        unsigned old = 0;
+        if (lane == leader) {
+            old = s_warp_hist[warp][d];
+            s_warp_hist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(kFull, old, leader);
+        rank[i] = (unsigned short)(old + __popc(peers & lt_mask));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per-bin: scan over warps, block count, local start, global base via decoupled look-back
+    unsigned bin_count = 0, incl = 0;
+    if (tid < kPkRadix) {
+        unsigned run = 0;
+#pragma unroll
+        for (int w = 0; w < kPkWarps; ++w) {
+            const unsigned c = s_warp_hist[w][tid];
+            s_warp_hist[w][tid] = run;
+            run += c;
+        }
+        bin_count = run;
+        incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+    }
+    __syncthreads();
+    if (tid < kPkRadix) {
+        unsigned off = 0;
+        for (int w = 0; w < warp; ++w) off += s_scan[w];
+        const unsigned local_start = incl - bin_count + off;
+
+        volatile unsigned* lb = lookback + (size_t)tile * kPkRadix;
+        unsigned excl = 0;
+        if (tile == 0) {
+            lb[tid] = kPkPrefix | bin_count;
+        } else {
+            lb[tid] = kPkAggregate | bin_count;
+            int64_t j = (int64_t)tile - 1;
+            while (true) {
+                const unsigned s = lookback[(size_t)j * kPkRadix + tid];
+                if (s & kPkPrefix) { excl += s & kPkValue; break; }
+                if (s & kPkAggregate) { excl += s & kPkValue; --j; }
+            }
+            lb[tid] = kPkPrefix | ((excl + bin_count) & kPkValue);
+        }
+        s_bin_global[tid] = (int64_t)bin_base[tid] + (int64_t)excl - (int64_t)local_start;
+        s_bin_start[tid] = local_start;
+    }
+    __syncthreads();
+
+    // scatter into the local sorted slot, then write runs of equal digits contiguously
+#pragma unroll
+    for (int i = 0; i < kPkItems; ++i) {
+        const unsigned d = pk_digit(e[i], shift, mask);
+        s_elts[s_bin_start[d] + s_warp_hist[warp][d] + rank[i]] = e[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kPkItems; ++i) {
+        const int slot = tid + i * kPkThreads;
+        if (slot < valid) {
+            const uint64_t x = s_elts[slot];
+            const int64_t g = s_bin_global[pk_digit(x, shift, mask)] + slot;
+            if (kLast) out32[g] = (int)(unsigned)x;
+            else out[g] = x;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// duplicateWithKeys in depth order (reference: k_fill_sort_pairs, rasterizer/sorting.cu:30-72).
+// A warp owns 32 consecutive positions of the depth-sorted Gaussian list; their output slots are
+// contiguous, so slot k is resolved to its owner lane by a shuffle binary search and every store
+// of the warp is coalesced, whatever the splat size. Pair = tile_id << 32 | gaussian index; the
+// reserved-but-not-emitted slots of quirk A.2 become (tile 0, Gaussian 0) = 0, as in the reference
+// (whose zero-filled key 0 / value 0 sorts to the front of tile 0).
+// ------------------------------------------------------------------------------------------------
+constexpr int kDupBlock = 256;
+
+__global__ void __launch_bounds__(kDupBlock)
+k_duplicate_sorted(int64_t n, int width, int height, int ntx, int nty,
+                   const uint64_t* __restrict__ sorted_elts, const float* __restrict__ means_2d,
+                   const int* __restrict__ radii, const int* __restrict__ tiles_touched,
+                   const int* __restrict__ offsets /* in sorted order */, int64_t p,
+                   uint64_t* __restrict__ pairs) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s0 = ((int64_t)blockIdx.x * (kDupBlock / 32) + (threadIdx.x >> 5)) * 32;
+    if (s0 >= n) return;
+    const int64_t si = s0 + lane;
+
+    int reserved = 0, emit = 0, tx0 = 0, ty0 = 0, w = 1;
+    unsigned g = 0;
+    int64_t off = 0;
+    if (si < n) {
+        g = (unsigned)sorted_elts[si];
+        reserved = tiles_touched[g];
+        off = offsets[si];
+        const int radius = radii[g];
+        if (radius > 0 && reserved > 0) {  // sorting.cu:44-45
+            const float2 m = reinterpret_cast<const float2*>(means_2d)[g];
+            const TileRect r = tile_rect(m.x, m.y, radius, width, height, ntx, nty);
+            const int ww = r.tx1 - r.tx0, hh = r.ty1 - r.ty0;
+            if (ww > 0 && hh > 0) { emit = ww * hh; w = ww; }
+            tx0 = r.tx0; ty0 = r.ty0;
+        }
+    }
+    int incl = reserved;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const int wpre = incl - reserved;
+    const int total = __shfl_sync(kFull, incl, 31);
+    const int64_t base = __shfl_sync(kFull, off, 0);
+
+    for (int k0 = 0; k0 < total; k0 += 32) {
+        const int k = k0 + lane;
+        int owner = 0;  // largest lane with wpre <= k
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int cand = owner + step;
+            const int vpre = __shfl_sync(kFull, wpre, cand & 31);
+            if (cand < 32 && vpre <= k) owner = cand;
+        }
+        const int j = k - __shfl_sync(kFull, wpre, owner);
+        const int o_emit = __shfl_sync(kFull, emit, owner);
+        const int o_w = __shfl_sync(kFull, w, owner);
+        const int o_tx0 = __shfl_sync(kFull, tx0, owner);
+        const int o_ty0 = __shfl_sync(kFull, ty0, owner);
+        const unsigned o_g = __shfl_sync(kFull, g, owner);
+        if (k < total && base + k < p) {
+            uint64_t pair = 0;
+            if (j < o_emit) {
+                const int ty = o_ty0 + j / o_w, tx = o_tx0 + j % o_w;  // ty outer, tx inner (:63-64)
+                pair = ((uint64_t)(unsigned)(ty * ntx + tx) << 32) | (uint64_t)o_g;
+            }
+            __stcs(pairs + base + k, pair);
+        }
+    }
+}
+
+}  // namespace cugs
+
+using namespace cugs;
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers (internal; used by api.cu)
+// ------------------------------------------------------------------------------------------------
+size_t cugs_packed_sort_temp_bytes(int64_t n, int passes, int num_tiles) {
+    const int64_t tiles = (n + kPkTile - 1) / kPkTile;
+    return (size_t)kPkMaxPasses * kPkRadix * 4 + 64 + align_up((size_t)(num_tiles > 0 ? num_tiles : 1) * 4, 256) +
+           (size_t)passes * (size_t)(tiles > 0 ? tiles : 1) * kPkRadix * 4;
+}
+
+int cugs_packed_passes(int key_bits) { return make_packed_plan(key_bits).passes; }
+
+// Stable LSD sort of n packed elements by the low `key_bits` bits of their HIGH word.
+//   a, b           : ping-pong buffers, input in a
+//   out32_last     : if non-null the last pass writes only the low words there (result elements
+//                    are then NOT materialised); else the result is in (passes odd ? b : a)
+//   tile_ranges    : if non-null (num_tiles > 0) the full key histogram is taken in the same read
+//                    as the digit histograms and turned into [start,end) ranges
+int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, uint64_t* a, uint64_t* b,
+                     int* out32_last, int num_tiles, int* tile_ranges, void* temp, size_t temp_bytes) {
+    const PackedPlan plan = make_packed_plan(key_bits);
+    if (n >= (1ll << 30))
+        return set_error(h, CUGS_ERR_UNSUPPORTED, "n = %lld >= 2^30 elements is not supported", (long long)n);
+    const size_t need = cugs_packed_sort_temp_bytes(n, plan.passes, num_tiles);
+    if (temp_bytes < need)
+        return set_error(h, CUGS_ERR_WORKSPACE, "packed sort temp too small: %zu < %zu", temp_bytes, need);
+    if (tile_ranges && num_tiles > 0 && n == 0) {
+        CUGS_CUDA_TRY(h, cudaMemsetAsync(tile_ranges, 0, (size_t)num_tiles * 8, s));
+        return CUGS_OK;
+    }
+    if (n == 0) return CUGS_OK;
+    const int64_t tiles = (n + kPkTile - 1) / kPkTile;
+    unsigned* digit_hist = reinterpret_cast<unsigned*>(temp);
+    unsigned* tickets = digit_hist + kPkMaxPasses * kPkRadix;
+    unsigned* tile_hist = tickets + 16;
+    unsigned* lookback = tile_hist + align_up((size_t)(num_tiles > 0 ? num_tiles : 1) * 4, 256) / 4;
+    CUGS_CUDA_TRY(h, cudaMemsetAsync(temp, 0, need, s));
+
+    int hist_blocks = h->sm_count * 2;
+    const int64_t hist_tile = (int64_t)kPkHistThreads * kPkHistItems;
+    if ((int64_t)hist_blocks * hist_tile > n) hist_blocks = (int)((n + hist_tile - 1) / hist_tile);
+    const bool want_ranges = tile_ranges != nullptr && num_tiles > 0;
+    const size_t hist_smem = (size_t)plan.passes * kPkRadix * 4 + (want_ranges ? (size_t)num_tiles * 4 : 0);
+    if (want_ranges) {
+        if (hist_smem > 200 * 1024)
+            return set_error(h, CUGS_ERR_UNSUPPORTED, "%d tiles exceed the shared-memory tile histogram", num_tiles);
+        CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_packed_histogram<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)hist_smem));
+        k_packed_histogram<true><<<hist_blocks, kPkHistThreads, hist_smem, s>>>(n, a, plan, digit_hist, num_tiles,
+                                                                                tile_hist);
+    } else {
+        k_packed_histogram<false><<<hist_blocks, kPkHistThreads, hist_smem, s>>>(n, a, plan, digit_hist, 0, nullptr);
+    }
+    CUGS_LAUNCH_CHECK(h, "k_packed_histogram");
+    k_packed_scan_bins<<<plan.passes, kPkRadix, 0, s>>>(digit_hist);
+    CUGS_LAUNCH_CHECK(h, "k_packed_scan_bins");
+    if (want_ranges) {
+        k_tile_hist_to_ranges<<<1, 1024, 0, s>>>(num_tiles, tile_hist, tile_ranges);
+        CUGS_LAUNCH_CHECK(h, "k_tile_hist_to_ranges");
+    }
+    CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_onesweep_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kPkSmemBytes));
+    CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_onesweep_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kPkSmemBytes));
+    uint64_t* src = a;
+    uint64_t* dst = b;
+    for (int ps = 0; ps < plan.passes; ++ps) {
+        const bool last = (ps == plan.passes - 1) && out32_last != nullptr;
+        unsigned* lb = lookback + (size_t)ps * tiles * kPkRadix;
+        if (last)
+            k_onesweep_packed<true><<<(unsigned)tiles, kPkThreads, kPkSmemBytes, s>>>(
+                n, src, dst, out32_last, digit_hist + ps * kPkRadix, lb, tickets + ps, plan.shift[ps], plan.bits[ps]);
+        else
+            k_onesweep_packed<false><<<(unsigned)tiles, kPkThreads, kPkSmemBytes, s>>>(
+                n, src, dst, nullptr, digit_hist + ps * kPkRadix, lb, tickets + ps, plan.shift[ps], plan.bits[ps]);
+        CUGS_LAUNCH_CHECK(h, "k_onesweep_packed");
+        uint64_t* t = src; src = dst; dst = t;
+    }
+    return CUGS_OK;
+}
+
+int cugs_duplicate_sorted(cugs_handle_t* h, cudaStream_t s, int64_t n, int width, int height,
+                          const uint64_t* sorted_elts, const float* means_2d, const int32_t* radii,
+                          const int32_t* tiles_touched, const int32_t* offsets_sorted, int64_t p, uint64_t* pairs) {
+    if (n == 0 || p == 0) return CUGS_OK;
+    const int ntx = (width + kTile - 1) / kTile, nty = (height + kTile - 1) / kTile;
+    const unsigned grid = (unsigned)((n + kDupBlock - 1) / kDupBlock);
+    k_duplicate_sorted<<<grid, kDupBlock, 0, s>>>(n, width, height, ntx, nty, sorted_elts, means_2d, radii,
+                                                  tiles_touched, offsets_sorted, p, pairs);
+    CUGS_LAUNCH_CHECK(h, "k_duplicate_sorted");
+    return CUGS_OK;
+}
