@@ -121,6 +121,43 @@ __device__ __forceinline__ int build_warp_list(const void* sg_void, int bc, floa
     return cnt;
 }
 
+// ---- packed FP32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, IEEE round-to-nearest per element, so
+// the results are the scalar ones bit for bit while the issue slots are halved) ------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// `power` of two pixels of one row at once, with the reference's roundings (see blend_power4):
+//   dx = px - x; s1 = fma(dx, a, dy*b); s2 = fma(dx, b, dy*c); power = fma(dx, s1, dy*s2) * -0.5
+__device__ __forceinline__ f32x2 blend_power_x2(f32x2 px, float neg_x, float dy, float a, float b, float dyb,
+                                                float dyc, f32x2& dx, f32x2& s1, f32x2& s2) {
+    dx = add2(px, pk2(neg_x, neg_x));  // px + (-x) == px - x exactly
+    s1 = fma2(dx, pk2(a, a), pk2(dyb, dyb));
+    s2 = fma2(dx, pk2(b, b), pk2(dyc, dyc));
+    return mul2(fma2(dx, s1, mul2(pk2(dy, dy), s2)), pk2(-0.5f, -0.5f));
+}
+
 // The reference's `power`, rounding for rounding (forward.cu:131-132 and
 // backward.cu:132-133 compile to the same sequence):
 //   s1 = fma(dx, a, dy*b); s2 = fma(dx, b, dy*c); power = (fma(dx, s1, dy*s2)) * -0.5
@@ -153,13 +190,17 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
     const float pyf = (float)py + 0.5f;  // forward.cu:72-73
     const int warp = threadIdx.x >> 5;
     const float patch_x0 = (float)(tile_x * kTile) + 0.5f, patch_y0 = (float)(tile_y * kTile + warp * 8) + 0.5f;
-    float pxf[kPix];
-    bool done[kPix];
+    // lim[k] = 0 while pixel k is live, -inf once it is done (or outside the image): the reference's
+    // `power > 0 -> skip` test becomes `power > lim[k]`, which also rejects everything for a done
+    // pixel at no extra cost (forward.cu:135, :153)
+    float pxf[kPix], lim[kPix];
 #pragma unroll
     for (int k = 0; k < kPix; ++k) {
         pxf[k] = (float)(px0 + k * kPixStride) + 0.5f;
-        done[k] = !((px0 + k * kPixStride < width) && (py < height));
+        lim[k] = ((px0 + k * kPixStride < width) && (py < height)) ? 0.0f : -INFINITY;
     }
+    const f32x2 px01 = pk2(pxf[0], pxf[1]), px23 = pk2(pxf[2], pxf[3]);
+#define CUGS_ALL_DONE (lim[0] < 0.0f && lim[1] < 0.0f && lim[2] < 0.0f && lim[3] < 0.0f)
 
     const int2 range = reinterpret_cast<const int2*>(tile_ranges)[tile];
     const int count = range.y - range.x;
@@ -209,7 +250,7 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
         const unsigned char* list = s_list[warp];
         const int cnt = build_warp_list(sg, bc, patch_x0, patch_y0, s_list[warp]);
         for (int i0 = 0; i0 < cnt; i0 += 8) {
-            if (__all_sync(kFull, done[0] && done[1] && done[2] && done[3])) break;
+            if (__all_sync(kFull, CUGS_ALL_DONE)) break;
             const int i1 = min(i0 + 8, cnt);
             for (int i = i0; i < i1; ++i) {
                 const int j = list[i];
@@ -219,13 +260,18 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
                 const float dyb = mul_rn(dy, q0.w), dyc = mul_rn(dy, ct.x);
                 float power[kPix];
                 bool pass[kPix];
+                {
+                    f32x2 dxa, s1a, s2a, dxb, s1b, s2b;
+                    const f32x2 pa = blend_power_x2(px01, -q0.x, dy, q0.z, q0.w, dyb, dyc, dxa, s1a, s2a);
+                    const f32x2 pb = blend_power_x2(px23, -q0.x, dy, q0.z, q0.w, dyb, dyc, dxb, s1b, s2b);
+                    unpk2(pa, power[0], power[1]);
+                    unpk2(pb, power[2], power[3]);
+                }
                 bool any = false;
 #pragma unroll
                 for (int k = 0; k < kPix; ++k) {
-                    float s1, s2;
-                    power[k] = blend_power4(pxf[k] - q0.x, dy, q0.z, q0.w, dyb, dyc, s1, s2);
                     // cheap reject: cannot reach alpha >= 1/255 (NaNs fall through to the exact path)
-                    pass[k] = !(done[k] || power[k] < ct.y || power[k] > 0.0f);
+                    pass[k] = !(power[k] < ct.y || power[k] > lim[k]);
                     any |= pass[k];
                 }
                 if (!any) continue;
@@ -242,13 +288,14 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
                     C2[k] = fma_rn(w, gb.y, C2[k]);
                     T[k] = mul_rn(T[k], add_rn(1.0f, -alpha));
                     ++contrib[k];
-                    if (T[k] < kTMin) done[k] = true;  // the crossing Gaussian is composited (forward.cu:153)
+                    if (T[k] < kTMin) lim[k] = -INFINITY;  // the crossing Gaussian is composited (forward.cu:153)
                 }
             }
         }
-        if (__syncthreads_and(done[0] && done[1] && done[2] && done[3])) break;
+        if (__syncthreads_and(CUGS_ALL_DONE)) break;
     }
     cp_async_wait<0>();
+#undef CUGS_ALL_DONE
 
     if (py < height) {
 #pragma unroll
@@ -329,7 +376,8 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
 
     // per-pixel forward outputs (backward.cu:65-87)
     float pxf[kPix], T[kPix], g0[kPix], g1[kPix], g2[kPix], S0[kPix], S1[kPix], S2[kPix];
-    int left[kPix];  // contributors still to process; <= 0 means the pixel is done
+    float lim[kPix];  // 0 while the pixel still has contributors to process, -inf afterwards (see forward)
+    int left[kPix];   // contributors still to process; <= 0 means the pixel is done
 #pragma unroll
     for (int k = 0; k < kPix; ++k) {
         pxf[k] = (float)(px0 + k * kPixStride) + 0.5f;
@@ -343,7 +391,10 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             g2[k] = dL_dcolor[pi * 3 + 2];
         }
         S0[k] = T[k] * bg_r; S1[k] = T[k] * bg_g; S2[k] = T[k] * bg_b;
+        lim[k] = (left[k] > 0) ? 0.0f : -INFINITY;
     }
+    const f32x2 px01 = pk2(pxf[0], pxf[1]), px23 = pk2(pxf[2], pxf[3]);
+#define CUGS_ALL_DONE (lim[0] < 0.0f && lim[1] < 0.0f && lim[2] < 0.0f && lim[3] < 0.0f)
 
     // batches are visited last to first; batch b covers [range.x + b*kBatch, ...)
     int next_idx[2] = {-1, -1};
@@ -384,8 +435,7 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
         const unsigned char* list = s_list[warp];
         const int cnt = build_warp_list(sg, bc, patch_x0, patch_y0, s_list[warp]);
         for (int i = cnt - 1; i >= 0; --i) {
-            if ((i & 7) == 7 && __all_sync(kFull, (left[0] <= 0) && (left[1] <= 0) && (left[2] <= 0) && (left[3] <= 0)))
-                break;
+            if ((i & 7) == 7 && __all_sync(kFull, CUGS_ALL_DONE)) break;
             const int j = list[i];
             const float4 q0 = sg[j].q0;
             const float4 q1 = sg[j].q1;
@@ -394,12 +444,19 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             const float dyb = mul_rn(dy, bq), dyc = mul_rn(dy, c);
             float power[kPix], dx[kPix], s1[kPix], s2[kPix];
             bool pass[kPix];
+            {
+                f32x2 dxa, s1a, s2a, dxb, s1b, s2b;
+                const f32x2 pa = blend_power_x2(px01, -q0.x, dy, a, bq, dyb, dyc, dxa, s1a, s2a);
+                const f32x2 pb = blend_power_x2(px23, -q0.x, dy, a, bq, dyb, dyc, dxb, s1b, s2b);
+                unpk2(pa, power[0], power[1]); unpk2(pb, power[2], power[3]);
+                unpk2(dxa, dx[0], dx[1]); unpk2(dxb, dx[2], dx[3]);
+                unpk2(s1a, s1[0], s1[1]); unpk2(s1b, s1[2], s1[3]);
+                unpk2(s2a, s2[0], s2[1]); unpk2(s2b, s2[2], s2[3]);
+            }
             bool any = false;
 #pragma unroll
             for (int k = 0; k < kPix; ++k) {
-                dx[k] = pxf[k] - q0.x;
-                power[k] = blend_power4(dx[k], dy, a, bq, dyb, dyc, s1[k], s2[k]);
-                pass[k] = !(left[k] <= 0 || power[k] < q1.y || power[k] > 0.0f);
+                pass[k] = !(power[k] < q1.y || power[k] > lim[k]);
                 any |= pass[k];
             }
             if (!__any_sync(kFull, any)) continue;
@@ -425,7 +482,7 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
                     }
                     const float alpha = fminf(oe, 0.99f);
                     if (alpha < kAlphaMin) continue;       // backward.cu:137-139
-                    --left[k];                              // found++ ; found > n_contrib -> stop (:141-145)
+                    if (--left[k] <= 0) lim[k] = -INFINITY;  // found++ ; found > n_contrib -> stop (:141-145)
                     const float oma = fmaxf(1.0f - alpha, 1e-5f);  // backward.cu:150-151
                     const float inv = __fdividef(1.0f, oma);
                     T[k] = T[k] * inv;
@@ -463,9 +520,10 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
                 atomicAdd(grad_acc + (int64_t)sid[j] * 12 + slot, (lane == 1) ? r8 : r);
             }
         }
-        if (__syncthreads_and((left[0] <= 0) && (left[1] <= 0) && (left[2] <= 0) && (left[3] <= 0))) break;
+        if (__syncthreads_and(CUGS_ALL_DONE)) break;
     }
     cp_async_wait<0>();
+#undef CUGS_ALL_DONE
 }
 
 // grad_acc [N,12] -> the four public arrays of RasterizeBackwardOutput (backward.hpp:13-18)
