@@ -76,6 +76,22 @@ __device__ __forceinline__ float dot3c(float a, float b, float c, float d, float
     return __fmaf_rn(e, f, __fmaf_rn(a, b, __fmul_rn(c, d)));
 }
 
+// Lanes of the warp holding the same `bits`-bit digit. A ballot per bit: match.any.sync is several
+// times slower when the warp holds many distinct digits (ncu: 45 % of the onesweep kernel's stall
+// samples sat on MATCH.ANY results).
+__device__ __forceinline__ unsigned match_digit(unsigned d, int bits) {
+    unsigned peers = kFull;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        if (b < bits) {
+            const bool set = (d >> b) & 1u;
+            const unsigned m = __ballot_sync(kFull, set);
+            peers &= set ? m : ~m;
+        }
+    }
+    return peers;
+}
+
 // Tile rectangle of a projected Gaussian, shared by preprocess (projection.cu:172-188) and key
 // emission (sorting.cu:52-57). (int) casts are cvt.rzi (truncate, saturate, NaN -> 0).
 struct TileRect {

@@ -150,7 +150,7 @@ k_onesweep(int64_t p, const uint64_t* __restrict__ keys_in, const int* __restric
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
         const unsigned d = digit_of(key[i], db, shift, mask);
-        const unsigned peers = __match_any_sync(kFull, d);
+        const unsigned peers = match_digit(d, bits);
         const int leader = __ffs(peers) - 1;
         unsigned old = 0;
         if (lane == leader) {

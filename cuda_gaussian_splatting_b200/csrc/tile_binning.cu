@@ -206,7 +206,7 @@ k_onesweep_packed(int64_t n, const uint64_t* __restrict__ in, uint64_t* __restri
 #pragma unroll
     for (int i = 0; i < kPkItems; ++i) {
         const unsigned d = pk_digit(e[i], shift, mask);
-        const unsigned peers = __match_any_sync(kFull, d);
+        const unsigned peers = match_digit(d, bits);
         const int leader = __ffs(peers) - 1;
         unsigned old = 0;
         if (lane == leader) {
