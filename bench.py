@@ -7,7 +7,7 @@ Metric (BASELINE.json): forward+backward throughput of the differentiable raster
 synthetic Gaussians / SH degree 3 / 1920x1080 (workload "B" = BASELINE.json configs[1]), as
 views/s (whole job) with ms/view beside it, plus the sort's GB/s.
 
-One "step" = `--views-per-gpu` views (default 1) rendered forward + backward on every GPU,
+One "step" = `--views-per-gpu` views (default 2) rendered forward + backward on every GPU,
 parameter gradients summed in place; with N > 1 GPUs the step ends with ONE NCCL all-reduce(sum)
 of the gradient arena (59 N floats + 2 N densification statistics), as BASELINE.json config[3].
 Per-GPU work is fixed as N grows ("scaling": "weak").
@@ -129,20 +129,29 @@ def sort_passes(P_bits_depth: int, num_tiles: int) -> int:
     return max(1, (P_bits_depth + tb + 7) // 8)
 
 
-def algorithmic_bytes(n: int, p: int, w: int, h: int, passes: int) -> dict:
-    """ALGORITHMIC bytes per launch of each stage (SURVEY.md §8d / DESIGN.md): each distinct
-    input read once + each output written once."""
+def algorithmic_bytes(n: int, p: int, w: int, h: int, tile_passes: int) -> dict:
+    """ALGORITHMIC bytes per frame of each stage: each distinct input read once +
+    each output written once, for the kernels as designed (depth passes hoisted before the key
+    duplication: the sort moves 8-byte packed elements)."""
     tiles = ((w + 15) // 16) * ((h + 15) // 16)
     return {
-        "preprocess_fwd": 284 * n,
-        "scan": 8 * n,
-        "duplicate_with_keys": 20 * n + 12 * p,
-        "sort": (8 + 24 * passes) * p,
-        "tile_ranges": 8 * p + 8 * tiles,
-        "blend_fwd": 40 * p + 20 * w * h,
-        "blend_bwd": 40 * p + 32 * w * h + 36 * n,
+        "preprocess_fwd": (284 + 48 + 8) * n,        # reference outputs + packed blend record + depth-sort element
+        "scan": 16 * n,                              # sorted element (8) + gathered tile count (4) + offset (4)
+        "duplicate_with_keys": 28 * n + 8 * p,       # element, offset, radius, tiles, mean (8+4+4+4+8) + packed pair
+        "sort": (8 + 4 * 16) * n + (8 + 16 * (tile_passes - 1) + 12) * p + 12 * tiles,
+        "tile_ranges": 0,                            # part of the sort (tile histogram -> ranges)
+        "blend_fwd": 52 * p + 20 * w * h,            # index (4) + packed record (48) per pair, 20 B per pixel
+        "blend_bwd": 52 * p + 20 * w * h + 48 * n,   # + dL/dcolor, final_T, n_contrib per pixel, 48-B gradient record
         "preprocess_bwd": 336 * n,
     }
+
+
+def reference_sort_bytes(p: int, w: int, h: int) -> int:
+    """The sort as the reference formulates it: 12-byte (u64 key, u32 value) pairs,
+    one histogram read + ceil((32 + tile_bits) / 8) onesweep passes."""
+    tiles = ((w + 15) // 16) * ((h + 15) // 16)
+    passes = (32 + max(0, (tiles - 1).bit_length()) + 7) // 8
+    return (8 + 24 * passes) * p
 
 
 # ------------------------------------------------------------------------------------------------
@@ -183,10 +192,14 @@ def run_b200(args) -> dict:
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     model = cugs.GaussianModel(t(scene.positions), t(scene.sh_coeffs), t(scene.opacities), t(scene.rotations),
                                t(scene.scales))
-    cams = bench_views(scene, world * V)[rank * V:(rank + 1) * V]
+    all_cams = bench_views(scene, world * V)
+    cams = [all_cams[i] for i in cugs.shard_views(world * V, world, rank)]
     settings = cugs.RenderSettings((0.0, 0.0, 0.0), 3, 1.0)
     buf = cugs.FrameBuffers(n, W, H, 16, dev)
     lib, h = _lib.load_library(), _lib.handle(local)
+
+    if args.mode == "train_step":
+        return run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world, local, dev, desc)
 
     # synthetic targets (host, pinned) and the resident dL/dcolor of each view
     rng = np.random.default_rng(4321 + rank)
@@ -202,9 +215,8 @@ def run_b200(args) -> dict:
         dLs.append(g)
     torch.cuda.synchronize()
 
-    def allreduce():
-        if world > 1:
-            dist.all_reduce(buf.grad_arena, op=dist.ReduceOp.SUM)
+    def allreduce():  # ONE collective per step: sum of the 61N-float gradient + statistics arena
+        cugs.allreduce_step(buf.grad_arena)
 
     def step_resident():
         for v in range(V):
@@ -281,9 +293,9 @@ def run_b200(args) -> dict:
         c_passes, c_bits = C.c_int(0), C.c_int(0)
         lib.cugs_b200_last_sort_plan(h, C.byref(c_passes), C.byref(c_bits))
         passes, key_bits = int(c_passes.value), int(c_bits.value)
-        alg = algorithmic_bytes(n, P, W, H, passes)
+        alg = algorithmic_bytes(n, P, W, H, max(passes - 4, 1))
         peak, peak_src = measured_peaks()
-        hbm_stages = ["preprocess_fwd", "scan", "duplicate_with_keys", "sort", "tile_ranges", "preprocess_bwd"]
+        hbm_stages = ["preprocess_fwd", "scan", "duplicate_with_keys", "sort", "preprocess_bwd"]
         rl_all = {}
         for nm in STAGES:
             ms = stages_ms[nm]
@@ -291,10 +303,18 @@ def run_b200(args) -> dict:
             rl_all[nm] = {"ms": round(ms, 4), "algorithmic_bytes": alg[nm], "achieved_gbs": round(gbs, 1),
                           "frac_of_hbm_peak": round(gbs / peak, 4),
                           "bound": "hbm" if nm in hbm_stages else "fp32-issue/L2-atomics (not HBM)"}
-        dom = max(hbm_stages, key=lambda k: stages_ms[k])
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": rl_all[dom]["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": rl_all[dom]["frac_of_hbm_peak"], "traffic": TRAFFIC.get(dom),
-                    "peak_source": peak_src, "ms": rl_all[dom]["ms"]}
+        # `roofline`: the largest HBM-bound stage that is ONE kernel launch (the sort stage is a dozen
+        # launches); the two blend kernels dominate the step but are instruction-issue bound, their
+        # HBM fraction is not a quality measure — see roofline_all / issue_bound and DESIGN.md §4
+        single = ["preprocess_fwd", "preprocess_bwd", "duplicate_with_keys", "scan"]
+        dom = max(single, key=lambda k: stages_ms[k])
+        kname = {"preprocess_fwd": "k_preprocess_fwd", "preprocess_bwd": "k_preprocess_bwd",
+                 "duplicate_with_keys": "k_duplicate_sorted", "scan": "k_scan_exclusive"}[dom]
+        roofline = {"kernel": kname, "bound": "hbm", "achieved": rl_all[dom]["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": rl_all[dom]["frac_of_hbm_peak"], "traffic": TRAFFIC.get(kname),
+                    "peak_source": peak_src, "ms": rl_all[dom]["ms"],
+                    "algorithmic_bytes_per_launch": alg[dom]}
+        ref_sort_gbs = reference_sort_bytes(P, W, H) / (stages_ms["sort"] * 1e-3) / 1e9 if stages_ms["sort"] > 0 else 0.0
         res = {
             "metric": METRIC, "value": round(value, 3), "unit": "views/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4),
@@ -313,7 +333,10 @@ def run_b200(args) -> dict:
             "stages_ms": {k: round(v_, 4) for k, v_ in stages_ms.items()},
             "stages_sum_ms": round(sum(stages_ms.values()), 4),
             "roofline_all": rl_all,
-            "sort_gbs": rl_all["sort"]["achieved_gbs"],
+            "sort_gbs": round(ref_sort_gbs, 1),
+            "sort_gbs_note": "bytes of the reference formulation (12-B pairs, 6 onesweep passes at 1080p = 152 B/pair) "
+                             "divided by the time of this library's whole sort stage (depth sort of N + tile sort of P); "
+                             "roofline_all.sort uses the bytes this design actually has to move",
             "sort_mpairs_per_s": round(P / (stages_ms["sort"] * 1e-3) / 1e6, 1) if stages_ms["sort"] > 0 else None,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -322,6 +345,65 @@ def run_b200(args) -> dict:
         dist.barrier()
         dist.destroy_process_group()
     return res
+
+
+def run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world, local, dev, desc):
+    """BASELINE.json configs[2]: the full training step (render fwd + fused L1/SSIM loss + render bwd
+    with fused densification statistics + one all-reduce + ONE fused Adam launch) through
+    SyntheticTrainer (the Trainer::train_step skeleton, training/trainer.cpp:178-316)."""
+    import numpy as np
+    from cuda_gaussian_splatting_b200 import _lib
+    n, W, H = scene.n, scene.camera.width, scene.camera.height
+    V = args.views_per_gpu
+    rng = np.random.default_rng(4321 + rank)
+    targets = [torch.from_numpy(rng.uniform(size=(H, W, 3)).astype(np.float32)).to(dev) for _ in range(V)]
+    trainer = cugs.SyntheticTrainer(model, cams, targets, cugs.TrainConfig(), total_views_per_step=world * V)
+    lib, h = _lib.load_library(), _lib.handle(local)
+    step_no = [3000]  # SH degree 3 active (lr_schedule.hpp:70-72)
+
+    def step():
+        trainer.train_step(step_no[0])
+        step_no[0] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = int(lib.cugs_b200_launch_count(h))
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = int(lib.cugs_b200_launch_count(h)) - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else {}
+    loss = float(trainer.last_scalars[0])
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    views = world * V * args.steps
+    return {"metric": "training views/s (render fwd+bwd + L1/SSIM loss + densification stats + fused Adam)",
+            "value": round(views / (total_ms * 1e-3), 3), "unit": "views/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4),
+            "ms_per_view": round(total_ms / args.steps / V, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc.replace("fwd+bwd", "full training step"), "views_per_gpu_per_step": V,
+                       "adam_elements": 59 * n, "l2": "inputs exceed L2"},
+            "clocks": clocks, "gpu_launches": launches, "final_loss": loss}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
@@ -363,7 +445,7 @@ def run_reference(args) -> dict:
     base = {"impl": "reference", "metric": METRIC, "unit": "views/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "views_per_gpu_per_step": 1}}
+            "config": {"workload": desc, "views_per_gpu_per_step": args.views_per_gpu}}
     ref = None
     why = ""
     try:
@@ -383,22 +465,28 @@ def run_reference(args) -> dict:
     torch.cuda.set_device(local)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     pos, sh, opa, rot, scl = t(scene.positions), t(scene.sh_coeffs), t(scene.opacities), t(scene.rotations), t(scene.scales)
-    cam, bg = scene.camera.as_ref_list(), [0.0, 0.0, 0.0]
-    target_host = torch.from_numpy(np.random.default_rng(4321).uniform(size=(H, W, 3)).astype(np.float32)).pin_memory()
-    target = target_host.to(dev)
-    out = ref.render(pos, sh, opa, rot, scl, cam, bg, 3, 1.0)
-    _, _, _, dL = ref.combined_loss_with_grad(out[0], target, 0.2)
+    V = args.views_per_gpu
+    cams, bg = [c.as_ref_list() for c in bench_views(scene, V)], [0.0, 0.0, 0.0]
+    rng = np.random.default_rng(4321)
+    targets_host = [torch.from_numpy(rng.uniform(size=(H, W, 3)).astype(np.float32)).pin_memory() for _ in range(V)]
+    dLs = []
+    for v in range(V):
+        out = ref.render(pos, sh, opa, rot, scl, cams[v], bg, 3, 1.0)
+        _, _, _, dL = ref.combined_loss_with_grad(out[0], targets_host[v].to(dev), 0.2)
+        dLs.append(dL)
 
-    def step_resident():
-        o = ref.render(pos, sh, opa, rot, scl, cam, bg, 3, 1.0)
-        ref.render_backward(dL, o, pos, sh, opa, rot, scl, cam, bg, 3, 1.0)
+    def step_resident():  # the reference has no gradient accumulation: each view's gradients are separate tensors
+        for v in range(V):
+            o = ref.render(pos, sh, opa, rot, scl, cams[v], bg, 3, 1.0)
+            ref.render_backward(dLs[v], o, pos, sh, opa, rot, scl, cams[v], bg, 3, 1.0)
 
     def step_e2e():
-        tg = target_host.to(dev, non_blocking=True)
-        o = ref.render(pos, sh, opa, rot, scl, cam, bg, 3, 1.0)
-        loss, _, _, g = ref.combined_loss_with_grad(o[0], tg, 0.2)   # trainer.cpp:214-225
-        ref.render_backward(g, o, pos, sh, opa, rot, scl, cam, bg, 3, 1.0)
-        loss.item()
+        for v in range(V):
+            tg = targets_host[v].to(dev, non_blocking=True)
+            o = ref.render(pos, sh, opa, rot, scl, cams[v], bg, 3, 1.0)
+            loss, _, _, g = ref.combined_loss_with_grad(o[0], tg, 0.2)   # trainer.cpp:214-225
+            ref.render_backward(g, o, pos, sh, opa, rot, scl, cams[v], bg, 3, 1.0)
+            loss.item()
 
     def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -419,16 +507,16 @@ def run_reference(args) -> dict:
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
-    value = args.steps / (ms * 1e-3)
+    value = args.steps * V / (ms * 1e-3)
     base.update({
-        "value": round(value, 3), "ms_per_step": round(ms / args.steps, 4), "ms_per_view": round(ms / args.steps, 4),
+        "value": round(value, 3), "ms_per_step": round(ms / args.steps, 4), "ms_per_view": round(ms / args.steps / V, 4),
         "clocks": clocks,
         "cpu_baseline": {"value": round(value, 3), "unit": "views/s", "cores": 0, "kind": "reference",
                          "sample": "the unmodified reference's own CUDA render()+render_backward() (oracle/_ref, built "
                                    "for sm_100), full workload, run on the GPU: the reference has no CPU rasterizer"},
-        "e2e": {"value": round(args.steps / (e2e_ms * 1e-3), 3), "unit": "views/s",
-                "ms_per_view": round(e2e_ms / args.steps, 4),
-                "h2d_bytes_per_step": H * W * 3 * 4, "d2h_bytes_per_step": 4,
+        "e2e": {"value": round(args.steps * V / (e2e_ms * 1e-3), 3), "unit": "views/s",
+                "ms_per_view": round(e2e_ms / args.steps / V, 4),
+                "h2d_bytes_per_step": V * H * W * 3 * 4, "d2h_bytes_per_step": V * 4,
                 "what": "H2D target (pinned) -> ref render -> ref combined_loss + autograd -> ref render_backward -> loss.item()"},
         "P_pairs": int(out[9].numel()),
     })
@@ -442,8 +530,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
-    ap.add_argument("--views-per-gpu", type=int, default=1)
+    ap.add_argument("--views-per-gpu", type=int, default=2,
+                    help="views rendered fwd+bwd per GPU per step (2 = BASELINE config[3]: 16 views/step on 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="fwd_bwd", choices=["fwd_bwd", "train_step"],
+                    help="fwd_bwd = the headline metric; train_step = BASELINE config[2] (full step incl. loss, Adam, stats)")
     args = ap.parse_args()
     res = run_reference(args) if args.impl == "reference" else run_b200(args)
     if res is not None:

@@ -449,20 +449,17 @@ class FrameBuffers:
         # positions, sh_coeffs, opacities, scales, rotations) followed by the two additive
         # densification statistics of the step, so that view-parallel training needs exactly one
         # all-reduce(sum) per step. Segment starts are 256-byte aligned (float4 accesses).
-        sizes = [3 * n, 3 * num_coeffs * n, n, 3 * n, 4 * n, n, n]
-        starts, off = [], 0
-        for sz in sizes:
-            starts.append(off)
-            off += (sz + 63) // 64 * 64
-        self.grad_arena = torch.zeros((max(off, 64),), **f)
-        seg = lambda k: self.grad_arena[starts[k]:starts[k] + sizes[k]]
-        self.dL_dpositions = seg(0).view(n, 3)
-        self.dL_dsh_coeffs = seg(1).view(n, 3, num_coeffs)
-        self.dL_dopacities = seg(2).view(n, 1)
-        self.dL_dscales = seg(3).view(n, 3)
-        self.dL_drotations = seg(4).view(n, 4)
-        self.step_grad_accum = seg(5)   # sum over the step's views of ||dL/dmeans_2d|| (visible only)
-        self.step_grad_count = seg(6)   # number of the step's views in which the Gaussian was visible
+        from .parallel import arena_layout
+        layout, total = arena_layout(n, num_coeffs)
+        self.grad_arena = torch.zeros((total,), **f)
+        seg = lambda nm: self.grad_arena[layout[nm][0]:layout[nm][0] + layout[nm][1]]
+        self.dL_dpositions = seg("positions").view(n, 3)
+        self.dL_dsh_coeffs = seg("sh_coeffs").view(n, 3, num_coeffs)
+        self.dL_dopacities = seg("opacities").view(n, 1)
+        self.dL_dscales = seg("scales").view(n, 3)
+        self.dL_drotations = seg("rotations").view(n, 4)
+        self.step_grad_accum = seg("grad_accum")   # sum over the step's views of ||dL/dmeans_2d|| (visible only)
+        self.step_grad_count = seg("grad_count")   # number of the step's views in which the Gaussian was visible
         self.step_max_radii = torch.zeros((n,), **f)  # needs a max-reduction, kept outside the arena
         self.dL_dmeans_2d = torch.empty((n, 2), **f)
 

@@ -204,3 +204,74 @@ class DensificationStats:
                                             _ptr(radii.contiguous()), _ptr(self.grad_accum),
                                             _ptr(self.grad_count), _ptr(self.max_radii_2d))
         _lib.check(h, st, "cugs_b200_accumulate_stats")
+
+
+# ----------------------------------------------------------------------------------------------
+# training-step driver on synthetic views (the caller of the hot path: training/trainer.cpp:178-316)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class TrainConfig:  # the fields of training/trainer.hpp:38-75 that reach the hot path
+    lambda_ssim: float = 0.2
+    max_sh_degree: int = 3
+    background: tuple = (0.0, 0.0, 0.0)
+    adam: AdamConfig = field(default_factory=AdamConfig)
+    densify: bool = True  # accumulate the ADC statistics every step (trainer.cpp:269)
+
+
+class SyntheticTrainer:
+    """``Trainer::train_step`` (training/trainer.cpp:178-316) without the Dataset: per step
+    update_lr -> active SH degree -> for each of the rank's views: render -> fused L1+SSIM loss and
+    its gradient -> render_backward (gradients summed in place over the views, densification
+    statistics fused into the same launch) -> ONE all-reduce over the ranks -> ONE fused Adam launch
+    with grad_scale = 1 / total views. No host synchronisation except the per-view pair-count read
+    (the reference has 3-6 `.item()` syncs per step: trainer.cpp:205-207, :223-224, :308)."""
+
+    def __init__(self, model: GaussianModel, cameras, targets, config: Optional[TrainConfig] = None,
+                 total_views_per_step: Optional[int] = None):
+        from .rasterizer import FrameBuffers, RenderSettings
+        self.model, self.cameras, self.targets = model, list(cameras), list(targets)
+        self.config = config or TrainConfig()
+        self.total_views = int(total_views_per_step or len(self.cameras))
+        n = model.num_gaussians()
+        cam0 = self.cameras[0]
+        self.buffers = FrameBuffers(n, cam0.width, cam0.height, int(model.sh_coeffs.shape[2]), model.positions.device)
+        self.optimizer = FusedAdam(model, self.config.adam)
+        self.optimizer.grad_scale = 1.0 / float(self.total_views)
+        self.stats = DensificationStats(n, model.positions.device)
+        self._RenderSettings = RenderSettings
+        self.last_scalars = None
+
+    def train_step(self, step: int) -> torch.Tensor:
+        from .parallel import allreduce_step, fold_step_stats
+        from .rasterizer import BackwardOutput, render, render_backward
+        cfg, b = self.config, self.buffers
+        self.optimizer.update_lr(step)                                   # trainer.cpp:180
+        degree = active_sh_degree_for_step(step, cfg.max_sh_degree)      # :183
+        settings = self._RenderSettings(cfg.background, degree, 1.0)
+        multi = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size() > 1
+        if cfg.densify:
+            if multi:  # per-step statistics live in the arena and are summed by the all-reduce
+                b.step_grad_accum.zero_(); b.step_grad_count.zero_(); b.step_max_radii.zero_()
+                stats = (b.step_grad_accum, b.step_grad_count, b.step_max_radii)
+            else:
+                stats = self.stats.as_tuple()
+        else:
+            stats = None
+        scal_sum = None
+        for k, (cam, target) in enumerate(zip(self.cameras, self.targets)):
+            out = render(self.model, cam, settings, b)                   # :211
+            scalars, dL = combined_loss_with_grad(out.color, target, cfg.lambda_ssim)  # :214-225 in one pass
+            render_backward(dL, out, self.model, cam, settings, b, stats=stats, accumulate=(k > 0))  # :228, :269
+            scal_sum = scalars if scal_sum is None else scal_sum + scalars
+        if multi:
+            allreduce_step(b.grad_arena, b.step_max_radii if cfg.densify else None)
+            if cfg.densify:
+                fold_step_stats(b.step_grad_accum, b.step_grad_count, b.step_max_radii, self.stats.grad_accum,
+                                self.stats.grad_count, self.stats.max_radii_2d)
+        self.optimizer.zero_grad()                                       # :240-242
+        self.optimizer.apply_gradients(BackwardOutput(b.dL_dpositions, b.dL_drotations, b.dL_dscales,
+                                                      b.dL_dopacities, b.dL_dsh_coeffs, b.dL_dmeans_2d))
+        self.optimizer.step()
+        self.last_scalars = scal_sum / float(len(self.cameras))
+        return self.last_scalars
