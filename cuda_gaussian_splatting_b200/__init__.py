@@ -14,7 +14,7 @@ from .rasterizer import (  # noqa: F401
 )
 from .training import (  # noqa: F401
     AdamConfig, DensificationStats, FusedAdam, PositionLRConfig, SyntheticTrainer, TrainConfig, active_sh_degree_for_step, combined_loss,
-    combined_loss_with_grad, l1_loss, position_lr, ssim_loss, ssim_mean,
+    combined_loss_with_grad, l1_loss, position_lr, ssim, ssim_loss, ssim_mean,
 )
 from .synth import Scene, default_camera, ring_cameras, synth  # noqa: F401
 from .parallel import allreduce_step, arena_layout, fold_step_stats, grad_scale_for, shard_views  # noqa: F401

@@ -67,7 +67,7 @@ SIGNATURES = {
     "cugs_b200_set_stage_timing": (_INT, [_P, _INT]),
     "cugs_b200_get_stage_ms": (_INT, [_P, C.POINTER(_F)]),
     "cugs_b200_loss_workspace_bytes": (_SZ, [_INT, _INT]),
-    "cugs_b200_loss_l1_ssim": (_INT, [_P, _P, _INT, _INT, _F, _P, _P, _P, _P, _P, _SZ]),
+    "cugs_b200_loss_l1_ssim": (_INT, [_P, _P, _INT, _INT, _F, _P, _P, _P, _P, _P, _SZ, _P]),
     "cugs_b200_adam_step": (_INT, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
                                     C.POINTER(_I64), C.POINTER(_F), _F, _F, _F, _F, _F, _F]),
     "cugs_b200_accumulate_stats": (_INT, [_P, _P, _I64, _P, _P, _P, _P, _P]),

@@ -30,7 +30,8 @@ struct SsimWindow {
 __global__ void __launch_bounds__(256)
 k_ssim_moments(int width, int height, SsimWindow win, const float* __restrict__ x_img,
                const float* __restrict__ y_img, float* __restrict__ g1, float* __restrict__ g2,
-               float* __restrict__ g3, double* __restrict__ sums /* [2]: sum|x-y|, sum S */) {
+               float* __restrict__ g3, double* __restrict__ sums /* [2]: sum|x-y|, sum S */,
+               float* __restrict__ ssim_map /* optional [H,W]: channel mean of S (loss.cpp:123) */) {
     __shared__ float sx[kLossIn][kLossIn * 3];
     __shared__ float sy[kLossIn][kLossIn * 3];
     __shared__ float sh[5][kLossIn][kLossTile * 3];
@@ -72,6 +73,7 @@ k_ssim_moments(int width, int height, SsimWindow win, const float* __restrict__ 
     const int lx = threadIdx.x % kLossTile, ly = threadIdx.x / kLossTile;
     const int gx = tx0 + lx, gy = ty0 + ly;
     float l1_local = 0.f, s_local = 0.f;
+    float s_pixel = 0.f;
     if (gx < width && gy < height) {
         const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
 #pragma unroll
@@ -97,8 +99,10 @@ k_ssim_moments(int width, int height, SsimWindow win, const float* __restrict__ 
             g2[gi] = -S / B2;
             g3[gi] = 2.0f * A1 * inv;
             s_local += S;
+            s_pixel += S;
             l1_local += fabsf(sx[ly + kHalo][(lx + kHalo) * 3 + ch] - sy[ly + kHalo][(lx + kHalo) * 3 + ch]);
         }
+        if (ssim_map != nullptr) ssim_map[(int64_t)gy * width + gx] = s_pixel / 3.0f;
     }
     // block reduction -> one double atomic per block and quantity
 #pragma unroll
@@ -290,7 +294,7 @@ extern "C" size_t cugs_b200_loss_workspace_bytes(int width, int height) {
 
 extern "C" int cugs_b200_loss_l1_ssim(cugs_handle_t* h, void* stream, int width, int height, float lambda,
                                       const float* rendered, const float* target, float* dL_dcolor,
-                                      float* scalars3, void* workspace, size_t workspace_bytes) {
+                                      float* scalars3, void* workspace, size_t workspace_bytes, float* ssim_map) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, width > 0 && height > 0, "image size must be positive");
     CUGS_REQUIRE(h, rendered && target && scalars3 && workspace, "null pointer");
@@ -306,7 +310,7 @@ extern "C" int cugs_b200_loss_l1_ssim(cugs_handle_t* h, void* stream, int width,
     float* g3 = g2 + plane;
     CUGS_CUDA_TRY(h, cudaMemsetAsync(sums, 0, 64, s));
     const dim3 grid((width + kLossTile - 1) / kLossTile, (height + kLossTile - 1) / kLossTile);
-    k_ssim_moments<<<grid, 256, 0, s>>>(width, height, win, rendered, target, g1, g2, g3, sums);
+    k_ssim_moments<<<grid, 256, 0, s>>>(width, height, win, rendered, target, g1, g2, g3, sums, ssim_map);
     CUGS_LAUNCH_CHECK(h, "k_ssim_moments");
     if (dL_dcolor) {
         k_ssim_gradient<<<grid, 256, 0, s>>>(width, height, win, lambda, rendered, target, g1, g2, g3, dL_dcolor);

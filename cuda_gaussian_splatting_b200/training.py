@@ -42,8 +42,9 @@ _loss_ws: dict = {}
 
 
 def combined_loss_with_grad(rendered: torch.Tensor, target: torch.Tensor, lambda_: float = 0.2,
-                            want_grad: bool = True):
-    """One fused pass: returns (scalars[3] = {loss, l1, mean ssim} on device, dL/d(rendered))."""
+                            want_grad: bool = True, ssim_map: Optional[torch.Tensor] = None):
+    """One fused pass: returns (scalars[3] = {loss, l1, mean ssim} on device, dL/d(rendered)).
+    ``ssim_map`` (optional [H,W] output) receives what the reference's ``ssim()`` returns."""
     _validate_pair(rendered, target)
     dev = rendered.device
     lib, h = _lib_and_handle(dev)
@@ -56,7 +57,8 @@ def combined_loss_with_grad(rendered: torch.Tensor, target: torch.Tensor, lambda
     scalars = torch.empty((3,), dtype=torch.float32, device=dev)
     grad = torch.empty_like(rendered, memory_format=torch.contiguous_format) if want_grad else None
     st = lib.cugs_b200_loss_l1_ssim(h, _stream(dev), W, H, float(lambda_), _ptr(rendered.contiguous()),
-                                    _ptr(target.contiguous()), _ptr(grad), _ptr(scalars), _ptr(ws), ws.numel())
+                                    _ptr(target.contiguous()), _ptr(grad), _ptr(scalars), _ptr(ws), ws.numel(),
+                                    _ptr(ssim_map))
     _lib.check(h, st, "cugs_b200_loss_l1_ssim")
     return scalars, grad
 
@@ -71,6 +73,14 @@ def l1_loss(rendered, target) -> torch.Tensor:  # loss.hpp:22
 
 def ssim_loss(rendered, target) -> torch.Tensor:  # loss.hpp:43
     return 1.0 - combined_loss_with_grad(rendered, target, 1.0, want_grad=False)[0][2]
+
+
+def ssim(rendered, target, window_size: int = 11) -> torch.Tensor:  # loss.hpp:33 -> [H,W] map
+    _check(window_size == 11, f"only the reference's default window_size = 11 is implemented, got {window_size}")
+    _validate_pair(rendered, target)
+    m = torch.empty(rendered.shape[:2], dtype=torch.float32, device=rendered.device)
+    combined_loss_with_grad(rendered, target, 1.0, want_grad=False, ssim_map=m)
+    return m
 
 
 def ssim_mean(rendered, target) -> torch.Tensor:

@@ -206,11 +206,13 @@ int cugs_b200_get_stage_ms(cugs_handle_t* h, float* ms8);
 /* ---- stage 7: fused L1 + SSIM loss and fused multi-tensor Adam ------------------------------
  * loss: combined_loss (training/loss.cpp:131-135) value AND its gradient w.r.t. rendered (the
  * reference gets the gradient from libtorch autograd, training/trainer.cpp:214-217).
- * scalars3 (device) = {loss, l1, mean ssim}. workspace: cugs_b200_loss_workspace_bytes(w,h). */
+ * scalars3 (device) = {loss, l1, mean ssim}. workspace: cugs_b200_loss_workspace_bytes(w,h).
+ * ssim_map (optional, may be NULL): [H,W] per-pixel SSIM averaged over the three channels, what
+ * cugs::ssim returns (training/loss.cpp:88-124; consumed by training/metrics.cpp:41-46). */
 size_t cugs_b200_loss_workspace_bytes(int width, int height);
 int cugs_b200_loss_l1_ssim(cugs_handle_t* h, void* stream, int width, int height, float lambda,
                            const float* rendered, const float* target, float* dL_dcolor,
-                           float* scalars3, void* workspace, size_t workspace_bytes);
+                           float* scalars3, void* workspace, size_t workspace_bytes, float* ssim_map);
 /* Adam: FusedAdam::step (optimizer/fused_adam.cu:140-164) + k_fused_adam (:44-76) for all five
  * groups in ONE launch. Group order positions, sh_coeffs, opacities, scales, rotations
  * (fused_adam.cu:94-97); counts[g] = number of floats. bc1/bc2 are computed by the caller in

@@ -1,0 +1,103 @@
+"""Drop-in check on the GPU: the reference's own C++ host API (GaussianModel / CameraInfo /
+RenderSettings / FusedAdam, declared by the reference's unmodified headers) DEFINED by
+wrapper/cugs_b200_dropin.cpp on top of libcugs_b200.so, driven through the same pybind harness
+(oracle/ref_harness.cpp) as the compiled reference. `cugs_dropin` and `cugs_ref` expose identical
+functions, so every check is "same call, two libraries"."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import cuda_gaussian_splatting_b200 as cugs
+from conftest import ROOT, to_torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    if not t.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return t
+
+
+@pytest.fixture(scope="module")
+def dropin(torch):
+    sys.path.insert(0, str(ROOT / "oracle" / "_ref"))
+    try:
+        import cugs_dropin
+        return cugs_dropin
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"oracle/_ref/cugs_dropin*.so not built (make -f oracle/Makefile.ref dropin): {e}")
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("n,w,h,seed,adv", [(5000, 320, 240, 11, False), (20000, 640, 360, 13, True),
+                                            (100_000, 1280, 720, 1235, False)])
+def test_render_and_backward_same_call_two_libraries(ref, dropin, torch, n, w, h, seed, adv):
+    scene = cugs.synth(n, w, h, seed=seed, adversarial=adv)
+    m = to_torch(scene)
+    cam, bg = scene.camera.as_ref_list(), [0.1, 0.2, 0.3]
+    args = (m.positions, m.sh_coeffs, m.opacities, m.rotations, m.scales, cam, bg, 3, 1.0)
+    r, d = ref.render(*args), dropin.render(*args)
+    for k, name in enumerate(["color", "final_T", "n_contrib", "means_2d", "depths", "cov_2d_inv", "radii", "rgb",
+                              "opacities_act", "gaussian_indices", "tile_ranges"]):
+        assert r[k].shape == d[k].shape and r[k].dtype == d[k].dtype, name
+    for k in (2, 6, 9, 10):  # n_contrib, radii, sort order, tile ranges: bit-exact
+        assert torch.equal(r[k], d[k])
+    for k in (3, 4, 5, 8):   # means_2d, depths, cov_2d_inv, opacities_act: bit-exact floats
+        assert torch.equal(r[k].view(torch.int32), d[k].view(torch.int32))
+    assert float((r[0] - d[0]).abs().max()) <= 1e-4 and float((r[1] - d[1]).abs().max()) <= 1e-6
+    g = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, size=(h, w, 3)).astype(np.float32)).cuda()
+    rb = ref.render_backward(g, r, *args)
+    db = dropin.render_backward(g, d, *args)        # cached frame: fused path
+    db2 = dropin.render_backward(g, r, *args)       # foreign RenderOutput: stage-function path
+    for a, b_, c in zip(rb, db, db2):
+        na = float(a.double().norm())
+        assert a.shape == b_.shape == c.shape
+        assert float((a.double() - b_.double()).norm()) <= 1e-3 * na + 1e-12
+        assert float((a.double() - c.double()).norm()) <= 1e-3 * na + 1e-12
+
+
+def test_stage_functions_same_call_two_libraries(ref, dropin, torch):
+    scene = cugs.synth(5000, 320, 240, seed=11)
+    m = to_torch(scene)
+    cam = scene.camera.as_ref_list()
+    pr = ref.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs, cam, 3, 1.0)
+    pd = dropin.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs, cam, 3, 1.0)
+    assert torch.equal(pr[3], pd[3]) and torch.equal(pr[4], pd[4])  # radii, tiles_touched
+    sr = ref.sort_gaussians(pr[0], pr[1], pr[3], pr[4], 320, 240)
+    sd = dropin.sort_gaussians(pr[0], pr[1], pr[3], pr[4], 320, 240)
+    assert all(torch.equal(a, b) for a, b in zip(sr, sd))           # keys, values, ranges, P
+    fr = ref.rasterize_forward(pr[0], pr[2], pr[5], pr[6], sr[2], sr[1], 320, 240, [0.0, 0.0, 0.0])
+    fd = dropin.rasterize_forward(pr[0], pr[2], pr[5], pr[6], sr[2], sr[1], 320, 240, [0.0, 0.0, 0.0])
+    assert torch.equal(fr[2], fd[2]) and torch.equal(fr[0], fd[0]) and torch.equal(fr[1], fd[1])  # bit-identical blend
+
+
+def test_loss_autograd_and_adam_same_call_two_libraries(ref, dropin, torch):
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.uniform(size=(90, 130, 3)).astype(np.float32)).cuda()
+    y = torch.from_numpy(rng.uniform(size=(90, 130, 3)).astype(np.float32)).cuda()
+    lr_, l1r, sr, gr = ref.combined_loss_with_grad(x, y, 0.2)   # combined_loss + loss.backward() + l1 + ssim().mean()
+    ld, l1d, sd, gd = dropin.combined_loss_with_grad(x, y, 0.2)
+    assert abs(float(lr_) - float(ld)) <= 1e-5 and abs(float(l1r) - float(l1d)) <= 1e-6 and abs(float(sr) - float(sd)) <= 1e-5
+    assert float((gr - gd).abs().max()) <= 1e-3 * float(gr.abs().max())
+    assert float((ref.ssim(x, y) - dropin.ssim(x, y)).abs().max()) <= 1e-4   # [H,W] map (metrics.cpp:41-46)
+    with pytest.raises(RuntimeError):  # c10::Error, as tests/test_loss.cpp:143-170 expects
+        dropin.combined_loss(x[:, :, :2], y[:, :, :2])
+    scene = cugs.synth(1003, 64, 48, seed=21)
+    a, b = to_torch(scene), to_torch(scene)
+    oa = ref.FusedAdam(a.positions, a.sh_coeffs, a.opacities, a.rotations, a.scales)
+    ob = dropin.FusedAdam(b.positions, b.sh_coeffs, b.opacities, b.rotations, b.scales)
+    for step in range(5):
+        g = [torch.from_numpy(rng.normal(size=tuple(t.shape)).astype(np.float32)).cuda()
+             for t in (a.positions, a.rotations, a.scales, a.opacities, a.sh_coeffs)]
+        oa.step(g, step)
+        ob.step(g, step)
+    for p, q in zip(oa.params(), ob.params()):
+        assert torch.equal(p.view(torch.int32), q.view(torch.int32)), "FusedAdam must be bit-identical"
