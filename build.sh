@@ -5,10 +5,11 @@ set -euo pipefail
 cd "$(dirname "$0")"
 SRC=cuda_gaussian_splatting_b200/csrc
 OUT=cuda_gaussian_splatting_b200
-OBJ=build/obj
+LIBNAME=${LIBNAME:-libcugs_b200.so}
+OBJ=${OBJDIR:-build/obj}
 mkdir -p "$OBJ"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=default"
+FLAGS="${EXTRA_NVCC_FLAGS:-} -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=default"
 pids=()
 for f in preprocess binning radix_sort tile_binning blend train_ops api; do
   if [ ! -f "$OBJ/$f.o" ] || [ "$SRC/$f.cu" -nt "$OBJ/$f.o" ] || [ "$SRC/common.cuh" -nt "$OBJ/$f.o" ] || [ include/cugs_b200.h -nt "$OBJ/$f.o" ]; then
@@ -17,5 +18,5 @@ for f in preprocess binning radix_sort tile_binning blend train_ops api; do
   fi
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
-$NVCC -shared -o "$OUT/libcugs_b200.so" $OBJ/preprocess.o $OBJ/binning.o $OBJ/radix_sort.o $OBJ/tile_binning.o $OBJ/blend.o $OBJ/train_ops.o $OBJ/api.o -lcudart
-echo "built $OUT/libcugs_b200.so"
+$NVCC -shared -o "$OUT/$LIBNAME" $OBJ/preprocess.o $OBJ/binning.o $OBJ/radix_sort.o $OBJ/tile_binning.o $OBJ/blend.o $OBJ/train_ops.o $OBJ/api.o -lcudart
+echo "built $OUT/$LIBNAME"

@@ -33,6 +33,12 @@
 namespace cugs {
 
 constexpr int kBlendThreads = 64;
+#ifndef CUGS_FWD_MINBLOCKS
+#define CUGS_FWD_MINBLOCKS 16
+#endif
+#ifndef CUGS_BWD_MINBLOCKS
+#define CUGS_BWD_MINBLOCKS 12
+#endif
 constexpr int kPix = 4;      // pixels per thread (one row segment)
 constexpr int kBatch = 128;  // Gaussians per staged batch (two per thread)
 constexpr float kAlphaMin = 1.0f / 255.0f;
@@ -52,6 +58,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ float exp2f_fast(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 template <int N>
@@ -173,7 +184,7 @@ __device__ __forceinline__ float blend_power4(float dx, float dy, float a, float
 // forward
 // ================================================================================================
 template <bool kPacked>
-__global__ void __launch_bounds__(kBlendThreads)
+__global__ void __launch_bounds__(kBlendThreads, CUGS_FWD_MINBLOCKS)
 k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             const int* __restrict__ tile_ranges, const int* __restrict__ gaussian_idx,
             const float4* __restrict__ packed, const float* __restrict__ means_2d,
@@ -350,7 +361,7 @@ __device__ __forceinline__ void warp_reduce9(const float (&v)[9], int lane, floa
 }
 
 template <bool kPacked>
-__global__ void __launch_bounds__(kBlendThreads)
+__global__ void __launch_bounds__(kBlendThreads, CUGS_BWD_MINBLOCKS)
 k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             const int* __restrict__ tile_ranges, const int* __restrict__ gaussian_idx,
             const float4* __restrict__ packed, const float* __restrict__ means_2d,
@@ -369,6 +380,9 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
     const float pyf = (float)py + 0.5f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float patch_x0 = (float)(tile_x * kTile) + 0.5f, patch_y0 = (float)(tile_y * kTile + warp * 8) + 0.5f;
+    // after warp_reduce9 lanes 0,4,...,28 hold v0..v7 and lane 1 takes v8: nine lanes, nine consecutive floats
+    const int red_slot = (lane == 1) ? 8
+                         : ((lane & 3) == 0 ? (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)) : -1);
 
     const int2 range = reinterpret_cast<const int2*>(tile_ranges)[tile];
     const int count = range.y - range.x;
@@ -484,7 +498,7 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
                     if (alpha < kAlphaMin) continue;       // backward.cu:137-139
                     if (--left[k] <= 0) lim[k] = -INFINITY;  // found++ ; found > n_contrib -> stop (:141-145)
                     const float oma = fmaxf(1.0f - alpha, 1e-5f);  // backward.cu:150-151
-                    const float inv = __fdividef(1.0f, oma);
+                    const float inv = rcp_fast(oma);  // oma >= 1e-5: no denormal handling needed
                     T[k] = T[k] * inv;
                     const float w = alpha * T[k];
                     v[0] = fmaf(g0[k], w, v[0]);
@@ -513,12 +527,7 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             }
             float r, r8;
             warp_reduce9(v, lane, r, r8);
-            // lanes 0,4,...,28 hold v0..v7; lane 1 takes v8: nine lanes, nine consecutive floats
-            const bool writer = ((lane & 3) == 0) || (lane == 1);
-            if (writer) {
-                const int slot = (lane == 1) ? 8 : (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1));
-                atomicAdd(grad_acc + (int64_t)sid[j] * 12 + slot, (lane == 1) ? r8 : r);
-            }
+            if (red_slot >= 0) atomicAdd(grad_acc + (int64_t)sid[j] * 12 + red_slot, (red_slot == 8) ? r8 : r);
         }
         if (__syncthreads_and(CUGS_ALL_DONE)) break;
     }

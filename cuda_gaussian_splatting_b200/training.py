@@ -285,3 +285,39 @@ class SyntheticTrainer:
         self.optimizer.step()
         self.last_scalars = scal_sum / float(len(self.cameras))
         return self.last_scalars
+
+
+class TargetUploader:
+    """Host -> device upload of the per-view target images on a side stream, double-buffered, so the
+    PCIe copy of view v+1 overlaps the rendering of view v (the reference's trainer loads and uploads
+    the image synchronously every step: training/trainer.cpp:186-198)."""
+
+    def __init__(self, height: int, width: int, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.bufs = [torch.empty((height, width, 3), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.cur = None      # buffer handed out by get() and possibly still in use
+        self.pending = None  # buffer being filled by prefetch()
+
+    def prefetch(self, host_image: torch.Tensor) -> None:
+        """Start the copy of a pinned host image into the buffer that is not in use."""
+        s = 0 if self.cur is None else self.cur ^ 1
+        self.stream.wait_event(self.consumed[s])  # the previous consumer of this buffer must be done
+        with torch.cuda.stream(self.stream):
+            self.bufs[s].copy_(host_image, non_blocking=True)
+            self.ready[s].record(self.stream)
+        self.pending = s
+
+    def get(self) -> torch.Tensor:
+        """The most recently prefetched image, usable on the current stream."""
+        assert self.pending is not None, "prefetch() first"
+        s = self.pending
+        torch.cuda.current_stream(self.device).wait_event(self.ready[s])
+        self.cur, self.pending = s, None
+        return self.bufs[s]
+
+    def release(self) -> None:
+        """Mark the current buffer as consumed by everything enqueued so far on the current stream."""
+        self.consumed[self.cur].record(torch.cuda.current_stream(self.device))
