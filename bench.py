@@ -57,9 +57,12 @@ STAGES = ["preprocess_fwd", "scan", "duplicate_with_keys", "sort", "tile_ranges"
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Polls nvidia-smi during the timed region (profiling recipe's clocks line)."""
+    """Polls nvidia-smi (profiling recipe's clocks line) from before the warm-up until after the timed
+    region; `stop()` summarises the samples whose timestamp falls INSIDE the timed window
+    (mark_begin / mark_end), falling back to all samples under load when the window is too short
+    to contain one."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -68,11 +71,12 @@ class ClockSampler:
         self.proc = None
         self.lines = []
         self.thread = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -82,35 +86,52 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                pw.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def summarise(rows):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, ln in rows:
+                parts = [p.strip() for p in ln.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                    pw.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, mx, pw, reasons
+
+        window = "timed region"
+        rows = [r for r in self.lines if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1 + 0.02]
+        sm, mx, pw, reasons = summarise(rows)
+        if len(sm) < 2:  # region shorter than the sampling period: use every sample taken under load
+            window = "warm-up + timed region + stage pass (timed region shorter than the sampling period)"
+            sm, mx, pw, reasons = summarise(self.lines)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peaks() -> tuple:
@@ -218,28 +239,68 @@ def run_b200(args) -> dict:
     def allreduce():  # ONE collective per step: sum of the 61N-float gradient + statistics arena
         cugs.allreduce_step(buf.grad_arena)
 
-    def step_resident():
+    # Two frames in flight inside one step: view v runs on stream v % 2 with its own frame buffers, so
+    # the preprocess / sort / forward blend of view v+1 overlap the (issue-bound) backward blend of view v.
+    # The gradient arena is shared: view v's backward waits for view v-1's (in-place accumulation), and a
+    # step starts only after the previous step has completely finished (no overlap across steps, where a
+    # real training loop has its optimizer update).
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)] if V > 1 and not args.no_overlap else None
+    bufs = [buf, cugs.FrameBuffers(n, W, H, 16, dev, share_grads_with=buf)] if streams else [buf, buf]
+
+    def run_views(per_view):
+        if streams is None:
+            for v in range(V):
+                per_view(v, bufs[0], None)
+            return
+        cur = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(cur)
+        prev_bwd = None
         for v in range(V):
-            out = cugs.render(model, cams[v], settings, buf)
-            cugs.render_backward(dLs[v], out, model, cams[v], settings, buf, accumulate=(v > 0))
+            s = streams[v % 2]
+            s.wait_event(start)
+            with torch.cuda.stream(s):
+                prev_bwd = per_view(v, bufs[v % 2], prev_bwd)
+        cur.wait_event(prev_bwd)
+
+    def view_resident(v, b, prev_bwd):
+        out = cugs.render(model, cams[v], settings, b)
+        if prev_bwd is not None:
+            torch.cuda.current_stream(dev).wait_event(prev_bwd)
+        cugs.render_backward(dLs[v], out, model, cams[v], settings, b, accumulate=(v > 0))
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        return ev
+
+    def step_resident():
+        run_views(view_resident)
         allreduce()
 
     uploader = cugs.TargetUploader(H, W, dev)
     uploader.prefetch(targets_host[0])
 
-    def step_e2e():
+    scal_hosts = [torch.empty((3,), dtype=torch.float32).pin_memory() for _ in range(V)]
+
+    def view_e2e(v, b, prev_bwd):
         # every view's target is copied host->device (pinned, side stream) INSIDE the step; the copy of
         # the next view overlaps the rendering of the current one
-        for v in range(V):
-            tgt = uploader.get()
-            uploader.prefetch(targets_host[(v + 1) % V])                      # H2D of the next view's target
-            out = cugs.render(model, cams[v], settings, buf)
-            sc, g = cugs.combined_loss_with_grad(out.color, tgt, 0.2)
-            uploader.release()
-            cugs.render_backward(g, out, model, cams[v], settings, buf, accumulate=(v > 0))
-            scal_host.copy_(sc, non_blocking=True)                            # D2H of {loss, l1, ssim}
+        tgt = uploader.get()
+        uploader.prefetch(targets_host[(v + 1) % V])                          # H2D of the next view's target
+        out = cugs.render(model, cams[v], settings, b)
+        sc, g = cugs.combined_loss_with_grad(out.color, tgt, 0.2)
+        uploader.release()
+        if prev_bwd is not None:
+            torch.cuda.current_stream(dev).wait_event(prev_bwd)
+        cugs.render_backward(g, out, model, cams[v], settings, b, accumulate=(v > 0))
+        scal_hosts[v].copy_(sc, non_blocking=True)                            # D2H of {loss, l1, ssim}
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        return ev
+
+    def step_e2e():
+        run_views(view_e2e)
         allreduce()
-        torch.cuda.current_stream().synchronize()                             # the loss is on the host now
+        torch.cuda.current_stream().synchronize()                             # the losses are on the host now
 
     def barrier():
         if world > 1:
@@ -259,15 +320,16 @@ def run_b200(args) -> dict:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
     l0 = int(lib.cugs_b200_launch_count(h))
+    sampler.mark_begin()
     total_ms = timed(step_resident, args.steps)
+    sampler.mark_end()
     launches = int(lib.cugs_b200_launch_count(h)) - l0
-    clocks = sampler.stop() if rank == 0 else {}
 
     # second pass: per-stage device timing (events recorded by the library on the launching stream)
     import ctypes as C
@@ -276,7 +338,7 @@ def run_b200(args) -> dict:
     lib.cugs_b200_set_stage_timing(h, 1)
     ms8 = (C.c_float * 8)()
     for _ in range(args.steps):
-        for v in range(V):
+        for v in range(V):  # (one frame in flight here: the stage events are per handle)
             out = cugs.render(model, cams[v], settings, buf)
             cugs.render_backward(dLs[v], out, model, cams[v], settings, buf, accumulate=(v > 0))
             lib.cugs_b200_get_stage_ms(h, ms8)
@@ -289,6 +351,7 @@ def run_b200(args) -> dict:
     for _ in range(3):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else {}
 
     views = world * V * args.steps
     value = views / (total_ms * 1e-3)
@@ -327,7 +390,8 @@ def run_b200(args) -> dict:
             "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4),
             "ms_per_view": round(total_ms / args.steps / V, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "views_per_gpu_per_step": V, "P_pairs_view0": P, "sort_passes": passes,
+            "config": {"workload": desc, "views_per_gpu_per_step": V, "frames_in_flight": 2 if streams else 1,
+                       "P_pairs_view0": P, "sort_passes": passes,
                        "sort_key_bits": key_bits,
                        "collective": "none" if world == 1 else "one NCCL all-reduce(sum) of 61N floats per step",
                        "l2": "no flush needed: per-step inputs (708 MB of Gaussian parameters at 3M) exceed the 126 MB L2"},
@@ -378,19 +442,21 @@ def run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = int(lib.cugs_b200_launch_count(h))
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    sampler.mark_end()
     launches = int(lib.cugs_b200_launch_count(h)) - l0
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -506,11 +572,13 @@ def run_reference(args) -> dict:
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
     sampler = ClockSampler(local)
     sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler.mark_begin()
     ms = timed(step_resident, args.steps)
+    sampler.mark_end()
     clocks = sampler.stop()
     for _ in range(2):
         step_e2e()
@@ -534,13 +602,14 @@ def run_reference(args) -> dict:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--views-per-gpu", type=int, default=2,
                     help="views rendered fwd+bwd per GPU per step (2 = BASELINE config[3]: 16 views/step on 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="one frame in flight (no 2-stream view pipelining)")
     ap.add_argument("--mode", default="fwd_bwd", choices=["fwd_bwd", "train_step"],
                     help="fwd_bwd = the headline metric; train_step = BASELINE config[2] (full step incl. loss, Adam, stats)")
     args = ap.parse_args()

@@ -427,7 +427,8 @@ class FrameBuffers:
     """Reusable device buffers for one in-flight frame of a fixed (N, W, H): everything render()
     would otherwise allocate per call (the reference allocates ~45 tensors per frame)."""
 
-    def __init__(self, n: int, width: int, height: int, num_coeffs: int, device, p_capacity: int = 0):
+    def __init__(self, n: int, width: int, height: int, num_coeffs: int, device, p_capacity: int = 0,
+                 share_grads_with: Optional["FrameBuffers"] = None):
         f = dict(dtype=torch.float32, device=device)
         i = dict(dtype=torch.int32, device=device)
         self.n, self.width, self.height = n, width, height
@@ -449,9 +450,13 @@ class FrameBuffers:
         # positions, sh_coeffs, opacities, scales, rotations) followed by the two additive
         # densification statistics of the step, so that view-parallel training needs exactly one
         # all-reduce(sum) per step. Segment starts are 256-byte aligned (float4 accesses).
+        # (a second in-flight frame of the same step shares the arena of the first: share_grads_with)
         from .parallel import arena_layout
         layout, total = arena_layout(n, num_coeffs)
-        self.grad_arena = torch.zeros((total,), **f)
+        if share_grads_with is not None:
+            _check(share_grads_with.n == n and share_grads_with.grad_arena.numel() == total,
+                   "share_grads_with: incompatible FrameBuffers")
+        self.grad_arena = share_grads_with.grad_arena if share_grads_with is not None else torch.zeros((total,), **f)
         seg = lambda nm: self.grad_arena[layout[nm][0]:layout[nm][0] + layout[nm][1]]
         self.dL_dpositions = seg("positions").view(n, 3)
         self.dL_dsh_coeffs = seg("sh_coeffs").view(n, 3, num_coeffs)
@@ -460,7 +465,8 @@ class FrameBuffers:
         self.dL_drotations = seg("rotations").view(n, 4)
         self.step_grad_accum = seg("grad_accum")   # sum over the step's views of ||dL/dmeans_2d|| (visible only)
         self.step_grad_count = seg("grad_count")   # number of the step's views in which the Gaussian was visible
-        self.step_max_radii = torch.zeros((n,), **f)  # needs a max-reduction, kept outside the arena
+        self.step_max_radii = (share_grads_with.step_max_radii if share_grads_with is not None
+                               else torch.zeros((n,), **f))  # needs a max-reduction, kept outside the arena
         self.dL_dmeans_2d = torch.empty((n, 2), **f)
 
     def ensure_capacity(self, p: int) -> None:

@@ -49,7 +49,7 @@ def combined_loss_with_grad(rendered: torch.Tensor, target: torch.Tensor, lambda
     dev = rendered.device
     lib, h = _lib_and_handle(dev)
     H, W = int(rendered.shape[0]), int(rendered.shape[1])
-    key = (dev.index, W, H)
+    key = (dev.index, W, H, _stream(dev))  # one scratch per stream: frames of two streams may overlap
     ws = _loss_ws.get(key)
     if ws is None:
         ws = torch.empty((lib.cugs_b200_loss_workspace_bytes(W, H),), dtype=torch.uint8, device=dev)
