@@ -195,13 +195,21 @@ k_onesweep_packed(int64_t n, const uint64_t* __restrict__ in, uint64_t* __restri
     const unsigned lt_mask = (1u << lane) - 1;
 
     uint64_t e[kPkItems];
+    if (tile_base + kPkTile <= n) {  // full tile: no bounds checks
 #pragma unroll
-    for (int i = 0; i < kPkItems; ++i) {
-        const int64_t idx = seg + i * 32 + lane;
-        e[i] = (idx < n) ? __ldcs(in + idx) : ~0ull;
+        for (int i = 0; i < kPkItems; ++i) e[i] = __ldcs(in + seg + i * 32 + lane);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kPkItems; ++i) {
+            const int64_t idx = seg + i * 32 + lane;
+            e[i] = (idx < n) ? __ldcs(in + idx) : ~0ull;
+        }
     }
 
-    // stable ranking inside the warp: match peers with the same digit, per-warp counters
+    // Stable ranking inside the warp: lanes holding the same digit are matched with a ballot per bit;
+    // the group's leader bumps the warp's counter with ONE shared-memory atomic whose return value is
+    // the number of equal digits in the warp's earlier items (shared atomics of one warp retire in
+    // program order), so the eight items are independent instruction streams for the scheduler.
     unsigned short rank[kPkItems];
 #pragma unroll
     for (int i = 0; i < kPkItems; ++i) {
@@ -209,18 +217,15 @@ k_onesweep_packed(int64_t n, const uint64_t* __restrict__ in, uint64_t* __restri
         const unsigned peers = match_digit(d, bits);
         const int leader = __ffs(peers) - 1;
         unsigned old = 0;
-        if (lane == leader) {
-            old = s_warp_hist[warp][d];
-            s_warp_hist[warp][d] = old + __popc(peers);
-        }
+        if (lane == leader) old = atomicAdd(&s_warp_hist[warp][d], (unsigned)__popc(peers));
         old = __shfl_sync(kFull, old, leader);
         rank[i] = (unsigned short)(old + __popc(peers & lt_mask));
-        __syncwarp();
     }
     __syncthreads();
 
-    // per-bin: scan over warps, block count, local start, global base via decoupled look-back
+    // per-bin: scan over warps -> block count; publish the tile's aggregate as early as possible
     unsigned bin_count = 0, incl = 0;
+    volatile unsigned* lb = lookback + (size_t)tile * kPkRadix;
     if (tid < kPkRadix) {
         unsigned run = 0;
 #pragma unroll
@@ -230,6 +235,7 @@ k_onesweep_packed(int64_t n, const uint64_t* __restrict__ in, uint64_t* __restri
             run += c;
         }
         bin_count = run;
+        lb[tid] = (tile == 0 ? kPkPrefix : kPkAggregate) | bin_count;
         incl = run;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -239,45 +245,58 @@ k_onesweep_packed(int64_t n, const uint64_t* __restrict__ in, uint64_t* __restri
         if (lane == 31) s_scan[warp] = incl;
     }
     __syncthreads();
+    unsigned local_start = 0;
     if (tid < kPkRadix) {
         unsigned off = 0;
         for (int w = 0; w < warp; ++w) off += s_scan[w];
-        const unsigned local_start = incl - bin_count + off;
-
-        volatile unsigned* lb = lookback + (size_t)tile * kPkRadix;
-        unsigned excl = 0;
-        if (tile == 0) {
-            lb[tid] = kPkPrefix | bin_count;
-        } else {
-            lb[tid] = kPkAggregate | bin_count;
-            int64_t j = (int64_t)tile - 1;
-            while (true) {
-                const unsigned s = lookback[(size_t)j * kPkRadix + tid];
-                if (s & kPkPrefix) { excl += s & kPkValue; break; }
-                if (s & kPkAggregate) { excl += s & kPkValue; --j; }
-            }
-            lb[tid] = kPkPrefix | ((excl + bin_count) & kPkValue);
-        }
-        s_bin_global[tid] = (int64_t)bin_base[tid] + (int64_t)excl - (int64_t)local_start;
+        local_start = incl - bin_count + off;
         s_bin_start[tid] = local_start;
     }
     __syncthreads();
 
-    // scatter into the local sorted slot, then write runs of equal digits contiguously
+    // scatter into the local sorted slot (needs only the local starts) ...
 #pragma unroll
     for (int i = 0; i < kPkItems; ++i) {
         const unsigned d = pk_digit(e[i], shift, mask);
         s_elts[s_bin_start[d] + s_warp_hist[warp][d] + rank[i]] = e[i];
     }
+    // ... then resolve the global bin bases with the decoupled look-back (by now the predecessors
+    // have had the whole ranking + scatter time to publish)
+    if (tid < kPkRadix) {
+        unsigned excl = 0;
+        if (tile != 0) {
+            int64_t j = (int64_t)tile - 1;
+            while (true) {
+                const unsigned st = lookback[(size_t)j * kPkRadix + tid];
+                if (st & kPkPrefix) { excl += st & kPkValue; break; }
+                if (st & kPkAggregate) { excl += st & kPkValue; --j; }
+            }
+            lb[tid] = kPkPrefix | ((excl + bin_count) & kPkValue);
+        }
+        s_bin_global[tid] = (int64_t)bin_base[tid] + (int64_t)excl - (int64_t)local_start;
+    }
     __syncthreads();
+
+    // write runs of equal digits contiguously
+    if (valid == kPkTile) {
 #pragma unroll
-    for (int i = 0; i < kPkItems; ++i) {
-        const int slot = tid + i * kPkThreads;
-        if (slot < valid) {
+        for (int i = 0; i < kPkItems; ++i) {
+            const int slot = tid + i * kPkThreads;
             const uint64_t x = s_elts[slot];
             const int64_t g = s_bin_global[pk_digit(x, shift, mask)] + slot;
             if (kLast) out32[g] = (int)(unsigned)x;
             else out[g] = x;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kPkItems; ++i) {
+            const int slot = tid + i * kPkThreads;
+            if (slot < valid) {
+                const uint64_t x = s_elts[slot];
+                const int64_t g = s_bin_global[pk_digit(x, shift, mask)] + slot;
+                if (kLast) out32[g] = (int)(unsigned)x;
+                else out[g] = x;
+            }
         }
     }
 }
