@@ -265,11 +265,29 @@ k_onesweep_packed(int64_t n, const uint64_t* __restrict__ in, uint64_t* __restri
     if (tid < kPkRadix) {
         unsigned excl = 0;
         if (tile != 0) {
+            // eight predecessors per round trip (independent loads in flight), consumed in order up to
+            // the first inclusive prefix or the first status that is not published yet
             int64_t j = (int64_t)tile - 1;
-            while (true) {
-                const unsigned st = lookback[(size_t)j * kPkRadix + tid];
-                if (st & kPkPrefix) { excl += st & kPkValue; break; }
-                if (st & kPkAggregate) { excl += st & kPkValue; --j; }
+            bool done = false;
+            while (!done) {
+                unsigned st[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    unsigned v = 2u << 30;  // before tile 0: an inclusive prefix of zero
+                    if (j - k >= 0) v = lookback[(size_t)(j - k) * kPkRadix + tid];
+                    st[k] = v;
+                }
+                int consumed = 0;
+                bool stop = false;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (!stop) {
+                        if (st[k] & kPkPrefix) { excl += st[k] & kPkValue; done = true; stop = true; }
+                        else if (st[k] & kPkAggregate) { excl += st[k] & kPkValue; ++consumed; }
+                        else stop = true;  // not published yet: retry from here
+                    }
+                }
+                j -= consumed;
             }
             lb[tid] = kPkPrefix | ((excl + bin_count) & kPkValue);
         }
