@@ -5,12 +5,14 @@
 //
 // Both kernels are instruction-issue bound (ncu: >80 % issue-active, <5 % DRAM), so the design
 // minimises instructions per (pixel, Gaussian) evaluation:
-//  * one CTA of 64 threads (2 warps) per tile; a thread owns FOUR horizontally adjacent pixels, a
-//    warp a 16x8 patch. The Gaussian record is read from shared memory once per thread (2
-//    broadcast LDS.128) for four evaluations, the dy-terms of `power` are shared by the four
-//    pixels, and the four independent dependency chains give the ILP a 2-warp CTA needs;
+//  * one CTA of 64 threads (2 warps) per tile; a thread owns FOUR pixels of one row (columns c, c+4,
+//    c+8, c+12), a warp a 16x8 patch. The Gaussian record is read from shared memory once per
+//    thread (2 broadcast LDS.128) for four evaluations, the dy-terms of `power` are shared by the
+//    four pixels, `power` is evaluated two pixels per instruction with packed FP32x2 arithmetic
+//    (FADD2/FMUL2/FFMA2, bit-identical to the scalar sequence), and the four independent
+//    dependency chains give the ILP a 2-warp CTA needs;
 //  * Gaussians are staged in batches of 128 through a 2-deep shared-memory ring of 48-byte packed
-//    records {x,y,a,b | c,thr,op,r | g,b,-,-} (written by preprocess) with 16-byte cp.async
+//    records {x,y,a,b | c,thr,op,r | g,b,hx,hy} (written by preprocess) with 16-byte cp.async
 //    (LDGSTS) copies; the gather of batch k+1 overlaps the blending of batch k;
 //  * `power` is computed with the reference's exact rounding and compared against a per-Gaussian
 //    conservative bound thr = -log(255*op) - 1e-4: the accurate expf (11 instructions + MUFU) only

@@ -34,7 +34,8 @@ k_ssim_moments(int width, int height, SsimWindow win, const float* __restrict__ 
                float* __restrict__ ssim_map /* optional [H,W]: channel mean of S (loss.cpp:123) */) {
     __shared__ float sx[kLossIn][kLossIn * 3];
     __shared__ float sy[kLossIn][kLossIn * 3];
-    __shared__ float sh[5][kLossIn][kLossTile * 3];
+    // four moment maps: mu_x, mu_y, E[x^2 + y^2], E[xy] (only the SUM of the two variances is needed)
+    __shared__ float sh[4][kLossIn][kLossTile * 3];
     __shared__ float s_red[2][8];
 
     const int tx0 = blockIdx.x * kLossTile, ty0 = blockIdx.y * kLossTile;
@@ -56,17 +57,16 @@ k_ssim_moments(int width, int height, SsimWindow win, const float* __restrict__ 
     for (int e = threadIdx.x; e < kLossIn * kLossTile * 3; e += 256) {
         const int r = e / (kLossTile * 3), cc = e % (kLossTile * 3);
         const int col = cc / 3, ch = cc % 3;
-        float mx = 0.f, my = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+        float mx = 0.f, my = 0.f, qq = 0.f, xy = 0.f;
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
             const float a = sx[r][(col + k) * 3 + ch], b = sy[r][(col + k) * 3 + ch], w = win.w[k];
             mx = fmaf(w, a, mx);
             my = fmaf(w, b, my);
-            xx = fmaf(w, a * a, xx);
-            yy = fmaf(w, b * b, yy);
+            qq = fmaf(w, fmaf(a, a, b * b), qq);
             xy = fmaf(w, a * b, xy);
         }
-        sh[0][r][cc] = mx; sh[1][r][cc] = my; sh[2][r][cc] = xx; sh[3][r][cc] = yy; sh[4][r][cc] = xy;
+        sh[0][r][cc] = mx; sh[1][r][cc] = my; sh[2][r][cc] = qq; sh[3][r][cc] = xy;
     }
     __syncthreads();
     // vertical pass + SSIM
@@ -78,19 +78,18 @@ k_ssim_moments(int width, int height, SsimWindow win, const float* __restrict__ 
         const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-            float mx = 0.f, my = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+            float mx = 0.f, my = 0.f, qq = 0.f, xy = 0.f;
 #pragma unroll
             for (int k = 0; k < 11; ++k) {
                 const float w = win.w[k];
                 mx = fmaf(w, sh[0][ly + k][lx * 3 + ch], mx);
                 my = fmaf(w, sh[1][ly + k][lx * 3 + ch], my);
-                xx = fmaf(w, sh[2][ly + k][lx * 3 + ch], xx);
-                yy = fmaf(w, sh[3][ly + k][lx * 3 + ch], yy);
-                xy = fmaf(w, sh[4][ly + k][lx * 3 + ch], xy);
+                qq = fmaf(w, sh[2][ly + k][lx * 3 + ch], qq);
+                xy = fmaf(w, sh[3][ly + k][lx * 3 + ch], xy);
             }
-            const float sxx = xx - mx * mx, syy = yy - my * my, sxy = xy - mx * my;
+            const float sxy = xy - mx * my;
             const float A1 = 2.0f * mx * my + C1, A2 = 2.0f * sxy + C2;
-            const float B1 = mx * mx + my * my + C1, B2 = sxx + syy + C2;
+            const float B1 = mx * mx + my * my + C1, B2 = (qq - mx * mx - my * my) + C2;  // sigma_x^2 + sigma_y^2 + C2
             const float inv = 1.0f / (B1 * B2);
             const float S = A1 * A2 * inv;
             const int64_t gi = ((int64_t)gy * width + gx) * 3 + ch;
