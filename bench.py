@@ -236,8 +236,19 @@ def run_b200(args) -> dict:
         dLs.append(g)
     torch.cuda.synchronize()
 
-    def allreduce():  # ONE collective per step: sum of the 61N-float gradient + statistics arena
-        cugs.allreduce_step(buf.grad_arena)
+    exchange = {"mode": "single"}
+
+    def allreduce():
+        # the step's gradient exchange: sparse (MAX-reduce of the touch mask + ONE sum all-reduce of the
+        # touched rows) unless --dense-allreduce (ONE sum all-reduce of the whole 61N-float arena)
+        if world == 1:
+            return
+        if args.dense_allreduce:
+            cugs.allreduce_step(buf.grad_arena)
+            exchange.update(mode="dense")
+        else:
+            exchange.update(cugs.sparse_allreduce_step(buf, with_stats=False))
+    touch = buf.touch_mask if (world > 1 and not args.dense_allreduce) else None
 
     # Two frames in flight inside one step: view v runs on stream v % 2 with its own frame buffers, so
     # the preprocess / sort / forward blend of view v+1 overlap the (issue-bound) backward blend of view v.
@@ -267,7 +278,7 @@ def run_b200(args) -> dict:
         out = cugs.render(model, cams[v], settings, b)
         if prev_bwd is not None:
             torch.cuda.current_stream(dev).wait_event(prev_bwd)
-        cugs.render_backward(dLs[v], out, model, cams[v], settings, b, accumulate=(v > 0))
+        cugs.render_backward(dLs[v], out, model, cams[v], settings, b, accumulate=(v > 0), touch_mask=touch)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
         return ev
@@ -291,7 +302,7 @@ def run_b200(args) -> dict:
         uploader.release()
         if prev_bwd is not None:
             torch.cuda.current_stream(dev).wait_event(prev_bwd)
-        cugs.render_backward(g, out, model, cams[v], settings, b, accumulate=(v > 0))
+        cugs.render_backward(g, out, model, cams[v], settings, b, accumulate=(v > 0), touch_mask=touch)
         scal_hosts[v].copy_(sc, non_blocking=True)                            # D2H of {loss, l1, ssim}
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
@@ -393,7 +404,11 @@ def run_b200(args) -> dict:
             "config": {"workload": desc, "views_per_gpu_per_step": V, "frames_in_flight": 2 if streams else 1,
                        "P_pairs_view0": P, "sort_passes": passes,
                        "sort_key_bits": key_bits,
-                       "collective": "none" if world == 1 else "one NCCL all-reduce(sum) of 61N floats per step",
+                       "collective": "none" if world == 1 else (
+                           "one NCCL all-reduce(sum) of the 61N-float arena per step" if args.dense_allreduce else
+                           "per step: int32 MAX all-reduce of the touch mask (8 B/Gaussian) + ONE all-reduce(sum) of the "
+                           "touched gradient rows"),
+                       "gradient_exchange": exchange,
                        "l2": "no flush needed: per-step inputs (708 MB of Gaussian parameters at 3M) exceed the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "ms_per_view": round(e2e_ms / args.steps / V, 4),
@@ -609,6 +624,8 @@ def main():
     ap.add_argument("--views-per-gpu", type=int, default=2,
                     help="views rendered fwd+bwd per GPU per step (2 = BASELINE config[3]: 16 views/step on 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-allreduce", action="store_true",
+                    help="N > 1: all-reduce the whole gradient arena instead of only the touched rows")
     ap.add_argument("--no-overlap", action="store_true", help="one frame in flight (no 2-stream view pipelining)")
     ap.add_argument("--mode", default="fwd_bwd", choices=["fwd_bwd", "train_step"],
                     help="fwd_bwd = the headline metric; train_step = BASELINE config[2] (full step incl. loss, Adam, stats)")

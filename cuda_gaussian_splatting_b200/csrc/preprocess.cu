@@ -318,7 +318,8 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                  float* __restrict__ grad_count, float* __restrict__ max_radii,
                  const float4* __restrict__ gacc /* [N,3] packed blend gradients or null */,
                  float* __restrict__ dL_dmeans_2d_out /* written when gacc != null */,
-                 bool accumulate /* add to the five parameter-gradient outputs instead of overwriting */) {
+                 bool accumulate /* add to the five parameter-gradient outputs instead of overwriting */,
+                 int* __restrict__ touch_mask /* optional: 1 where the incoming 2-D gradient is non-zero */) {
     __shared__ __align__(16) float sY[kPreWarps][32 * kYStride];
     __shared__ float sG[kPreWarps][96];  // gated dL/drgb per (Gaussian, channel)
 
@@ -341,6 +342,11 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
             dr[0] = a.x; dr[1] = a.y; dr[2] = a.z; in_dop = a.w;
             in_m0 = b.x; in_m1 = b.y; in_da = b.z; in_db = b.w; in_dc = c.x;
             reinterpret_cast<float2*>(dL_dmeans_2d_out)[i] = make_float2(in_m0, in_m1);
+            if (touch_mask != nullptr) {
+                const bool t = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) |
+                               (b.z != 0.f) | (b.w != 0.f) | (c.x != 0.f);
+                touch_mask[i] = accumulate ? (touch_mask[i] | (int)t) : (int)t;
+            }
         } else {
             dr[0] = dL_drgb[i * 3]; dr[1] = dL_drgb[i * 3 + 1]; dr[2] = dL_drgb[i * 3 + 2];
             in_dop = dL_dopa_act[i];
@@ -652,7 +658,7 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
                                float* dL_drotations, float* dL_dscales, float* dL_dopacities,
                                float* dL_dsh_coeffs, float* grad_accum, float* grad_count,
                                float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out,
-                               bool accumulate) {
+                               bool accumulate, int32_t* touch_mask) {
     const ViewParams vp = make_view_params(v);
     const unsigned grid = (unsigned)((n + kPreBlock - 1) / kPreBlock);
     if (v->num_coeffs == 16)
@@ -660,13 +666,13 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
             n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
             dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
             dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
-            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate);
+            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate, touch_mask);
     else
         k_preprocess_bwd<false><<<grid, kPreBlock, 0, s>>>(
             n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
             dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
             dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
-            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate);
+            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate, touch_mask);
     CUGS_LAUNCH_CHECK(h, "k_preprocess_bwd");
     return CUGS_OK;
 }
@@ -698,7 +704,7 @@ extern "C" int cugs_b200_preprocess_bwd(cugs_handle_t* h, void* stream, int64_t 
                                       opacities, sh_coeffs, radii, rgb, dL_dmeans_2d, dL_dcov_2d_inv,
                                       dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
                                       dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
-                                      nullptr, nullptr, false);
+                                      nullptr, nullptr, false, nullptr);
 }
 
 extern "C" int cugs_b200_sh_forward(cugs_handle_t* h, void* stream, int64_t n, int degree,

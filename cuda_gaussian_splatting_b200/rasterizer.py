@@ -465,8 +465,14 @@ class FrameBuffers:
         self.dL_drotations = seg("rotations").view(n, 4)
         self.step_grad_accum = seg("grad_accum")   # sum over the step's views of ||dL/dmeans_2d|| (visible only)
         self.step_grad_count = seg("grad_count")   # number of the step's views in which the Gaussian was visible
-        self.step_max_radii = (share_grads_with.step_max_radii if share_grads_with is not None
-                               else torch.zeros((n,), **f))  # needs a max-reduction, kept outside the arena
+        # quantities that need a MAX reduction live in one int32 buffer [touch mask | max_radii bits]
+        # (non-negative floats order like their bit patterns, so one int32 MAX all-reduce serves both)
+        self.max_buf = (share_grads_with.max_buf if share_grads_with is not None
+                        else torch.zeros((2 * max(n, 1),), **i))
+        self.touch_mask = self.max_buf[:n]                       # 1 where some view gave a non-zero gradient
+        self.step_max_radii = self.max_buf[n:2 * n].view(torch.float32)
+        self.grad_compact = None                                  # lazily allocated by parallel.sparse_allreduce_step
+        self.touch_offsets = None
         self.dL_dmeans_2d = torch.empty((n, 2), **f)
 
     def ensure_capacity(self, p: int) -> None:
@@ -530,11 +536,13 @@ def render(model: GaussianModel, camera: CameraInfo, settings: RenderSettings,
 
 def render_backward(dL_dcolor: torch.Tensor, render_out: RenderOutput, model: GaussianModel,
                     camera: CameraInfo, settings: RenderSettings, buffers: Optional[FrameBuffers] = None,
-                    stats: Optional[Sequence[torch.Tensor]] = None, accumulate: bool = False) -> BackwardOutput:
+                    stats: Optional[Sequence[torch.Tensor]] = None, accumulate: bool = False,
+                    touch_mask: Optional[torch.Tensor] = None) -> BackwardOutput:
     """rasterizer.hpp:88-93 / rasterizer.cpp:115-186. ``stats`` = (grad_accum, grad_count,
     max_radii) fuses DensificationController::accumulate_gradients into the same launch;
     ``accumulate`` adds the parameter gradients to ``buffers`` instead of overwriting them
-    (gradient of a batch of views)."""
+    (gradient of a batch of views); ``touch_mask`` ([N] int32) records which Gaussians received a
+    non-zero gradient (input of the sparse gradient exchange, parallel.sparse_allreduce_step)."""
     _check(dL_dcolor.is_cuda, "dL_dcolor must be on CUDA device")
     _check(dL_dcolor.dim() == 3 and dL_dcolor.shape[2] == 3, "dL_dcolor must be [H, W, 3]")
     dev = dL_dcolor.device
@@ -563,6 +571,6 @@ def render_backward(dL_dcolor: torch.Tensor, render_out: RenderOutput, model: Ga
         h, _stream(dev), n, C.byref(v), _ptr(pos), _ptr(rot), _ptr(scl), _ptr(opa), _ptr(sh), _ptr(r.means_2d),
         _ptr(r.cov_2d_inv), _ptr(r.radii), _ptr(r.rgb), _ptr(r.opacities_act), _ptr(r.gaussian_indices),
         _ptr(r.tile_ranges), _ptr(r.final_T), _ptr(r.n_contrib), _ptr(dL_dcolor.contiguous()),
-        *[_ptr(t) for t in g], *sp, int(bool(accumulate)), _ptr(ws), ws.numel())
+        *[_ptr(t) for t in g], *sp, _ptr(touch_mask), int(bool(accumulate)), _ptr(ws), ws.numel())
     _lib.check(h, st, "cugs_b200_render_backward")
     return BackwardOutput(*g)

@@ -252,7 +252,7 @@ class SyntheticTrainer:
         self.last_scalars = None
 
     def train_step(self, step: int) -> torch.Tensor:
-        from .parallel import allreduce_step, fold_step_stats
+        from .parallel import fold_step_stats, sparse_allreduce_step
         from .rasterizer import BackwardOutput, render, render_backward
         cfg, b = self.config, self.buffers
         self.optimizer.update_lr(step)                                   # trainer.cpp:180
@@ -272,10 +272,11 @@ class SyntheticTrainer:
         for k, (cam, target) in enumerate(zip(self.cameras, self.targets)):
             out = render(self.model, cam, settings, b)                   # :211
             scalars, dL = combined_loss_with_grad(out.color, target, cfg.lambda_ssim)  # :214-225 in one pass
-            render_backward(dL, out, self.model, cam, settings, b, stats=stats, accumulate=(k > 0))  # :228, :269
+            render_backward(dL, out, self.model, cam, settings, b, stats=stats, accumulate=(k > 0),
+                            touch_mask=b.touch_mask if multi else None)  # :228, :269
             scal_sum = scalars if scal_sum is None else scal_sum + scalars
         if multi:
-            allreduce_step(b.grad_arena, b.step_max_radii if cfg.densify else None)
+            self.last_exchange = sparse_allreduce_step(b, with_stats=cfg.densify)
             if cfg.densify:
                 fold_step_stats(b.step_grad_accum, b.step_grad_count, b.step_max_radii, self.stats.grad_accum,
                                 self.stats.grad_count, self.stats.max_radii_2d)

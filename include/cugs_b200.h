@@ -165,7 +165,10 @@ int cugs_b200_preprocess_bwd(cugs_handle_t* h, void* stream, int64_t n, const cu
  * accumulate = 0: the five parameter gradients are overwritten (reference behaviour);
  * accumulate = 1: they are added to what the buffers hold (view-batched training: the gradient
  * of a batch of views is summed in place, no separate axpy pass). dL_dmeans_2d is always
- * overwritten (it is a per-view quantity, optimizer/densification.cpp:77). */
+ * overwritten (it is a per-view quantity, optimizer/densification.cpp:77).
+ * touch_mask (optional, [N] i32): 1 where this view gave the Gaussian a non-zero 2-D gradient, else
+ * 0 (OR-ed into the previous content when accumulate = 1). Rows with mask 0 have all-zero parameter
+ * gradients; the view-parallel gradient exchange below only moves the other rows. */
 size_t cugs_b200_render_workspace_bytes(int64_t n, int64_t p_capacity);
 int cugs_b200_render_plan(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
                           const float* positions, const float* rotations, const float* scales,
@@ -189,7 +192,7 @@ int cugs_b200_render_backward(cugs_handle_t* h, void* stream, int64_t n, const c
                               const float* dL_dcolor, float* dL_dpositions, float* dL_drotations,
                               float* dL_dscales, float* dL_dopacities, float* dL_dsh_coeffs,
                               float* dL_dmeans_2d, float* grad_accum, float* grad_count,
-                              float* max_radii, int accumulate, void* workspace,
+                              float* max_radii, int32_t* touch_mask, int accumulate, void* workspace,
                               size_t workspace_bytes);
 
 /* Optional per-stage device timing of the three fused entry points above: when enabled, CUDA
@@ -226,6 +229,19 @@ int cugs_b200_adam_step(cugs_handle_t* h, void* stream, float* const params[5],
 int cugs_b200_accumulate_stats(cugs_handle_t* h, void* stream, int64_t n,
                                const float* dL_dmeans_2d, const int32_t* radii, float* grad_accum,
                                float* grad_count, float* max_radii);
+
+/* ---- view-parallel gradient exchange (no reference counterpart: the reference is single-GPU) ----
+ * Compaction of the gradient rows of the touched Gaussians around the all-reduce. touch: [N] i32
+ * union mask (after a MAX all-reduce over the ranks); offsets: its exclusive scan (cugs_b200_scan);
+ * m: number of touched Gaussians; grads: the five dense gradient arrays in Adam group order
+ * (positions [N,3], sh_coeffs [N,3,C], opacities [N,1], scales [N,3], rotations [N,4]); compact:
+ * (3C + 11) * m floats, group-major. */
+int cugs_b200_gather_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs,
+                               const int32_t* touch, const int32_t* offsets, int64_t m,
+                               const float* const grads[5], float* compact);
+int cugs_b200_scatter_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs,
+                                const int32_t* touch, const int32_t* offsets, int64_t m,
+                                const float* compact, float* const grads[5]);
 
 #ifdef __cplusplus
 }

@@ -600,3 +600,42 @@ def test_training_loop_recovers_sh_colour(torch):
     for step in range(1, 100):
         last = float(tr.train_step(step)[0])
     assert last < 0.9 * first, (first, last)
+
+
+# ================================================================================================
+# view-parallel gradient exchange: touch mask + row compaction kernels (single GPU part)
+# ================================================================================================
+def test_touch_mask_and_row_compaction(torch):
+    from cuda_gaussian_splatting_b200.parallel import _CudaRowOps
+    scene = cugs.synth(30_011, 640, 360, seed=41)
+    m = to_torch(scene)
+    settings = cugs.RenderSettings((0, 0, 0), 3, 1.0)
+    b = cugs.FrameBuffers(scene.n, 640, 360, 16, "cuda")
+    cams = [scene.camera] + cugs.ring_cameras(scene, 1, radius_frac=0.02)
+    for k, cam in enumerate(cams):
+        out = cugs.render(m, cam, settings, b)
+        cugs.render_backward(_dL(torch, scene, 5 + k), out, m, cam, settings, b, accumulate=(k > 0),
+                             touch_mask=b.touch_mask)
+    mask = b.touch_mask.bool()
+    assert 0 < int(mask.sum()) < scene.n, "the scene must have touched and untouched Gaussians"
+    rows = torch.cat([b.dL_dpositions, b.dL_dsh_coeffs.reshape(scene.n, -1), b.dL_dopacities, b.dL_dscales,
+                      b.dL_drotations], dim=1)
+    assert float(rows[~mask].abs().max()) == 0.0, "untouched rows must be exactly zero"
+    assert bool((rows[mask].abs().sum(dim=1) > 0).float().mean() > 0.99)
+    ops = _CudaRowOps()
+    offsets, mcount = ops.scan(b)
+    assert mcount == int(mask.sum())
+    compact = torch.empty((59 * mcount,), dtype=torch.float32, device="cuda")
+    ops.gather(b, offsets, mcount, compact)
+    o = 0
+    for g in (b.dL_dpositions, b.dL_dsh_coeffs.reshape(scene.n, -1), b.dL_dopacities, b.dL_dscales, b.dL_drotations):
+        w = g.shape[1]
+        assert torch.equal(compact[o:o + mcount * w].view(mcount, w), g[mask]), "group-major compact layout"
+        o += mcount * w
+    before = b.grad_arena.clone()
+    for g in (b.dL_dpositions, b.dL_dsh_coeffs, b.dL_dopacities, b.dL_dscales, b.dL_drotations):
+        g.zero_()
+    ops.scatter(b, offsets, mcount, compact * 2.0)
+    assert torch.equal(rows * 0 + torch.cat([b.dL_dpositions, b.dL_dsh_coeffs.reshape(scene.n, -1), b.dL_dopacities,
+                                             b.dL_dscales, b.dL_drotations], dim=1), rows * 2.0)
+    assert before.numel() == b.grad_arena.numel()

@@ -96,3 +96,89 @@ def test_allreduce_world_size_2_gloo(tmp_path):
     assert torch.equal(r0["max_radii"], expect_max) and torch.equal(r1["max_radii"], expect_max)
     o, s = layout["grad_accum"]
     assert torch.equal(r0["acc"], r0["arena"][o:o + s]) and torch.equal(r0["mx"], expect_max)
+
+
+# ---- sparse gradient exchange: host logic with torch stand-ins for the three CUDA row operations ----
+class TorchRowOps:
+    def scan(self, b):
+        mask = b.touch_mask.to(torch.int64)
+        inc = torch.cumsum(mask, 0)
+        return (inc - mask).to(torch.int32), int(inc[-1])
+
+    def _groups(self, b):
+        return [b.dL_dpositions, b.dL_dsh_coeffs.view(b.n, -1), b.dL_dopacities, b.dL_dscales, b.dL_drotations]
+
+    def gather(self, b, offsets, m, compact):
+        sel = b.touch_mask.bool()
+        off = 0
+        for g in self._groups(b):
+            w = g.shape[1]
+            compact[off:off + m * w].copy_(g[sel].reshape(-1))
+            off += m * w
+
+    def scatter(self, b, offsets, m, compact):
+        sel = b.touch_mask.bool()
+        off = 0
+        for g in self._groups(b):
+            w = g.shape[1]
+            g[sel] = compact[off:off + m * w].view(m, w)
+            off += m * w
+
+
+class FakeBuffers:
+    def __init__(self, n, C):
+        from cuda_gaussian_splatting_b200 import parallel
+        layout, total = parallel.arena_layout(n, C)
+        self.n = n
+        self.grad_arena = torch.zeros(total)
+        seg = lambda nm: self.grad_arena[layout[nm][0]:layout[nm][0] + layout[nm][1]]
+        self.dL_dpositions = seg("positions").view(n, 3)
+        self.dL_dsh_coeffs = seg("sh_coeffs").view(n, 3, C)
+        self.dL_dopacities = seg("opacities").view(n, 1)
+        self.dL_dscales = seg("scales").view(n, 3)
+        self.dL_drotations = seg("rotations").view(n, 4)
+        self.step_grad_accum, self.step_grad_count = seg("grad_accum"), seg("grad_count")
+        self.max_buf = torch.zeros(2 * n, dtype=torch.int32)
+        self.touch_mask = self.max_buf[:n]
+        self.step_max_radii = self.max_buf[n:].view(torch.float32)
+        self.grad_compact = None
+        self.touch_offsets = None
+
+
+def fill_rank(b, rank):
+    g = torch.Generator().manual_seed(77 + rank)
+    touched = torch.rand(b.n, generator=g) < (0.2 if rank == 0 else 0.3)
+    for t in (b.dL_dpositions, b.dL_dsh_coeffs, b.dL_dopacities, b.dL_dscales, b.dL_drotations):
+        t.copy_(torch.randn(t.shape, generator=g) * touched.view(-1, *([1] * (t.dim() - 1))))
+    b.touch_mask.copy_(touched.to(torch.int32))
+    b.step_grad_accum.copy_(torch.rand(b.n, generator=g))
+    b.step_grad_count.copy_((torch.rand(b.n, generator=g) < 0.5).float())
+    b.step_max_radii.copy_(torch.randint(0, 40, (b.n,), generator=g).float())
+
+
+def sparse_worker(rank, world, port, out_dir, threshold):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cuda_gaussian_splatting_b200 import parallel
+    b = FakeBuffers(N, C)
+    fill_rank(b, rank)
+    info = parallel.sparse_allreduce_step(b, with_stats=True, dense_threshold=threshold, ops=TorchRowOps())
+    torch.save({"arena": b.grad_arena.clone(), "max_buf": b.max_buf.clone(), "info": info}, os.path.join(out_dir, f"s{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("threshold,mode", [(0.6, "sparse"), (0.1, "dense")])
+def test_sparse_exchange_equals_dense_sum(tmp_path, threshold, mode):
+    world, port = 2, 31500 + (os.getpid() % 2000) + (7 if mode == "dense" else 0)
+    mp.spawn(sparse_worker, args=(world, port, str(tmp_path), threshold), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "s0.pt"), torch.load(tmp_path / "s1.pt")
+    assert r0["info"]["mode"] == mode
+    assert torch.equal(r0["arena"], r1["arena"]) and torch.equal(r0["max_buf"], r1["max_buf"])
+    a, b = FakeBuffers(N, C), FakeBuffers(N, C)
+    fill_rank(a, 0)
+    fill_rank(b, 1)
+    assert torch.equal(r0["arena"], a.grad_arena + b.grad_arena), "sparse exchange must equal the dense sum"
+    assert torch.equal(r0["max_buf"][:N], torch.maximum(a.touch_mask, b.touch_mask))
+    assert torch.equal(r0["max_buf"][N:].view(torch.float32), torch.maximum(a.step_max_radii, b.step_max_radii))
