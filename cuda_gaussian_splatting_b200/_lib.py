@@ -63,8 +63,9 @@ SIGNATURES = {
     "cugs_b200_render_plan": (_INT, [_P, _P, _I64, _VP] + [_P] * 11 + [_P, _SZ, C.POINTER(_I64)]),
     "cugs_b200_render_finish": (_INT, [_P, _P, _I64, _I64, _VP] + [_P] * 11 + [_P, _SZ]),
     "cugs_b200_render_backward": (_INT, [_P, _P, _I64, _VP] + [_P] * 25 + [_INT, _P, _SZ]),
-    "cugs_b200_gather_grad_rows": (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, C.POINTER(_P), _P]),
-    "cugs_b200_scatter_grad_rows": (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, _P, C.POINTER(_P)]),
+    "cugs_b200_compact_grad_floats": (_I64, [_I64, _INT]),
+    "cugs_b200_gather_grad_rows": (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, C.POINTER(_P), _P, _P]),
+    "cugs_b200_scatter_grad_rows": (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, _P, C.POINTER(_P), _P]),
     "cugs_b200_last_sort_plan": (_INT, [_P, C.POINTER(_INT), C.POINTER(_INT)]),
     "cugs_b200_set_stage_timing": (_INT, [_P, _INT]),
     "cugs_b200_get_stage_ms": (_INT, [_P, C.POINTER(_F)]),

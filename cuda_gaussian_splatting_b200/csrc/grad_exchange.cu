@@ -11,7 +11,7 @@
 //
 // Compact layout for M touched Gaussians (group-major, the Adam group order of
 // optimizer/fused_adam.cu:94-97): positions [M,3] | sh_coeffs [M,3C] | opacities [M] | scales [M,3]
-// | rotations [M,4].
+// | rotations [M,4], each block starting at a multiple of 4 floats (cugs_b200_compact_grad_floats).
 #include "common.cuh"
 
 namespace cugs {
@@ -20,27 +20,48 @@ struct GradGroups {
     float* g[5];  // positions, sh_coeffs, opacities, scales, rotations
 };
 
+// index list of the touched Gaussians: idx[offsets[i]] = i
+__global__ void __launch_bounds__(256)
+k_build_touch_index(int64_t n, const int* __restrict__ touch, const int* __restrict__ offsets, int* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && touch[i] != 0) idx[offsets[i]] = (int)i;
+}
+
+// One thread per float of the compact buffer (fully coalesced on the compact side, w-float contiguous
+// runs on the dense side: 192-byte runs for the SH group, which is 81 % of the bytes).
+// blockIdx.y = parameter group.
+__host__ __device__ __forceinline__ int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
+
 template <bool kGather>
 __global__ void __launch_bounds__(256)
-k_move_grad_rows(int64_t n, int C, const int* __restrict__ touch, const int* __restrict__ offsets, int64_t m,
-                 GradGroups dense, float* __restrict__ compact) {
-    const int lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-    if (i >= n || touch[i] == 0) return;
-    const int64_t j = offsets[i];
+k_move_grad_rows(int C, const int* __restrict__ idx, int64_t m, GradGroups dense, float* __restrict__ compact) {
+    const int grp = blockIdx.y;
     const int shw = 3 * C;
-    const int row = shw + 11;
-    const int64_t b_sh = 3 * m, b_op = b_sh + (int64_t)shw * m, b_sc = b_op + m, b_ro = b_sc + 3 * m;
-    for (int e = lane; e < row; e += 32) {
-        float* d;
-        float* c;
-        if (e < 3) { d = dense.g[0] + i * 3 + e; c = compact + j * 3 + e; }
-        else if (e < 3 + shw) { d = dense.g[1] + i * shw + (e - 3); c = compact + b_sh + j * shw + (e - 3); }
-        else if (e < 4 + shw) { d = dense.g[2] + i; c = compact + b_op + j; }
-        else if (e < 7 + shw) { d = dense.g[3] + i * 3 + (e - 4 - shw); c = compact + b_sc + j * 3 + (e - 4 - shw); }
-        else { d = dense.g[4] + i * 4 + (e - 7 - shw); c = compact + b_ro + j * 4 + (e - 7 - shw); }
-        if (kGather) *c = *d;
-        else *d = *c;
+    // group bases, each rounded up to 4 floats so that the SH block can be moved as float4
+    const int64_t b_sh = align4(3 * m), b_op = b_sh + align4((int64_t)shw * m), b_sc = b_op + align4(m),
+                  b_ro = b_sc + align4(3 * m);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp == 1 && (shw & 3) == 0) {  // SH: 81 % of the bytes, rows are 16-byte aligned on both sides
+        const int w4 = shw >> 2;
+        const float4* __restrict__ d4 = reinterpret_cast<const float4*>(dense.g[1]);
+        float4* __restrict__ d4w = reinterpret_cast<float4*>(dense.g[1]);
+        float4* __restrict__ c4 = reinterpret_cast<float4*>(compact + b_sh);
+        for (int64_t e = t0; e < m * w4; e += stride) {
+            const int64_t j = e / w4;
+            const int64_t src = (int64_t)idx[j] * w4 + (e - j * w4);
+            if (kGather) c4[e] = d4[src];
+            else d4w[src] = c4[e];
+        }
+        return;
+    }
+    const int w = (grp == 0) ? 3 : (grp == 1) ? shw : (grp == 2) ? 1 : (grp == 3) ? 3 : 4;
+    const int64_t base = (grp == 0) ? 0 : (grp == 1) ? b_sh : (grp == 2) ? b_op : (grp == 3) ? b_sc : b_ro;
+    float* __restrict__ d = dense.g[grp];
+    for (int64_t e = t0; e < m * w; e += stride) {
+        const int64_t j = e / w;
+        const int64_t src = (int64_t)idx[j] * w + (e - j * w);
+        if (kGather) compact[base + e] = d[src];
+        else d[src] = compact[base + e];
     }
 }
 
@@ -48,35 +69,48 @@ k_move_grad_rows(int64_t n, int C, const int* __restrict__ touch, const int* __r
 
 using namespace cugs;
 
+// idx_temp: m ints of scratch (the caller passes the tail of its offsets/compact scratch); here the
+// index list is rebuilt on every call into `idx`.
 static int move_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs, const int32_t* touch,
-                     const int32_t* offsets, int64_t m, float* const grads[5], float* compact, bool gather) {
+                     const int32_t* offsets, int64_t m, float* const grads[5], float* compact, int32_t* idx,
+                     bool gather) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, n >= 0 && m >= 0 && m <= n, "bad n / m");
     CUGS_REQUIRE(h, num_coeffs >= 1 && num_coeffs <= 64, "bad num_coeffs");
     if (n == 0 || m == 0) return CUGS_OK;
-    CUGS_REQUIRE(h, touch && offsets && grads && compact, "null pointer");
+    CUGS_REQUIRE(h, touch && offsets && grads && compact && idx, "null pointer");
     GradGroups G;
     for (int k = 0; k < 5; ++k) {
         CUGS_REQUIRE(h, grads[k] != nullptr, "null gradient group");
         G.g[k] = grads[k];
     }
-    const unsigned grid = (unsigned)((n + 7) / 8);
-    if (gather)
-        k_move_grad_rows<true><<<grid, 256, 0, (cudaStream_t)stream>>>(n, num_coeffs, touch, offsets, m, G, compact);
-    else
-        k_move_grad_rows<false><<<grid, 256, 0, (cudaStream_t)stream>>>(n, num_coeffs, touch, offsets, m, G, compact);
+    cudaStream_t s = (cudaStream_t)stream;
+    k_build_touch_index<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, touch, offsets, idx);
+    CUGS_LAUNCH_CHECK(h, "k_build_touch_index");
+    int64_t bx = (m * 3 * num_coeffs + 255) / 256;
+    const int64_t cap = (int64_t)h->sm_count * 16;
+    if (bx > cap) bx = cap;
+    const dim3 grid((unsigned)bx, 5);
+    if (gather) k_move_grad_rows<true><<<grid, 256, 0, s>>>(num_coeffs, idx, m, G, compact);
+    else k_move_grad_rows<false><<<grid, 256, 0, s>>>(num_coeffs, idx, m, G, compact);
     CUGS_LAUNCH_CHECK(h, "k_move_grad_rows");
     return CUGS_OK;
 }
 
+extern "C" int64_t cugs_b200_compact_grad_floats(int64_t m, int num_coeffs) {
+    return align4(3 * m) + align4((int64_t)3 * num_coeffs * m) + align4(m) + align4(3 * m) + align4(4 * m);
+}
+
 extern "C" int cugs_b200_gather_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs,
                                           const int32_t* touch, const int32_t* offsets, int64_t m,
-                                          const float* const grads[5], float* compact) {
-    return move_rows(h, stream, n, num_coeffs, touch, offsets, m, const_cast<float* const*>(grads), compact, true);
+                                          const float* const grads[5], float* compact, int32_t* idx_scratch) {
+    return move_rows(h, stream, n, num_coeffs, touch, offsets, m, const_cast<float* const*>(grads), compact,
+                     idx_scratch, true);
 }
 
 extern "C" int cugs_b200_scatter_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs,
                                            const int32_t* touch, const int32_t* offsets, int64_t m,
-                                           const float* compact, float* const grads[5]) {
-    return move_rows(h, stream, n, num_coeffs, touch, offsets, m, grads, const_cast<float*>(compact), false);
+                                           const float* compact, float* const grads[5], int32_t* idx_scratch) {
+    return move_rows(h, stream, n, num_coeffs, touch, offsets, m, grads, const_cast<float*>(compact), idx_scratch,
+                     false);
 }

@@ -71,20 +71,20 @@ def sparse_allreduce_step(buffers, with_stats: bool = True, dense_threshold: flo
     if m > dense_threshold * n:
         dist.all_reduce(b.grad_arena, op=dist.ReduceOp.SUM, group=group)
         return {"mode": "dense", "touched": m}
-    row = 3 * int(b.dL_dsh_coeffs.shape[2]) + 11
-    need = row * m + (2 * n if with_stats else 0)
+    rows = ops.compact_floats(m, int(b.dL_dsh_coeffs.shape[2]))  # the M gradient rows, group-major
+    need = rows + (2 * n if with_stats else 0)
     if b.grad_compact is None or b.grad_compact.numel() < need:
         b.grad_compact = torch.empty((int(need * 1.25) + 1024,), dtype=torch.float32, device=b.grad_arena.device)
     compact = b.grad_compact[:need]
     ops.gather(b, offsets, m, compact)
     if with_stats:
-        compact[row * m:row * m + n].copy_(b.step_grad_accum)
-        compact[row * m + n:].copy_(b.step_grad_count)
+        compact[rows:rows + n].copy_(b.step_grad_accum)
+        compact[rows + n:].copy_(b.step_grad_count)
     dist.all_reduce(compact, op=dist.ReduceOp.SUM, group=group)
     ops.scatter(b, offsets, m, compact)
     if with_stats:
-        b.step_grad_accum.copy_(compact[row * m:row * m + n])
-        b.step_grad_count.copy_(compact[row * m + n:])
+        b.step_grad_accum.copy_(compact[rows:rows + n])
+        b.step_grad_count.copy_(compact[rows + n:])
     return {"mode": "sparse", "touched": m, "floats": need}
 
 
@@ -98,6 +98,10 @@ class _CudaRowOps:
             arr[k] = t.data_ptr()
         return arr
 
+    def compact_floats(self, m, num_coeffs):
+        from . import _lib
+        return int(_lib.load_library().cugs_b200_compact_grad_floats(int(m), int(num_coeffs)))
+
     def scan(self, b):
         import ctypes as C
         from . import _lib
@@ -108,6 +112,7 @@ class _CudaRowOps:
         if b.touch_offsets is None:
             b.touch_offsets = torch.empty((n,), dtype=torch.int32, device=dev)
             b._scan_tmp = torch.empty((lib.cugs_b200_scan_temp_bytes(n),), dtype=torch.uint8, device=dev)
+            b._touch_idx = torch.empty((n,), dtype=torch.int32, device=dev)
         total = C.c_int64(0)
         st = lib.cugs_b200_scan(h, _stream(dev), n, b.touch_mask.data_ptr(), b.touch_offsets.data_ptr(), None,
                                 C.byref(total), b._scan_tmp.data_ptr(), b._scan_tmp.numel())
@@ -121,7 +126,7 @@ class _CudaRowOps:
         lib, h = _lib_and_handle(dev)
         st = lib.cugs_b200_gather_grad_rows(h, _stream(dev), int(b.n), int(b.dL_dsh_coeffs.shape[2]),
                                             b.touch_mask.data_ptr(), offsets.data_ptr(), int(m), self._groups(b),
-                                            compact.data_ptr())
+                                            compact.data_ptr(), b._touch_idx.data_ptr())
         _lib.check(h, st, "cugs_b200_gather_grad_rows")
 
     def scatter(self, b, offsets, m, compact):
@@ -131,7 +136,7 @@ class _CudaRowOps:
         lib, h = _lib_and_handle(dev)
         st = lib.cugs_b200_scatter_grad_rows(h, _stream(dev), int(b.n), int(b.dL_dsh_coeffs.shape[2]),
                                              b.touch_mask.data_ptr(), offsets.data_ptr(), int(m), compact.data_ptr(),
-                                             self._groups(b))
+                                             self._groups(b), b._touch_idx.data_ptr())
         _lib.check(h, st, "cugs_b200_scatter_grad_rows")
 
 

@@ -235,13 +235,15 @@ int cugs_b200_accumulate_stats(cugs_handle_t* h, void* stream, int64_t n,
  * union mask (after a MAX all-reduce over the ranks); offsets: its exclusive scan (cugs_b200_scan);
  * m: number of touched Gaussians; grads: the five dense gradient arrays in Adam group order
  * (positions [N,3], sh_coeffs [N,3,C], opacities [N,1], scales [N,3], rotations [N,4]); compact:
- * (3C + 11) * m floats, group-major. */
+ * cugs_b200_compact_grad_floats(m, C) floats, group-major, every group block starting at a multiple of
+ * 4 floats; idx_scratch: m ints of device scratch (index list). */
+int64_t cugs_b200_compact_grad_floats(int64_t m, int num_coeffs);
 int cugs_b200_gather_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs,
                                const int32_t* touch, const int32_t* offsets, int64_t m,
-                               const float* const grads[5], float* compact);
+                               const float* const grads[5], float* compact, int32_t* idx_scratch);
 int cugs_b200_scatter_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs,
                                 const int32_t* touch, const int32_t* offsets, int64_t m,
-                                const float* compact, float* const grads[5]);
+                                const float* compact, float* const grads[5], int32_t* idx_scratch);
 
 #ifdef __cplusplus
 }

@@ -625,13 +625,13 @@ def test_touch_mask_and_row_compaction(torch):
     ops = _CudaRowOps()
     offsets, mcount = ops.scan(b)
     assert mcount == int(mask.sum())
-    compact = torch.empty((59 * mcount,), dtype=torch.float32, device="cuda")
+    compact = torch.zeros((ops.compact_floats(mcount, 16),), dtype=torch.float32, device="cuda")
     ops.gather(b, offsets, mcount, compact)
     o = 0
     for g in (b.dL_dpositions, b.dL_dsh_coeffs.reshape(scene.n, -1), b.dL_dopacities, b.dL_dscales, b.dL_drotations):
         w = g.shape[1]
         assert torch.equal(compact[o:o + mcount * w].view(mcount, w), g[mask]), "group-major compact layout"
-        o += mcount * w
+        o += (mcount * w + 3) // 4 * 4
     before = b.grad_arena.clone()
     for g in (b.dL_dpositions, b.dL_dsh_coeffs, b.dL_dopacities, b.dL_dscales, b.dL_drotations):
         g.zero_()

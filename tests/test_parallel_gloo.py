@@ -99,7 +99,14 @@ def test_allreduce_world_size_2_gloo(tmp_path):
 
 
 # ---- sparse gradient exchange: host logic with torch stand-ins for the three CUDA row operations ----
+def _a4(x):
+    return (x + 3) // 4 * 4
+
+
 class TorchRowOps:
+    def compact_floats(self, m, num_coeffs):
+        return _a4(3 * m) + _a4(3 * num_coeffs * m) + _a4(m) + _a4(3 * m) + _a4(4 * m)
+
     def scan(self, b):
         mask = b.touch_mask.to(torch.int64)
         inc = torch.cumsum(mask, 0)
@@ -114,7 +121,8 @@ class TorchRowOps:
         for g in self._groups(b):
             w = g.shape[1]
             compact[off:off + m * w].copy_(g[sel].reshape(-1))
-            off += m * w
+            compact[off + m * w:off + _a4(m * w)] = 0
+            off += _a4(m * w)
 
     def scatter(self, b, offsets, m, compact):
         sel = b.touch_mask.bool()
@@ -122,7 +130,7 @@ class TorchRowOps:
         for g in self._groups(b):
             w = g.shape[1]
             g[sel] = compact[off:off + m * w].view(m, w)
-            off += m * w
+            off += _a4(m * w)
 
 
 class FakeBuffers:
