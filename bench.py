@@ -150,7 +150,7 @@ def sort_passes(P_bits_depth: int, num_tiles: int) -> int:
     return max(1, (P_bits_depth + tb + 7) // 8)
 
 
-def algorithmic_bytes(n: int, p: int, w: int, h: int, tile_passes: int) -> dict:
+def algorithmic_bytes(n: int, p: int, w: int, h: int, tile_passes: int, views: int = 1) -> dict:
     """ALGORITHMIC bytes per frame of each stage: each distinct input read once +
     each output written once, for the kernels as designed (depth passes hoisted before the key
     duplication: the sort moves 8-byte packed elements)."""
@@ -163,7 +163,8 @@ def algorithmic_bytes(n: int, p: int, w: int, h: int, tile_passes: int) -> dict:
         "tile_ranges": 0,                            # part of the sort (tile histogram -> ranges)
         "blend_fwd": 52 * p + 20 * w * h,            # index (4) + packed record (48) per pair, 20 B per pixel
         "blend_bwd": 52 * p + 20 * w * h + 48 * n,   # + dL/dcolor, final_T, n_contrib per pixel, 48-B gradient record
-        "preprocess_bwd": 336 * n,
+        # 336 B/Gaussian; views after the first of a step also READ the 236-B gradient row they add to
+        "preprocess_bwd": int((336 + 236 * (views - 1) / max(views, 1)) * n),
     }
 
 
@@ -374,7 +375,7 @@ def run_b200(args) -> dict:
         c_passes, c_bits = C.c_int(0), C.c_int(0)
         lib.cugs_b200_last_sort_plan(h, C.byref(c_passes), C.byref(c_bits))
         passes, key_bits = int(c_passes.value), int(c_bits.value)
-        alg = algorithmic_bytes(n, P, W, H, max(passes - 4, 1))
+        alg = algorithmic_bytes(n, P, W, H, max(passes - 4, 1), V)
         peak, peak_src = measured_peaks()
         hbm_stages = ["preprocess_fwd", "scan", "duplicate_with_keys", "sort", "preprocess_bwd"]
         rl_all = {}

@@ -94,6 +94,13 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    header = _HERE.parent / "include" / "cugs_b200.h"
+    if header.exists():  # a stale .so (older signatures) must fail loudly, not corrupt arguments
+        import re
+        want = int(re.search(r"#define CUGS_B200_ABI_VERSION (\d+)", header.read_text()).group(1))
+        if lib.cugs_b200_abi_version() != want:
+            raise RuntimeError(f"{path} has ABI version {lib.cugs_b200_abi_version()}, include/cugs_b200.h declares "
+                               f"{want}: rebuild with ./build.sh")
     _lib = lib
     return lib
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CUGS_B200_ABI_VERSION 1
+#define CUGS_B200_ABI_VERSION 3 /* bump on ANY signature change: callers compare it with cugs_b200_abi_version() */
 #define CUGS_TILE 16 /* rasterizer/sorting.hpp:16 kTileSize */
 
 enum {

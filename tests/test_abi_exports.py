@@ -28,7 +28,8 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/cugs_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
-    assert lib.cugs_b200_abi_version() == 1
+    header = (ROOT / "include" / "cugs_b200.h").read_text()
+    assert lib.cugs_b200_abi_version() == int(re.search(r"#define CUGS_B200_ABI_VERSION (\d+)", header).group(1))
 
 
 def test_size_queries_need_no_gpu():

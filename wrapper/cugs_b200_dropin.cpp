@@ -44,6 +44,9 @@ cugs_handle_t* handle_for(const torch::Tensor& t) {
     TORCH_CHECK(dev >= 0 && dev < 64, "bad CUDA device index ", dev);
     std::lock_guard<std::mutex> lock(mu);
     if (!handles[dev]) {
+        TORCH_CHECK(cugs_b200_abi_version() == CUGS_B200_ABI_VERSION, "libcugs_b200.so has ABI version ",
+                    cugs_b200_abi_version(), " but this wrapper was compiled against ", CUGS_B200_ABI_VERSION,
+                    ": rebuild the wrapper");
         const int st = cugs_b200_create(dev, &handles[dev]);
         TORCH_CHECK(st == 0, "cugs_b200_create(device=", dev, ") failed with status ", st,
                     " (the library is built for sm_100a only; there is no fallback)");
