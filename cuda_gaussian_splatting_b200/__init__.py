@@ -13,7 +13,7 @@ from .rasterizer import (  # noqa: F401
     rasterize_forward, render, render_backward, sort_gaussians,
 )
 from .training import (  # noqa: F401
-    AdamConfig, DensificationStats, FusedAdam, PositionLRConfig, SyntheticTrainer, TargetUploader, TrainConfig, active_sh_degree_for_step, combined_loss,
+    AdamConfig, DensificationStats, FusedAdam, MCMCConfig, PositionLRConfig, mcmc_inject_noise, mcmc_noise_lr, SyntheticTrainer, TargetUploader, TrainConfig, active_sh_degree_for_step, combined_loss,
     combined_loss_with_grad, l1_loss, position_lr, ssim, ssim_loss, ssim_mean,
 )
 from .synth import Scene, default_camera, ring_cameras, synth  # noqa: F401

@@ -73,6 +73,9 @@ SIGNATURES = {
     "cugs_b200_loss_l1_ssim": (_INT, [_P, _P, _INT, _INT, _F, _P, _P, _P, _P, _P, _SZ, _P]),
     "cugs_b200_adam_step": (_INT, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
                                     C.POINTER(_I64), C.POINTER(_F), _F, _F, _F, _F, _F, _F]),
+    "cugs_b200_adam_step_mcmc": (_INT, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
+                                         C.POINTER(_I64), C.POINTER(_F), _F, _F, _F, _F, _F, _F, _F, _F]),
+    "cugs_b200_mcmc_inject_noise": (_INT, [_P, _P, _I64, _P, _P, _P, _F, _F, _F, C.c_uint64, C.c_uint32, _P]),
     "cugs_b200_accumulate_stats": (_INT, [_P, _P, _I64, _P, _P, _P, _P, _P]),
 }
 

@@ -226,9 +226,22 @@ __device__ __forceinline__ void adam_element(float& p, float g, float& m, float&
     p = add_rn(p, -(mul_rn(lr, m_hat) / add_rn(sqrtf(v_hat), eps)));
 }
 
+// MCMC regulariser (optimizer/mcmc_densification.cpp:167-186): loss = lambda_o * mean(sigmoid(opacity)) +
+// lambda_s * mean(exp(scale)); its gradient is closed-form per element and is added to the incoming
+// gradient of the opacity / scale groups inside the Adam launch (the reference builds two autograd
+// graphs and two extra tensors per step, training/trainer.cpp:232-237).
+__device__ __forceinline__ float mcmc_reg_grad(int grp, float p, float reg_opa, float reg_scl) {
+    if (grp == 2) {
+        const float sg = 1.0f / (1.0f + expf(-p));
+        return reg_opa * sg * (1.0f - sg);
+    }
+    if (grp == 3) return reg_scl * expf(p);
+    return 0.0f;
+}
+
 __global__ void __launch_bounds__(256)
 k_adam_multi(AdamGroups G, int64_t total_chunks, float b1, float b2, float eps, float bc1, float bc2,
-             float grad_scale) {
+             float grad_scale, float reg_opa /* lambda_o / N */, float reg_scl /* lambda_s / (3N) */) {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total_chunks;
          c += (int64_t)gridDim.x * blockDim.x) {
         int grp = 0;
@@ -242,9 +255,26 @@ k_adam_multi(AdamGroups G, int64_t total_chunks, float b1, float b2, float eps, 
         float* m = G.m[grp];
         float* v = G.v[grp];
         const float lr = G.lr[grp];
+        const bool reg = (reg_opa != 0.0f && grp == 2) || (reg_scl != 0.0f && grp == 3);
         if (e0 + 4 <= G.count[grp]) {
             float4 pv = *reinterpret_cast<float4*>(p + e0);
-            const float4 gv = __ldcs(reinterpret_cast<const float4*>(g + e0));
+            float4 gv = __ldcs(reinterpret_cast<const float4*>(g + e0));
+            if (reg) {  // grad_scale == 1 in this mode is not required: the regulariser is added after scaling
+                gv.x = gv.x * grad_scale + mcmc_reg_grad(grp, pv.x, reg_opa, reg_scl);
+                gv.y = gv.y * grad_scale + mcmc_reg_grad(grp, pv.y, reg_opa, reg_scl);
+                gv.z = gv.z * grad_scale + mcmc_reg_grad(grp, pv.z, reg_opa, reg_scl);
+                gv.w = gv.w * grad_scale + mcmc_reg_grad(grp, pv.w, reg_opa, reg_scl);
+                float4 mv = *reinterpret_cast<float4*>(m + e0);
+                float4 vv = *reinterpret_cast<float4*>(v + e0);
+                adam_element(pv.x, gv.x, mv.x, vv.x, lr, b1, b2, eps, bc1, bc2);
+                adam_element(pv.y, gv.y, mv.y, vv.y, lr, b1, b2, eps, bc1, bc2);
+                adam_element(pv.z, gv.z, mv.z, vv.z, lr, b1, b2, eps, bc1, bc2);
+                adam_element(pv.w, gv.w, mv.w, vv.w, lr, b1, b2, eps, bc1, bc2);
+                *reinterpret_cast<float4*>(p + e0) = pv;
+                *reinterpret_cast<float4*>(m + e0) = mv;
+                *reinterpret_cast<float4*>(v + e0) = vv;
+                continue;
+            }
             float4 mv = *reinterpret_cast<float4*>(m + e0);
             float4 vv = *reinterpret_cast<float4*>(v + e0);
             adam_element(pv.x, gv.x * grad_scale, mv.x, vv.x, lr, b1, b2, eps, bc1, bc2);
@@ -257,10 +287,62 @@ k_adam_multi(AdamGroups G, int64_t total_chunks, float b1, float b2, float eps, 
         } else {
             for (int64_t e = e0; e < G.count[grp]; ++e) {
                 float pe = p[e], me = m[e], ve = v[e];
-                adam_element(pe, g[e] * grad_scale, me, ve, lr, b1, b2, eps, bc1, bc2);
+                const float ge = g[e] * grad_scale + (reg ? mcmc_reg_grad(grp, pe, reg_opa, reg_scl) : 0.0f);
+                adam_element(pe, ge, me, ve, lr, b1, b2, eps, bc1, bc2);
                 p[e] = pe; m[e] = me; v[e] = ve;
             }
         }
+    }
+}
+
+// ================================================================================================
+// MCMC position noise (optimizer/mcmc_densification.cpp:144-161): after the optimizer step
+//   positions += noise_lr * exp(scales) * sigmoid(-k (sigmoid(opacity) - t)) * N(0, 1)
+// One elementwise kernel (the reference: 6 libtorch kernels + a randn tensor); the normals come from
+// Philox-4x32-10 keyed by (seed) with counter (Gaussian index, step), so every rank of a
+// view-parallel run draws the same noise and the replicas stay bit-identical.
+// ================================================================================================
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
+                                              unsigned k1, unsigned (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(256)
+k_mcmc_noise(int64_t n, float* __restrict__ positions, const float* __restrict__ scales,
+             const float* __restrict__ opacities, float noise_lr, float gate_k, float gate_t, unsigned seed_lo,
+             unsigned seed_hi, unsigned step, float* __restrict__ normals_out /* optional [N,3] */) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned r[4];
+    philox4x32_10((unsigned)i, (unsigned)((uint64_t)i >> 32), step, 0x3c6ef372u, seed_lo, seed_hi, r);
+    // uniforms in (0, 1): 24 random bits + 0.5
+    const float u0 = ((float)(r[0] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float u1 = ((float)(r[1] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float u2 = ((float)(r[2] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float u3 = ((float)(r[3] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u1, &s0, &c0);
+    sincospif(2.0f * u3, &s1, &c1);
+    const float z0 = ra * c0, z1 = ra * s0, z2 = rb * c1;
+    (void)s1;
+    const float sg = 1.0f / (1.0f + expf(-opacities[i]));
+    const float gate = 1.0f / (1.0f + expf(gate_k * (sg - gate_t)));  // sigmoid(-k (sg - t))
+    const float f = noise_lr * gate;
+    positions[i * 3 + 0] += f * expf(scales[i * 3 + 0]) * z0;
+    positions[i * 3 + 1] += f * expf(scales[i * 3 + 1]) * z1;
+    positions[i * 3 + 2] += f * expf(scales[i * 3 + 2]) * z2;
+    if (normals_out != nullptr) {
+        normals_out[i * 3 + 0] = z0; normals_out[i * 3 + 1] = z1; normals_out[i * 3 + 2] = z2;
     }
 }
 
@@ -324,6 +406,15 @@ extern "C" int cugs_b200_adam_step(cugs_handle_t* h, void* stream, float* const 
                                    const float* const grads[5], float* const m[5], float* const v[5],
                                    const int64_t counts[5], const float lr[5], float beta1, float beta2,
                                    float eps, float bc1, float bc2, float grad_scale) {
+    return cugs_b200_adam_step_mcmc(h, stream, params, grads, m, v, counts, lr, beta1, beta2, eps, bc1, bc2,
+                                    grad_scale, 0.0f, 0.0f);
+}
+
+extern "C" int cugs_b200_adam_step_mcmc(cugs_handle_t* h, void* stream, float* const params[5],
+                                        const float* const grads[5], float* const m[5], float* const v[5],
+                                        const int64_t counts[5], const float lr[5], float beta1, float beta2,
+                                        float eps, float bc1, float bc2, float grad_scale, float lambda_opacity,
+                                        float lambda_scale) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, params && grads && m && v && counts && lr, "null pointer");
     AdamGroups G;
@@ -341,9 +432,27 @@ extern "C" int cugs_b200_adam_step(cugs_handle_t* h, void* stream, float* const 
     int64_t blocks = (chunks + 255) / 256;
     const int64_t cap = (int64_t)h->sm_count * 8 * 4;  // persistent-ish grid, multiple of the SM count
     if (blocks > cap) blocks = cap;
+    // mean over N opacities / 3N scale components (mcmc_densification.cpp:177-178)
+    const float reg_opa = (lambda_opacity != 0.0f && counts[2] > 0) ? lambda_opacity / (float)counts[2] : 0.0f;
+    const float reg_scl = (lambda_scale != 0.0f && counts[3] > 0) ? lambda_scale / (float)counts[3] : 0.0f;
     k_adam_multi<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(G, chunks, beta1, beta2, eps, bc1, bc2,
-                                                                    grad_scale);
+                                                                    grad_scale, reg_opa, reg_scl);
     CUGS_LAUNCH_CHECK(h, "k_adam_multi");
+    return CUGS_OK;
+}
+
+extern "C" int cugs_b200_mcmc_inject_noise(cugs_handle_t* h, void* stream, int64_t n, float* positions,
+                                           const float* scales, const float* opacities, float noise_lr,
+                                           float gate_k, float gate_t, uint64_t seed, uint32_t step,
+                                           float* normals_out) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    CUGS_REQUIRE(h, n >= 0, "n must be >= 0");
+    if (n == 0) return CUGS_OK;
+    CUGS_REQUIRE(h, positions && scales && opacities, "null pointer");
+    k_mcmc_noise<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n, positions, scales, opacities, noise_lr, gate_k, gate_t, (unsigned)(seed & 0xffffffffu),
+        (unsigned)(seed >> 32), step, normals_out);
+    CUGS_LAUNCH_CHECK(h, "k_mcmc_noise");
     return CUGS_OK;
 }
 

@@ -123,6 +123,42 @@ class AdamConfig:  # optimizer/adam.hpp:30-41
     eps: float = 1e-15
 
 
+@dataclass
+class MCMCConfig:  # the per-step fields of optimizer/mcmc_densification.hpp:27-51
+    noise_lr_init: float = 5e5
+    noise_lr_final: float = 1e3
+    noise_lr_max_steps: int = 30000
+    noise_gate_k: float = 100.0
+    noise_gate_t: float = 0.995
+    lambda_opacity: float = 0.01
+    lambda_scale: float = 0.01
+    seed: int = 0x5EED
+
+
+def mcmc_noise_lr(step: int, config: MCMCConfig) -> float:
+    """MCMCController::noise_lr (mcmc_densification.cpp:38-47): log-linear decay in float32."""
+    if step >= config.noise_lr_max_steps:
+        return float(np.float32(config.noise_lr_final))
+    if step <= 0:
+        return float(np.float32(config.noise_lr_init))
+    t = np.float32(step) / np.float32(config.noise_lr_max_steps)
+    log_ratio = np.float32(math.log(np.float32(config.noise_lr_final) / np.float32(config.noise_lr_init)))
+    return float(np.float32(config.noise_lr_init) * np.float32(math.exp(np.float32(t * log_ratio))))
+
+
+def mcmc_inject_noise(model: GaussianModel, step: int, config: MCMCConfig, return_normals: bool = False):
+    """MCMCController::inject_noise (mcmc_densification.cpp:144-161), one kernel, in place."""
+    dev = model.positions.device
+    lib, h = _lib_and_handle(dev)
+    n = model.num_gaussians()
+    normals = torch.empty((n, 3), dtype=torch.float32, device=dev) if return_normals else None
+    st = lib.cugs_b200_mcmc_inject_noise(h, _stream(dev), n, _ptr(model.positions), _ptr(model.scales),
+                                         _ptr(model.opacities), mcmc_noise_lr(step, config), config.noise_gate_k,
+                                         config.noise_gate_t, int(config.seed), int(step), _ptr(normals))
+    _lib.check(h, st, "cugs_b200_mcmc_inject_noise")
+    return normals
+
+
 class FusedAdam:
     """optimizer/fused_adam.hpp:29-106. Group order positions, sh_coeffs, opacities, scales,
     rotations (fused_adam.cu:94-97); all five groups are updated by ONE kernel launch."""
@@ -144,6 +180,8 @@ class FusedAdam:
         self.learning_rates = [c.position_lr_config.lr_init, c.lr_sh_coeffs, c.lr_opacities, c.lr_scales,
                                c.lr_rotations]
         self.grad_scale = 1.0
+        self.mcmc_lambda_opacity = 0.0  # > 0: MCMC regulariser gradient added inside the launch
+        self.mcmc_lambda_scale = 0.0
 
     def apply_gradients(self, grads: BackwardOutput) -> None:  # fused_adam.cu:113-120
         self.grads = [grads.dL_dpositions, grads.dL_dsh_coeffs, grads.dL_dopacities, grads.dL_dscales,
@@ -186,9 +224,10 @@ class FusedAdam:
                                       self.v[k].data_ptr())
             cnt[k] = self._params[k].numel()
             lr[k] = self.learning_rates[k]
-        st = lib.cugs_b200_adam_step(h, _stream(dev), P, G, M, V, cnt, lr, self.config.beta1, self.config.beta2,
-                                     self.config.eps, bc1, bc2, float(self.grad_scale))
-        _lib.check(h, st, "cugs_b200_adam_step")
+        st = lib.cugs_b200_adam_step_mcmc(h, _stream(dev), P, G, M, V, cnt, lr, self.config.beta1, self.config.beta2,
+                                          self.config.eps, bc1, bc2, float(self.grad_scale),
+                                          float(self.mcmc_lambda_opacity), float(self.mcmc_lambda_scale))
+        _lib.check(h, st, "cugs_b200_adam_step_mcmc")
 
 
 class DensificationStats:
@@ -226,6 +265,7 @@ class TrainConfig:  # the fields of training/trainer.hpp:38-75 that reach the ho
     background: tuple = (0.0, 0.0, 0.0)
     adam: AdamConfig = field(default_factory=AdamConfig)
     densify: bool = True  # accumulate the ADC statistics every step (trainer.cpp:269)
+    mcmc: Optional["MCMCConfig"] = None  # MCMC mode (trainer.cpp:232-237, :246-266): regulariser + noise, no ADC stats
 
 
 class SyntheticTrainer:
@@ -247,6 +287,9 @@ class SyntheticTrainer:
         self.buffers = FrameBuffers(n, cam0.width, cam0.height, int(model.sh_coeffs.shape[2]), model.positions.device)
         self.optimizer = FusedAdam(model, self.config.adam)
         self.optimizer.grad_scale = 1.0 / float(self.total_views)
+        if self.config.mcmc is not None:
+            self.optimizer.mcmc_lambda_opacity = self.config.mcmc.lambda_opacity
+            self.optimizer.mcmc_lambda_scale = self.config.mcmc.lambda_scale
         self.stats = DensificationStats(n, model.positions.device)
         self._RenderSettings = RenderSettings
         self.last_scalars = None
@@ -260,7 +303,8 @@ class SyntheticTrainer:
         settings = self._RenderSettings(cfg.background, degree, 1.0)
         multi = torch.distributed.is_available() and torch.distributed.is_initialized() and \
             torch.distributed.get_world_size() > 1
-        if cfg.densify:
+        densify = cfg.densify and cfg.mcmc is None  # the ADC statistics are unused in MCMC mode (trainer.cpp:246-266)
+        if densify:
             if multi:  # per-step statistics live in the arena and are summed by the all-reduce
                 b.step_grad_accum.zero_(); b.step_grad_count.zero_(); b.step_max_radii.zero_()
                 stats = (b.step_grad_accum, b.step_grad_count, b.step_max_radii)
@@ -276,14 +320,16 @@ class SyntheticTrainer:
                             touch_mask=b.touch_mask if multi else None)  # :228, :269
             scal_sum = scalars if scal_sum is None else scal_sum + scalars
         if multi:
-            self.last_exchange = sparse_allreduce_step(b, with_stats=cfg.densify)
-            if cfg.densify:
+            self.last_exchange = sparse_allreduce_step(b, with_stats=densify)
+            if densify:
                 fold_step_stats(b.step_grad_accum, b.step_grad_count, b.step_max_radii, self.stats.grad_accum,
                                 self.stats.grad_count, self.stats.max_radii_2d)
         self.optimizer.zero_grad()                                       # :240-242
         self.optimizer.apply_gradients(BackwardOutput(b.dL_dpositions, b.dL_drotations, b.dL_dscales,
                                                       b.dL_dopacities, b.dL_dsh_coeffs, b.dL_dmeans_2d))
         self.optimizer.step()
+        if cfg.mcmc is not None:  # position noise every iteration, after the optimizer step (trainer.cpp:251)
+            mcmc_inject_noise(self.model, step, cfg.mcmc)
         self.last_scalars = scal_sum / float(len(self.cameras))
         return self.last_scalars
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CUGS_B200_ABI_VERSION 3 /* bump on ANY signature change: callers compare it with cugs_b200_abi_version() */
+#define CUGS_B200_ABI_VERSION 4 /* bump on ANY signature change: callers compare it with cugs_b200_abi_version() */
 #define CUGS_TILE 16 /* rasterizer/sorting.hpp:16 kTileSize */
 
 enum {
@@ -225,6 +225,22 @@ int cugs_b200_adam_step(cugs_handle_t* h, void* stream, float* const params[5],
                         const float* const grads[5], float* const m[5], float* const v[5],
                         const int64_t counts[5], const float lr[5], float beta1, float beta2,
                         float eps, float bc1, float bc2, float grad_scale);
+/* MCMC per-step operations (optimizer/mcmc_densification.cpp; training/trainer.cpp:232-237, :251).
+ * adam_step_mcmc = adam_step with the closed-form gradient of MCMCController::compute_regularization
+ * (:167-186: lambda_opacity * mean(sigmoid(opacity)) + lambda_scale * mean(exp(scale))) added to the
+ * opacity / scale gradients inside the same launch (after grad_scale).
+ * mcmc_inject_noise = MCMCController::inject_noise (:144-161), in place on positions, using the
+ * (already updated) scales and opacities; noise_lr = MCMCController::noise_lr(step) computed by the
+ * caller; normals are Philox-4x32-10(seed; index, step) so that replicated ranks draw identical noise;
+ * normals_out (optional [N,3]) returns the N(0,1) draws for testing. */
+int cugs_b200_adam_step_mcmc(cugs_handle_t* h, void* stream, float* const params[5],
+                             const float* const grads[5], float* const m[5], float* const v[5],
+                             const int64_t counts[5], const float lr[5], float beta1, float beta2,
+                             float eps, float bc1, float bc2, float grad_scale, float lambda_opacity,
+                             float lambda_scale);
+int cugs_b200_mcmc_inject_noise(cugs_handle_t* h, void* stream, int64_t n, float* positions,
+                                const float* scales, const float* opacities, float noise_lr, float gate_k,
+                                float gate_t, uint64_t seed, uint32_t step, float* normals_out);
 /* DensificationController::accumulate_gradients (optimizer/densification.cpp:59-88). */
 int cugs_b200_accumulate_stats(cugs_handle_t* h, void* stream, int64_t n,
                                const float* dL_dmeans_2d, const int32_t* radii, float* grad_accum,

@@ -20,6 +20,10 @@
 #include "core/sh_backward.hpp"
 #include "core/types.hpp"
 #include "optimizer/fused_adam.hpp"
+#define private public  // test harness only: read DensificationController's accumulators
+#include "optimizer/densification.hpp"
+#undef private
+#include "optimizer/mcmc_densification.hpp"
 #include "rasterizer/backward.hpp"
 #include "rasterizer/forward.hpp"
 #include "rasterizer/projection.hpp"
@@ -166,6 +170,35 @@ struct RefAdam {
     }
 };
 
+// MCMCController::compute_regularization (autograd) -> {loss, dL/dopacities, dL/dscales}
+std::vector<T> ref_mcmc_regularization(const T& pos, const T& sh, const T& opa, const T& rot, const T& scl,
+                                       double lambda_opacity, double lambda_scale) {
+    cugs::MCMCConfig cfg;
+    cfg.lambda_opacity = static_cast<float>(lambda_opacity);
+    cfg.lambda_scale = static_cast<float>(lambda_scale);
+    cugs::MCMCController ctrl(cfg, 1.0f);
+    T d_opa, d_scl;
+    const float loss = ctrl.compute_regularization(make_model(pos, sh, opa, rot, scl), d_opa, d_scl);
+    return {torch::tensor({loss}), d_opa, d_scl};
+}
+
+// MCMCController::inject_noise, in place on `pos`; returns the noise learning rate of the step
+double ref_mcmc_inject_noise(T pos, const T& sh, const T& opa, const T& rot, const T& scl, int step) {
+    cugs::MCMCController ctrl(cugs::MCMCConfig{}, 1.0f);
+    auto model = make_model(pos, sh, opa, rot, scl);
+    ctrl.inject_noise(model, step);
+    return ctrl.noise_lr(step);
+}
+
+double ref_mcmc_noise_lr(int step) { return cugs::MCMCController(cugs::MCMCConfig{}, 1.0f).noise_lr(step); }
+
+// DensificationController::accumulate_gradients applied `times` times -> {grad_accum, grad_count, max_radii}
+std::vector<T> ref_accumulate_gradients(const T& dL_dmeans_2d, const T& radii, int times) {
+    cugs::DensificationController ctrl(cugs::DensificationConfig{}, 1.0f);
+    for (int i = 0; i < times; ++i) ctrl.accumulate_gradients(dL_dmeans_2d, radii);
+    return {ctrl.grad_accum_, ctrl.grad_count_, ctrl.max_radii_2d_};
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -179,6 +212,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("render_backward", &ref_render_backward);
     m.def("combined_loss_with_grad", &ref_combined_loss_with_grad,
           py::call_guard<py::gil_scoped_release>());  // autograd must not run under the GIL
+    m.def("mcmc_regularization", &ref_mcmc_regularization, py::call_guard<py::gil_scoped_release>());
+    m.def("mcmc_inject_noise", &ref_mcmc_inject_noise);
+    m.def("mcmc_noise_lr", &ref_mcmc_noise_lr);
+    m.def("accumulate_gradients", &ref_accumulate_gradients);
     m.def("evaluate_sh_cuda", &cugs::evaluate_sh_cuda);
     m.def("evaluate_sh_cpu", &cugs::evaluate_sh_cpu);
     m.def("evaluate_sh_backward_cuda", &cugs::evaluate_sh_backward_cuda);

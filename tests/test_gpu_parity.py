@@ -639,3 +639,88 @@ def test_touch_mask_and_row_compaction(torch):
     assert torch.equal(rows * 0 + torch.cat([b.dL_dpositions, b.dL_dsh_coeffs.reshape(scene.n, -1), b.dL_dopacities,
                                              b.dL_dscales, b.dL_drotations], dim=1), rows * 2.0)
     assert before.numel() == b.grad_arena.numel()
+
+
+# ================================================================================================
+# MCMC per-step operations, and the densification statistics against the
+# reference's own DensificationController
+# ================================================================================================
+def test_accumulate_stats_vs_reference_controller(ref, torch):
+    rng = np.random.default_rng(16)
+    n = 20_011
+    g = torch.from_numpy(rng.normal(size=(n, 2)).astype(np.float32)).cuda()
+    r = torch.from_numpy(rng.integers(0, 5, size=n).astype(np.int32)).cuda()
+    st = cugs.DensificationStats(n, "cuda")
+    for _ in range(3):
+        st.accumulate_gradients(g, r)
+    ra, rc, rm = ref.accumulate_gradients(g, r, 3)   # optimizer/densification.cpp:59-88, unmodified
+    assert torch.equal(st.grad_count, rc) and torch.equal(st.max_radii_2d, rm)
+    assert float((st.grad_accum - ra).abs().max()) <= 1e-6 * float(ra.abs().max())
+
+
+def test_mcmc_regulariser_fused_in_adam_vs_reference(ref, torch):
+    """One optimizer step with the MCMC regulariser: reference = compute_regularization (autograd) added
+    to the gradients (trainer.cpp:232-237) then FusedAdam::step; here = one launch."""
+    scene = cugs.synth(2003, 64, 48, seed=23)
+    mine, theirs = to_torch(scene), to_torch(scene)
+    rng = np.random.default_rng(2)
+    g = {k: torch.from_numpy(rng.normal(size=tuple(getattr(mine, k).shape)).astype(np.float32)).cuda()
+         for k in ("positions", "rotations", "scales", "opacities", "sh_coeffs")}
+    lam_o, lam_s = 0.5, 0.25   # large enough to matter against unit gradients
+    _, d_opa, d_scl = ref.mcmc_regularization(theirs.positions, theirs.sh_coeffs, theirs.opacities, theirs.rotations,
+                                              theirs.scales, lam_o, lam_s)
+    # closed form vs the reference's autograd result
+    sg = torch.sigmoid(mine.opacities)
+    assert float((d_opa - lam_o * sg * (1 - sg) / scene.n).abs().max()) <= 1e-9
+    assert float((d_scl - lam_s * torch.exp(mine.scales) / (3 * scene.n)).abs().max()) <= 1e-9
+    ropt = ref.FusedAdam(theirs.positions, theirs.sh_coeffs, theirs.opacities, theirs.rotations, theirs.scales)
+    opt = cugs.FusedAdam(mine)
+    opt.mcmc_lambda_opacity, opt.mcmc_lambda_scale = lam_o * 1e3, lam_s * 1e3   # visible against O(1) gradients
+    _, d_opa, d_scl = ref.mcmc_regularization(theirs.positions, theirs.sh_coeffs, theirs.opacities, theirs.rotations,
+                                              theirs.scales, lam_o * 1e3, lam_s * 1e3)
+    for step in range(3):
+        opt.update_lr(step)
+        opt.zero_grad()
+        opt.apply_gradients(cugs.BackwardOutput(g["positions"], g["rotations"], g["scales"], g["opacities"],
+                                                g["sh_coeffs"], None))
+        opt.step()
+        _, d_opa, d_scl = ref.mcmc_regularization(theirs.positions, theirs.sh_coeffs, theirs.opacities,
+                                                  theirs.rotations, theirs.scales, lam_o * 1e3, lam_s * 1e3)
+        ropt.step([g["positions"], g["rotations"], g["scales"] + d_scl, g["opacities"] + d_opa, g["sh_coeffs"]], step)
+    for a, b_ in zip((mine.positions, mine.sh_coeffs, mine.opacities, mine.rotations, mine.scales), ropt.params()):
+        assert float((a - b_).abs().max()) <= 2e-6, "parameters after 3 MCMC-regularised Adam steps"
+
+
+def test_mcmc_noise_matches_reference_formula_and_is_replicable(ref, torch):
+    """inject_noise: positions += noise_lr(step) * exp(scales) * sigmoid(-k (sigmoid(o) - t)) * N(0,1)
+    (mcmc_densification.cpp:144-161). The deterministic factor must match the reference's formula; the
+    normals are Philox draws: standard-normal statistics, identical for equal (seed, step), different
+    across steps. The reference's own randn cannot be reproduced, so its displacement is compared
+    statistically."""
+    scene = cugs.synth(200_000, 64, 48, seed=29)
+    m = to_torch(scene)
+    m.opacities.copy_(torch.randn_like(m.opacities) * 3 - 4)   # low opacities: gate is not ~0
+    cfg = cugs.MCMCConfig()
+    assert abs(cugs.mcmc_noise_lr(12345, cfg) - ref.mcmc_noise_lr(12345)) <= 1e-3 * ref.mcmc_noise_lr(12345)
+    assert cugs.mcmc_noise_lr(0, cfg) == ref.mcmc_noise_lr(0) and cugs.mcmc_noise_lr(40000, cfg) == ref.mcmc_noise_lr(40000)
+    p0 = m.positions.clone()
+    z = cugs.mcmc_inject_noise(m, 100, cfg, return_normals=True)
+    gate = torch.sigmoid(-cfg.noise_gate_k * (torch.sigmoid(m.opacities) - cfg.noise_gate_t))
+    expect = p0 + cugs.mcmc_noise_lr(100, cfg) * torch.exp(m.scales) * gate * z
+    assert float((m.positions - expect).abs().max()) <= 1e-5 * float(expect.abs().max())
+    zs = z.double()
+    assert abs(float(zs.mean())) < 0.01 and abs(float(zs.std()) - 1.0) < 0.01
+    assert abs(float((zs ** 4).mean()) - 3.0) < 0.1 and abs(float((zs[:, 0] * zs[:, 1]).mean())) < 0.01
+    m2 = to_torch(scene)
+    m2.opacities.copy_(m.opacities)
+    z2 = cugs.mcmc_inject_noise(m2, 100, cfg, return_normals=True)
+    z3 = cugs.mcmc_inject_noise(m2, 101, cfg, return_normals=True)
+    assert torch.equal(z, z2) and not torch.equal(z, z3)
+    # the reference on the same model: displacement / deterministic factor is standard normal too
+    r = to_torch(scene)
+    r.opacities.copy_(m.opacities)
+    rp0 = r.positions.clone()
+    lr = ref.mcmc_inject_noise(r.positions, r.sh_coeffs, r.opacities, r.rotations, r.scales, 100)
+    fac = lr * torch.exp(r.scales) * gate
+    zr = ((r.positions - rp0) / fac)[(fac > 1e-3 * fac.max()).all(dim=1)].double()
+    assert abs(float(zr.mean())) < 0.02 and abs(float(zr.std()) - 1.0) < 0.02
