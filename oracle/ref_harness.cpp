@@ -170,6 +170,42 @@ struct RefAdam {
     }
 };
 
+// The per-step sequence of Trainer::train_step (training/trainer.cpp:201-242) written against the
+// reference's public API only: render -> combined_loss + autograd -> render_backward -> FusedAdam.
+// Compiled unchanged into cugs_ref (reference kernels) and cugs_dropin (libcugs_b200 behind
+// wrapper/cugs_b200_dropin.cpp): the same caller code runs on both libraries.
+// Returns {loss per step [K], positions, sh_coeffs, opacities, rotations, scales}.
+std::vector<T> ref_train_steps(const T& pos, const T& sh, const T& opa, const T& rot, const T& scl,
+                               const std::vector<double>& cam, const T& target, const std::vector<double>& bg,
+                               int max_degree, double lambda, int first_step, int n_steps) {
+    auto model = make_model(pos.clone(), sh.clone(), opa.clone(), rot.clone(), scl.clone());
+    cugs::FusedAdam optimizer(model, cugs::AdamConfig{});
+    const auto camera = make_camera(cam);
+    std::vector<float> losses;
+    for (int step = first_step; step < first_step + n_steps; ++step) {
+        optimizer.update_lr(step);                                                    // trainer.cpp:180
+        const int degree = cugs::active_sh_degree_for_step(step, max_degree);         // :183
+        const auto settings = make_settings(bg, degree, 1.0);
+        cugs::RenderOutput out;
+        {
+            torch::NoGradGuard ng;
+            out = cugs::render(model, camera, settings);                              // :211
+        }
+        auto rendered = out.color.clone().detach().requires_grad_(true);             // :214-217
+        auto loss = cugs::combined_loss(rendered, target, static_cast<float>(lambda));
+        loss.backward();
+        auto dL_dcolor = rendered.grad().clone();
+        torch::NoGradGuard ng;
+        auto grads = cugs::render_backward(dL_dcolor, out, model, camera, settings);  // :228
+        optimizer.zero_grad();                                                        // :240-242
+        optimizer.apply_gradients(grads);
+        optimizer.step();
+        losses.push_back(loss.item<float>());
+    }
+    return {torch::tensor(losses), model.positions.detach(), model.sh_coeffs.detach(), model.opacities.detach(),
+            model.rotations.detach(), model.scales.detach()};
+}
+
 // MCMCController::compute_regularization (autograd) -> {loss, dL/dopacities, dL/dscales}
 std::vector<T> ref_mcmc_regularization(const T& pos, const T& sh, const T& opa, const T& rot, const T& scl,
                                        double lambda_opacity, double lambda_scale) {
@@ -212,6 +248,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("render_backward", &ref_render_backward);
     m.def("combined_loss_with_grad", &ref_combined_loss_with_grad,
           py::call_guard<py::gil_scoped_release>());  // autograd must not run under the GIL
+    m.def("train_steps", &ref_train_steps, py::call_guard<py::gil_scoped_release>());
     m.def("mcmc_regularization", &ref_mcmc_regularization, py::call_guard<py::gil_scoped_release>());
     m.def("mcmc_inject_noise", &ref_mcmc_inject_noise);
     m.def("mcmc_noise_lr", &ref_mcmc_noise_lr);
