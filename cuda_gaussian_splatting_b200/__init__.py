@@ -17,6 +17,7 @@ from .training import (  # noqa: F401
     combined_loss_with_grad, l1_loss, position_lr, ssim, ssim_loss, ssim_mean,
 )
 from .synth import Scene, default_camera, ring_cameras, synth  # noqa: F401
+from .ply_io import read_gaussian_ply, write_gaussian_ply  # noqa: F401
 from .parallel import (  # noqa: F401
     allreduce_step, arena_layout, fold_step_stats, grad_scale_for, shard_views, sparse_allreduce_step,
 )

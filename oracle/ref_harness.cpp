@@ -31,6 +31,7 @@
 #include "rasterizer/rasterizer.hpp"
 #include "rasterizer/sorting.hpp"
 #include "training/loss.hpp"
+#include "utils/ply_io.hpp"
 
 namespace {
 
@@ -206,6 +207,16 @@ std::vector<T> ref_train_steps(const T& pos, const T& sh, const T& opa, const T&
             model.rotations.detach(), model.scales.detach()};
 }
 
+// Gaussian PLY checkpoint format (utils/ply_io.cpp:98-196, :258-351), CPU tensors
+bool ref_write_gaussian_ply(const std::string& path, const T& pos, const T& sh, const T& opa, const T& rot,
+                            const T& scl) {
+    return cugs::write_gaussian_ply(path, make_model(pos, sh, opa, rot, scl));
+}
+std::vector<T> ref_read_gaussian_ply(const std::string& path) {
+    auto m = cugs::read_gaussian_ply(path);
+    return {m.positions, m.sh_coeffs, m.opacities, m.rotations, m.scales};
+}
+
 // MCMCController::compute_regularization (autograd) -> {loss, dL/dopacities, dL/dscales}
 std::vector<T> ref_mcmc_regularization(const T& pos, const T& sh, const T& opa, const T& rot, const T& scl,
                                        double lambda_opacity, double lambda_scale) {
@@ -248,6 +259,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("render_backward", &ref_render_backward);
     m.def("combined_loss_with_grad", &ref_combined_loss_with_grad,
           py::call_guard<py::gil_scoped_release>());  // autograd must not run under the GIL
+    m.def("write_gaussian_ply", &ref_write_gaussian_ply);
+    m.def("read_gaussian_ply", &ref_read_gaussian_ply);
     m.def("train_steps", &ref_train_steps, py::call_guard<py::gil_scoped_release>());
     m.def("mcmc_regularization", &ref_mcmc_regularization, py::call_guard<py::gil_scoped_release>());
     m.def("mcmc_inject_noise", &ref_mcmc_inject_noise);
