@@ -249,7 +249,9 @@ def run_b200(args) -> dict:
             exchange.update(mode="dense")
         else:
             exchange.update(cugs.sparse_allreduce_step(buf, with_stats=False))
-    touch = buf.touch_mask if (world > 1 and not args.dense_allreduce) else None
+    # touch mask + sparse gradient rows (rows a view does not touch are neither read nor written) unless
+    # the dense exchange is requested (it sums rows this rank's mask does not know about)
+    touch = None if args.dense_allreduce else buf.touch_mask
 
     # Two frames in flight inside one step: view v runs on stream v % 2 with its own frame buffers, so
     # the preprocess / sort / forward blend of view v+1 overlap the (issue-bound) backward blend of view v.
@@ -279,7 +281,8 @@ def run_b200(args) -> dict:
         out = cugs.render(model, cams[v], settings, b)
         if prev_bwd is not None:
             torch.cuda.current_stream(dev).wait_event(prev_bwd)
-        cugs.render_backward(dLs[v], out, model, cams[v], settings, b, accumulate=(v > 0), touch_mask=touch)
+        cugs.render_backward(dLs[v], out, model, cams[v], settings, b, accumulate=(v > 0), touch_mask=touch,
+                             sparse_rows=touch is not None)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
         return ev
@@ -303,7 +306,8 @@ def run_b200(args) -> dict:
         uploader.release()
         if prev_bwd is not None:
             torch.cuda.current_stream(dev).wait_event(prev_bwd)
-        cugs.render_backward(g, out, model, cams[v], settings, b, accumulate=(v > 0), touch_mask=touch)
+        cugs.render_backward(g, out, model, cams[v], settings, b, accumulate=(v > 0), touch_mask=touch,
+                             sparse_rows=touch is not None)
         scal_hosts[v].copy_(sc, non_blocking=True)                            # D2H of {loss, l1, ssim}
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
@@ -352,7 +356,8 @@ def run_b200(args) -> dict:
     for _ in range(args.steps):
         for v in range(V):  # (one frame in flight here: the stage events are per handle)
             out = cugs.render(model, cams[v], settings, buf)
-            cugs.render_backward(dLs[v], out, model, cams[v], settings, buf, accumulate=(v > 0))
+            cugs.render_backward(dLs[v], out, model, cams[v], settings, buf, accumulate=(v > 0), touch_mask=touch,
+                                 sparse_rows=touch is not None)
             lib.cugs_b200_get_stage_ms(h, ms8)
             for k in range(8):
                 stage_sum[k] += max(float(ms8[k]), 0.0)

@@ -39,7 +39,7 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
                                float* dL_drotations, float* dL_dscales, float* dL_dopacities,
                                float* dL_dsh_coeffs, float* grad_accum, float* grad_count,
                                float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out,
-                               bool accumulate, int32_t* touch_mask);
+                               bool accumulate, int32_t* touch_mask, bool sparse_rows);
 extern "C" int cugs_b200_sort_num_passes(int depth_bits, int tile_bits);
 extern "C" int cugs_b200_sort_pairs_pingpong(cugs_handle_t* h, void* stream, int64_t p, int depth_bits,
                                              int tile_bits, uint64_t* keys_a, int32_t* vals_a,
@@ -318,7 +318,7 @@ extern "C" int cugs_b200_render_backward(
     const float* final_T, const int32_t* n_contrib, const float* dL_dcolor, float* dL_dpositions,
     float* dL_drotations, float* dL_dscales, float* dL_dopacities, float* dL_dsh_coeffs,
     float* dL_dmeans_2d, float* grad_accum, float* grad_count, float* max_radii, int32_t* touch_mask,
-    int accumulate, void* workspace, size_t workspace_bytes) {
+    int flags, void* workspace, size_t workspace_bytes) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, n >= 0, "n must be >= 0");
     if (n == 0) return CUGS_OK;
@@ -345,8 +345,9 @@ extern "C" int cugs_b200_render_backward(
     if (int e = cugs_preprocess_bwd_launch(h, s, n, v, positions, rotations, scales, opacities, sh_coeffs,
                                            radii, rgb, nullptr, nullptr, nullptr, nullptr, dL_dpositions,
                                            dL_drotations, dL_dscales, dL_dopacities, dL_dsh_coeffs, grad_accum,
-                                           grad_count, max_radii, w.grad_acc, dL_dmeans_2d, accumulate != 0,
-                                           touch_mask))
+                                           grad_count, max_radii, w.grad_acc, dL_dmeans_2d,
+                                           (flags & CUGS_BWD_ACCUMULATE) != 0, touch_mask,
+                                           (flags & CUGS_BWD_SPARSE_ROWS) != 0))
         return e;
     mark(h, 10, s);
     return CUGS_OK;

@@ -319,7 +319,8 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                  const float4* __restrict__ gacc /* [N,3] packed blend gradients or null */,
                  float* __restrict__ dL_dmeans_2d_out /* written when gacc != null */,
                  bool accumulate /* add to the five parameter-gradient outputs instead of overwriting */,
-                 int* __restrict__ touch_mask /* optional: 1 where the incoming 2-D gradient is non-zero */) {
+                 int* __restrict__ touch_mask /* optional: 1 where the incoming 2-D gradient is non-zero */,
+                 bool sparse_rows /* with touch_mask: only move gradient rows that can be non-zero */) {
     __shared__ __align__(16) float sY[kPreWarps][32 * kYStride];
     __shared__ float sG[kPreWarps][96];  // gated dL/drgb per (Gaussian, channel)
 
@@ -333,6 +334,12 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
     int radius = 0;
     float gate_g[3] = {0.f, 0.f, 0.f};
     float in_m0 = 0.f, in_m1 = 0.f, in_da = 0.f, in_db = 0.f, in_dc = 0.f, in_dop = 0.f;
+    // sparse_rows: the caller guarantees that every gradient row whose mask entry is 0 on entry is all
+    // zero (true after allocation with zeros, after this kernel, and after the sparse exchange). A
+    // row is then written only if it is touched now or may hold an old value (overwrite mode), and
+    // read-modified-written only if it is touched now (accumulate mode): ~80 % of the rows of a
+    // view are skipped entirely.
+    bool write_row = valid;
     if (valid) {
         px = positions[i * 3 + 0]; py = positions[i * 3 + 1]; pz = positions[i * 3 + 2];
         radius = radii[i];
@@ -345,7 +352,9 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
             if (touch_mask != nullptr) {
                 const bool t = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) |
                                (b.z != 0.f) | (b.w != 0.f) | (c.x != 0.f);
-                touch_mask[i] = accumulate ? (touch_mask[i] | (int)t) : (int)t;
+                const int old = (accumulate || sparse_rows) ? touch_mask[i] : 0;
+                touch_mask[i] = accumulate ? (old | (int)t) : (int)t;
+                if (sparse_rows) write_row = accumulate ? t : (t || old != 0);
             }
         } else {
             dr[0] = dL_drgb[i * 3]; dr[1] = dL_drgb[i * 3 + 1]; dr[2] = dL_drgb[i * 3 + 2];
@@ -489,7 +498,7 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
             g_opa = in_dop * sg * (1.0f - sg);
         }
     }
-    if (valid) {
+    if (write_row) {
         if (accumulate) {
             g_pos[0] += dL_dpos[i * 3 + 0]; g_pos[1] += dL_dpos[i * 3 + 1]; g_pos[2] += dL_dpos[i * 3 + 2];
             const float4 r4 = reinterpret_cast<const float4*>(dL_drot)[i];
@@ -501,6 +510,8 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
         reinterpret_cast<float4*>(dL_drot)[i] = make_float4(g_rot[0], g_rot[1], g_rot[2], g_rot[3]);
         dL_dscl[i * 3 + 0] = g_scl[0]; dL_dscl[i * 3 + 1] = g_scl[1]; dL_dscl[i * 3 + 2] = g_scl[2];
         dL_dopa[i] = g_opa;
+    }
+    if (valid) {
         if (grad_accum != nullptr) {  // optimizer/densification.cpp:59-88
             if (radius > 0) {
                 grad_accum[i] += sqrtf(m0 * m0 + m1 * m1);
@@ -511,6 +522,7 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
     }
 
     // ---- phase B: dL/dSH = gate * dL/drgb * Y_k, explicit zeros for inactive coefficients ----
+    const unsigned row_mask = __ballot_sync(kFull, write_row);  // bit g: Gaussian g0 + g moves its rows
     if (kVecSH) {
         __syncwarp();
         float4* out4 = reinterpret_cast<float4*>(dL_dsh) + g0 * 12;
@@ -520,6 +532,7 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
             const int q = lane + 32 * it;
             if (q >= lim) break;
             const int g = q / 12;
+            if (!((row_mask >> g) & 1u)) continue;
             const int k0 = (q & 3) * 4;
             const float gd = sG[warp][q >> 2];
             const float4 y4 = *reinterpret_cast<const float4*>(&sY[warp][g * kYStride + k0]);
@@ -534,7 +547,7 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
             }
             __stcs(out4 + q, o);
         }
-    } else if (valid) {
+    } else if (write_row) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             float* o = dL_dsh + (i * 3 + ch) * vp.C;
@@ -658,7 +671,7 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
                                float* dL_drotations, float* dL_dscales, float* dL_dopacities,
                                float* dL_dsh_coeffs, float* grad_accum, float* grad_count,
                                float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out,
-                               bool accumulate, int32_t* touch_mask) {
+                               bool accumulate, int32_t* touch_mask, bool sparse_rows) {
     const ViewParams vp = make_view_params(v);
     const unsigned grid = (unsigned)((n + kPreBlock - 1) / kPreBlock);
     if (v->num_coeffs == 16)
@@ -666,13 +679,15 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
             n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
             dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
             dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
-            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate, touch_mask);
+            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate, touch_mask,
+            sparse_rows && touch_mask != nullptr);
     else
         k_preprocess_bwd<false><<<grid, kPreBlock, 0, s>>>(
             n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
             dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
             dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
-            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate, touch_mask);
+            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate, touch_mask,
+            sparse_rows && touch_mask != nullptr);
     CUGS_LAUNCH_CHECK(h, "k_preprocess_bwd");
     return CUGS_OK;
 }
@@ -704,7 +719,7 @@ extern "C" int cugs_b200_preprocess_bwd(cugs_handle_t* h, void* stream, int64_t 
                                       opacities, sh_coeffs, radii, rgb, dL_dmeans_2d, dL_dcov_2d_inv,
                                       dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
                                       dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
-                                      nullptr, nullptr, false, nullptr);
+                                      nullptr, nullptr, false, nullptr, false);
 }
 
 extern "C" int cugs_b200_sh_forward(cugs_handle_t* h, void* stream, int64_t n, int degree,

@@ -537,12 +537,15 @@ def render(model: GaussianModel, camera: CameraInfo, settings: RenderSettings,
 def render_backward(dL_dcolor: torch.Tensor, render_out: RenderOutput, model: GaussianModel,
                     camera: CameraInfo, settings: RenderSettings, buffers: Optional[FrameBuffers] = None,
                     stats: Optional[Sequence[torch.Tensor]] = None, accumulate: bool = False,
-                    touch_mask: Optional[torch.Tensor] = None) -> BackwardOutput:
+                    touch_mask: Optional[torch.Tensor] = None, sparse_rows: bool = False) -> BackwardOutput:
     """rasterizer.hpp:88-93 / rasterizer.cpp:115-186. ``stats`` = (grad_accum, grad_count,
     max_radii) fuses DensificationController::accumulate_gradients into the same launch;
     ``accumulate`` adds the parameter gradients to ``buffers`` instead of overwriting them
     (gradient of a batch of views); ``touch_mask`` ([N] int32) records which Gaussians received a
-    non-zero gradient (input of the sparse gradient exchange, parallel.sparse_allreduce_step)."""
+    non-zero gradient (input of the sparse gradient exchange, parallel.sparse_allreduce_step);
+    ``sparse_rows`` additionally skips the gradient rows that are not touched, relying on the invariant
+    that rows with mask 0 are zero (FrameBuffers allocates zeros; use the buffers' own touch_mask and
+    do not write the gradient tensors by other means in between)."""
     _check(dL_dcolor.is_cuda, "dL_dcolor must be on CUDA device")
     _check(dL_dcolor.dim() == 3 and dL_dcolor.shape[2] == 3, "dL_dcolor must be [H, W, 3]")
     dev = dL_dcolor.device
@@ -567,10 +570,13 @@ def render_backward(dL_dcolor: torch.Tensor, render_out: RenderOutput, model: Ga
              torch.empty((n, 1), **f), torch.empty_like(sh), torch.empty((n, 2), **f))
     sp = [None, None, None] if stats is None else [_ptr(t) for t in stats]
     r = render_out
+    _check(not sparse_rows or (touch_mask is not None and buffers is not None),
+           "sparse_rows=True needs persistent FrameBuffers and their touch_mask")
+    flags = (1 if accumulate else 0) | (2 if sparse_rows else 0)  # CUGS_BWD_ACCUMULATE | CUGS_BWD_SPARSE_ROWS
     st = lib.cugs_b200_render_backward(
         h, _stream(dev), n, C.byref(v), _ptr(pos), _ptr(rot), _ptr(scl), _ptr(opa), _ptr(sh), _ptr(r.means_2d),
         _ptr(r.cov_2d_inv), _ptr(r.radii), _ptr(r.rgb), _ptr(r.opacities_act), _ptr(r.gaussian_indices),
         _ptr(r.tile_ranges), _ptr(r.final_T), _ptr(r.n_contrib), _ptr(dL_dcolor.contiguous()),
-        *[_ptr(t) for t in g], *sp, _ptr(touch_mask), int(bool(accumulate)), _ptr(ws), ws.numel())
+        *[_ptr(t) for t in g], *sp, _ptr(touch_mask), flags, _ptr(ws), ws.numel())
     _lib.check(h, st, "cugs_b200_render_backward")
     return BackwardOutput(*g)

@@ -317,7 +317,7 @@ class SyntheticTrainer:
             out = render(self.model, cam, settings, b)                   # :211
             scalars, dL = combined_loss_with_grad(out.color, target, cfg.lambda_ssim)  # :214-225 in one pass
             render_backward(dL, out, self.model, cam, settings, b, stats=stats, accumulate=(k > 0),
-                            touch_mask=b.touch_mask if multi else None)  # :228, :269
+                            touch_mask=b.touch_mask, sparse_rows=True)  # :228, :269
             scal_sum = scalars if scal_sum is None else scal_sum + scalars
         if multi:
             self.last_exchange = sparse_allreduce_step(b, with_stats=densify)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CUGS_B200_ABI_VERSION 4 /* bump on ANY signature change: callers compare it with cugs_b200_abi_version() */
+#define CUGS_B200_ABI_VERSION 5 /* bump on ANY signature change: callers compare it with cugs_b200_abi_version() */
 #define CUGS_TILE 16 /* rasterizer/sorting.hpp:16 kTileSize */
 
 enum {
@@ -162,9 +162,14 @@ int cugs_b200_preprocess_bwd(cugs_handle_t* h, void* stream, int64_t n, const cu
  * entries. workspace: cugs_b200_render_workspace_bytes(n, p_capacity) bytes; the SAME workspace
  * must be passed to plan, finish and render_backward of one frame (it carries the packed
  * records). render_backward = blend_bwd + preprocess_bwd (rasterizer/rasterizer.cpp:115-186).
- * accumulate = 0: the five parameter gradients are overwritten (reference behaviour);
- * accumulate = 1: they are added to what the buffers hold (view-batched training: the gradient
- * of a batch of views is summed in place, no separate axpy pass). dL_dmeans_2d is always
+ * flags = 0: the five parameter gradients are overwritten (reference behaviour);
+ * flags & CUGS_BWD_ACCUMULATE: they are added to what the buffers hold (view-batched training: the
+ * gradient of a batch of views is summed in place, no separate axpy pass).
+ * flags & CUGS_BWD_SPARSE_ROWS (needs touch_mask): the caller guarantees that every gradient row
+ * whose touch_mask entry is 0 on entry is all zero (buffers allocated with zeros and only ever
+ * written by this call / cugs_b200_scatter_grad_rows with the matching mask); rows that are not
+ * touched are then neither read nor written (overwrite mode still zeroes rows touched before).
+ * dL_dmeans_2d is always
  * overwritten (it is a per-view quantity, optimizer/densification.cpp:77).
  * touch_mask (optional, [N] i32): 1 where this view gave the Gaussian a non-zero 2-D gradient, else
  * 0 (OR-ed into the previous content when accumulate = 1). Rows with mask 0 have all-zero parameter
@@ -192,7 +197,7 @@ int cugs_b200_render_backward(cugs_handle_t* h, void* stream, int64_t n, const c
                               const float* dL_dcolor, float* dL_dpositions, float* dL_drotations,
                               float* dL_dscales, float* dL_dopacities, float* dL_dsh_coeffs,
                               float* dL_dmeans_2d, float* grad_accum, float* grad_count,
-                              float* max_radii, int32_t* touch_mask, int accumulate, void* workspace,
+                              float* max_radii, int32_t* touch_mask, int flags, void* workspace,
                               size_t workspace_bytes);
 
 /* Optional per-stage device timing of the three fused entry points above: when enabled, CUDA
@@ -202,6 +207,8 @@ int cugs_b200_render_backward(cugs_handle_t* h, void* stream, int64_t n, const c
  * preprocess_bwd} of the most recent frame (-1 for a stage that did not run). */
 /* Sort plan of the most recent render_finish: number of onesweep passes and sorted key bits. */
 int cugs_b200_last_sort_plan(const cugs_handle_t* h, int* passes, int* key_bits);
+#define CUGS_BWD_ACCUMULATE 1
+#define CUGS_BWD_SPARSE_ROWS 2
 #define CUGS_NUM_STAGES 8
 int cugs_b200_set_stage_timing(cugs_handle_t* h, int enable);
 int cugs_b200_get_stage_ms(cugs_handle_t* h, float* ms8);

@@ -724,3 +724,27 @@ def test_mcmc_noise_matches_reference_formula_and_is_replicable(ref, torch):
     fac = lr * torch.exp(r.scales) * gate
     zr = ((r.positions - rp0) / fac)[(fac > 1e-3 * fac.max()).all(dim=1)].double()
     assert abs(float(zr.mean())) < 0.02 and abs(float(zr.std()) - 1.0) < 0.02
+
+
+def test_sparse_gradient_rows_equal_dense_over_several_steps(torch):
+    """CUGS_BWD_SPARSE_ROWS: skipping untouched rows must give bit-identical gradient arenas to the
+    dense path, step after step, with changing cameras (rows touched in one step and not in the next
+    must be zeroed) and two accumulated views per step."""
+    scene = cugs.synth(40_003, 480, 270, seed=43)
+    m = to_torch(scene)
+    settings = cugs.RenderSettings((0, 0, 0), 3, 1.0)
+    cams = [scene.camera] + cugs.ring_cameras(scene, 5, radius_frac=0.3)
+    bs = cugs.FrameBuffers(scene.n, 480, 270, 16, "cuda")
+    bd = cugs.FrameBuffers(scene.n, 480, 270, 16, "cuda")
+    for step in range(3):
+        for k in range(2):
+            cam = cams[2 * step + k]
+            g = _dL(torch, scene, 100 + 2 * step + k)
+            out = cugs.render(m, cam, settings, bs)
+            cugs.render_backward(g, out, m, cam, settings, bs, accumulate=(k > 0), touch_mask=bs.touch_mask,
+                                 sparse_rows=True)
+            out = cugs.render(m, cam, settings, bd)
+            cugs.render_backward(g, out, m, cam, settings, bd, accumulate=(k > 0))
+        assert torch.equal(bs.grad_arena.view(torch.int32), bd.grad_arena.view(torch.int32)), f"step {step}"
+        frac = float(bs.touch_mask.float().mean())
+        assert 0.0 < frac < 0.9

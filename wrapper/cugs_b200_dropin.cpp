@@ -217,7 +217,7 @@ BackwardOutput render_backward(const torch::Tensor& dL_dcolor, const RenderOutpu
                          ip(r.radii), fp(r.rgb), fp(r.opacities_act), ip(r.gaussian_indices), ip(r.tile_ranges),
                          fp(r.final_T), ip(r.n_contrib), fp(dL), fp(g.dL_dpositions), fp(g.dL_drotations),
                          fp(g.dL_dscales), fp(g.dL_dopacities), fp(g.dL_dsh_coeffs), fp(g.dL_dmeans_2d), nullptr, nullptr,
-                         nullptr, /*touch_mask=*/nullptr, /*accumulate=*/0, ws.data_ptr(), (size_t)ws.numel()));
+                         nullptr, /*touch_mask=*/nullptr, /*flags=*/0, ws.data_ptr(), (size_t)ws.numel()));
         return g;
     }
     // a RenderOutput assembled by the caller: go through the two stage functions (rasterizer.cpp:146-176)
