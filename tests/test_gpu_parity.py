@@ -727,9 +727,10 @@ def test_mcmc_noise_matches_reference_formula_and_is_replicable(ref, torch):
 
 
 def test_sparse_gradient_rows_equal_dense_over_several_steps(torch):
-    """CUGS_BWD_SPARSE_ROWS: skipping untouched rows must give bit-identical gradient arenas to the
-    dense path, step after step, with changing cameras (rows touched in one step and not in the next
-    must be zeroed) and two accumulated views per step."""
+    """CUGS_BWD_SPARSE_ROWS: skipping untouched rows must give the same gradient arena as the dense
+    path, step after step, with changing cameras (rows touched in one step and not in the next must be
+    zeroed) and two accumulated views per step. The two paths run blend_bwd separately, whose float
+    reductions are order-dependent, so touched rows agree to rounding and untouched rows are exactly 0."""
     scene = cugs.synth(40_003, 480, 270, seed=43)
     m = to_torch(scene)
     settings = cugs.RenderSettings((0, 0, 0), 3, 1.0)
@@ -745,6 +746,13 @@ def test_sparse_gradient_rows_equal_dense_over_several_steps(torch):
                                  sparse_rows=True)
             out = cugs.render(m, cam, settings, bd)
             cugs.render_backward(g, out, m, cam, settings, bd, accumulate=(k > 0))
-        assert torch.equal(bs.grad_arena.view(torch.int32), bd.grad_arena.view(torch.int32)), f"step {step}"
-        frac = float(bs.touch_mask.float().mean())
+        rows = lambda b: torch.cat([b.dL_dpositions, b.dL_dsh_coeffs.reshape(scene.n, -1), b.dL_dopacities,
+                                    b.dL_dscales, b.dL_drotations], dim=1)
+        rs, rd = rows(bs), rows(bd)
+        mask = bs.touch_mask.bool()
+        assert float(rs[~mask].abs().max()) == 0.0 and float(rd[~mask].abs().max()) == 0.0, f"step {step}"
+        scale = float(rd.abs().max())
+        assert float((rs - rd).abs().max()) <= 1e-4 * scale, f"step {step}"
+        assert float((rs - rd).double().norm() / rd.double().norm()) <= 1e-5
+        frac = float(mask.float().mean())
         assert 0.0 < frac < 0.9
