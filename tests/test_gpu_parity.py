@@ -63,6 +63,9 @@ def scenes():
         "deg2_c16": (cugs.synth(4000, 256, 192, seed=16, num_coeffs=16), 2),  # allocated 16, active 9
         "dense_big_splats": (cugs.synth(3000, 160, 120, seed=17, sigma_px=12.0), 3),  # saturating pixels
         "config_A": (cugs.synth(100_000, 1280, 720, seed=1235), 3),
+        "giant_splats": (cugs.synth(300, 256, 192, seed=18, sigma_px=150.0), 3),   # radius cap, every tile, long lists
+        "tiny_image": (cugs.synth(500, 17, 9, seed=19, sigma_px=1.0), 2),          # one partial tile row
+        "deg1_c16": (cugs.synth(3000, 200, 150, seed=20, num_coeffs=16), 1),       # active degree < allocated
     }
 
 
@@ -76,7 +79,8 @@ def get_scene(name):
     return SCENES[name]
 
 
-NAMES = ["small", "ragged", "adversarial", "deg0_c1", "deg1_c4", "deg2_c16", "dense_big_splats", "config_A"]
+NAMES = ["small", "ragged", "adversarial", "deg0_c1", "deg1_c4", "deg2_c16", "dense_big_splats", "config_A",
+         "giant_splats", "tiny_image", "deg1_c16"]
 
 
 def ref_render(ref, torch, scene, deg, bg=(0.0, 0.0, 0.0), scale_mod=1.0, camera=None):
@@ -307,6 +311,48 @@ def test_render_backward_vs_cpu_oracle(oracle, torch, name):
     for nm in ["dL_dpositions", "dL_drotations", "dL_dscales", "dL_dopacities", "dL_dsh_coeffs", "dL_dmeans_2d"]:
         ok, msg = grad_close(np_(getattr(b, nm)), ob[nm], rel=2e-3)  # CPU expf / summation order
         assert ok, f"{nm}: {msg}"
+
+
+def test_render_with_scale_modifier_background_and_ring_camera_vs_reference(ref, torch):
+    """RenderSettings.scale_modifier != 1, a non-black background (it enters the backward through
+    S_after = T * bg, backward.cu:75-77) and a rotated / translated camera, through render()."""
+    scene, deg = get_scene("small")
+    cam = cugs.ring_cameras(scene, 4, radius_frac=0.25)[2]
+    bg = (0.9, 0.1, 0.4)
+    for sm in (0.6, 1.7):
+        m = to_torch(scene)
+        r = ref.render(m.positions, m.sh_coeffs, m.opacities, m.rotations, m.scales, cam.as_ref_list(), list(bg), deg, sm)
+        st = cugs.RenderSettings(bg, deg, sm)
+        out = cugs.render(m, cam, st)
+        assert torch.equal(out.radii, r[6]) and torch.equal(out.gaussian_indices, r[9]) and torch.equal(out.tile_ranges, r[10])
+        assert torch.equal(out.n_contrib, r[2]) and float((out.color - r[0]).abs().max()) <= IMG_TOL
+        g = _dL(torch, scene, 9)
+        rb = ref.render_backward(g, r, m.positions, m.sh_coeffs, m.opacities, m.rotations, m.scales, cam.as_ref_list(),
+                                 list(bg), deg, sm)
+        b = cugs.render_backward(g, out, m, cam, st)
+        for nm, rt in zip(["dL_dpositions", "dL_drotations", "dL_dscales", "dL_dopacities", "dL_dsh_coeffs", "dL_dmeans_2d"], rb):
+            ok, msg = grad_close(np_(getattr(b, nm)), np_(rt))
+            assert ok, f"scale_mod {sm} {nm}: {msg}"
+
+
+def test_all_culled_scene_backward_is_zero_and_p_is_zero(ref, torch):
+    f = np.float32
+    cam = CameraInfo(80, 60, 100.0, 100.0, 40.0, 30.0)
+    n = 100
+    rng = np.random.default_rng(3)
+    pos = rng.normal(size=(n, 3)).astype(f)
+    pos[:, 2] = -np.abs(pos[:, 2]) - 1.0          # everything behind the camera
+    s = Scene(pos, rng.normal(size=(n, 3, 4)).astype(f), np.zeros((n, 1), f), rng.normal(size=(n, 4)).astype(f),
+              np.full((n, 3), -2.0, f), cam)
+    m = to_torch(s)
+    st = cugs.RenderSettings((0.2, 0.3, 0.4), 1, 1.0)
+    out = cugs.render(m, cam, st)
+    r = ref.render(m.positions, m.sh_coeffs, m.opacities, m.rotations, m.scales, cam.as_ref_list(), [0.2, 0.3, 0.4], 1, 1.0)
+    assert out.gaussian_indices.numel() == 0 == r[9].numel()
+    assert torch.equal(out.color, r[0]) and torch.equal(out.final_T, r[1]) and torch.equal(out.n_contrib, r[2])
+    b = cugs.render_backward(_dL(torch, s), out, m, cam, st)
+    for nm in ["dL_dpositions", "dL_drotations", "dL_dscales", "dL_dopacities", "dL_dsh_coeffs", "dL_dmeans_2d"]:
+        assert float(getattr(b, nm).abs().sum()) == 0.0
 
 
 def test_culled_gaussian_has_exactly_zero_gradients(torch):  # test_backward.cpp:181-201
