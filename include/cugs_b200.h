@@ -16,6 +16,16 @@
  *                                                                    (rasterizer/sorting.hpp:19-24)
  *   color [H,W,3], final_T [H,W], n_contrib [H,W] i32                (rasterizer/forward.hpp:11-15)
  *   all f32 unless noted, contiguous, row-major, 16-byte aligned base pointers.
+ *
+ * Threading / streams: a handle belongs to one device and is NOT thread-safe (it owns the pinned
+ * word through which render_plan returns P, the error string and the optional stage-timing
+ * events); use one handle per host thread. Every kernel is launched on the stream passed in; the
+ * only blocking calls are cugs_b200_render_plan and cugs_b200_scan with total_host != NULL (one
+ * cudaStreamSynchronize each, the read the reference does at rasterizer/sorting.cu:146) and
+ * cugs_b200_get_stage_ms. Two frames may be in flight on two streams through one handle as long as
+ * each frame's render_finish is called before the next frame's render_plan (bench.py does this).
+ * Limits: P < 2^30 pairs, N < 2^31 Gaussians, at most 48 K tiles (7680x4096) on the fused path
+ * (CUGS_ERR_UNSUPPORTED otherwise); the stage functions have no tile limit.
  */
 #ifndef CUGS_B200_H_
 #define CUGS_B200_H_
