@@ -150,7 +150,7 @@ def sort_passes(P_bits_depth: int, num_tiles: int) -> int:
     return max(1, (P_bits_depth + tb + 7) // 8)
 
 
-def algorithmic_bytes(n: int, p: int, w: int, h: int, tile_passes: int, views: int = 1) -> dict:
+def algorithmic_bytes(n: int, p: int, w: int, h: int, tile_passes: int, views: int = 1, touched=None) -> dict:
     """ALGORITHMIC bytes per frame of each stage: each distinct input read once +
     each output written once, for the kernels as designed (depth passes hoisted before the key
     duplication: the sort moves 8-byte packed elements)."""
@@ -163,8 +163,12 @@ def algorithmic_bytes(n: int, p: int, w: int, h: int, tile_passes: int, views: i
         "tile_ranges": 0,                            # part of the sort (tile histogram -> ranges)
         "blend_fwd": 52 * p + 20 * w * h,            # index (4) + packed record (48) per pair, 20 B per pixel
         "blend_bwd": 52 * p + 20 * w * h + 48 * n,   # + dL/dcolor, final_T, n_contrib per pixel, 48-B gradient record
-        # 336 B/Gaussian; views after the first of a step also READ the 236-B gradient row they add to
-        "preprocess_bwd": int((336 + 236 * (views - 1) / max(views, 1)) * n),
+        # dense: 336 B/Gaussian, views after the first of a step also READ the 236-B gradient row they
+        # add to. Sparse rows (touched = fraction of Gaussians with a gradient): 120 B/Gaussian of inputs,
+        # mask and dL/dmeans_2d, plus the 236-B row written (first view) or read+written (later views)
+        # for the touched fraction only.
+        "preprocess_bwd": int(((336 + 236 * (views - 1) / max(views, 1)) if touched is None else
+                               (120 + 236 * touched * (2 * views - 1) / max(views, 1))) * n),
     }
 
 
@@ -380,7 +384,8 @@ def run_b200(args) -> dict:
         c_passes, c_bits = C.c_int(0), C.c_int(0)
         lib.cugs_b200_last_sort_plan(h, C.byref(c_passes), C.byref(c_bits))
         passes, key_bits = int(c_passes.value), int(c_bits.value)
-        alg = algorithmic_bytes(n, P, W, H, max(passes - 4, 1), V)
+        touched_frac = float(buf.touch_mask.float().mean()) if touch is not None else None
+        alg = algorithmic_bytes(n, P, W, H, max(passes - 4, 1), V, touched_frac)
         peak, peak_src = measured_peaks()
         hbm_stages = ["preprocess_fwd", "scan", "duplicate_with_keys", "sort", "preprocess_bwd"]
         rl_all = {}
@@ -414,7 +419,7 @@ def run_b200(args) -> dict:
                            "one NCCL all-reduce(sum) of the 61N-float arena per step" if args.dense_allreduce else
                            "per step: int32 MAX all-reduce of the touch mask (8 B/Gaussian) + ONE all-reduce(sum) of the "
                            "touched gradient rows"),
-                       "gradient_exchange": exchange,
+                       "gradient_exchange": exchange, "touched_fraction": touched_frac,
                        "l2": "no flush needed: per-step inputs (708 MB of Gaussian parameters at 3M) exceed the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "ms_per_view": round(e2e_ms / args.steps / V, 4),
