@@ -4,11 +4,18 @@
  * cpu_baseline / --impl reference legs may load this library. The product
  * (cuda_gaussian_splatting_b200/) never links or calls it and has no CPU fallback.
  *
- * Parity status: the reference ships no golden files; this oracle is pinned
- * against (a) the known-answer tests of the reference's own test-suite, ported in
- * tests/test_oracle_known_answers.py, and (b) golden vectors produced by the UNMODIFIED
- * reference kernels (oracle/_ref, built by oracle/Makefile.ref) on a B200 and committed under
- * tests/golden/ by tests/golden/make_golden.py.
+ * Parity status: PINNED. The reference ships no golden files; this oracle is
+ * checked, in the CPU-only suite, against
+ *  (a) the known-answer tests of the reference's own test-suite, ported one by one in
+ *      tests/test_oracle_known_answers.py;
+ *  (b) tests/golden/ref_gpu_golden.npz: stage outputs, images, gradients, loss and three
+ *      FusedAdam steps of the UNMODIFIED reference CUDA kernels (oracle/_ref, built from
+ *      /root/reference by oracle/Makefile.ref) recorded on a B200 by
+ *      tests/golden/make_golden_gpu.py -- tests/test_oracle_vs_reference_golden.py: radii, tile
+ *      counts, sorted keys, sort order, tile ranges, n_contrib and Adam bit-exact, floats <= 2e-6;
+ *  (c) tests/golden/sh_cpu_golden.npz (the reference's evaluate_sh_cpu, make_golden_cpu.py) and
+ *      the PLY files written by the reference (make_golden_ply.py);
+ * and, on the GPU box, against oracle/_ref live (tests/test_gpu_parity.py).
  *
  * Every function cites the reference file:line (relative to /root/reference/src) it restates.
  * Build: gcc -O2 -ffp-contract=off -fopenmp (see oracle/Makefile). -ffp-contract=off matters:
