@@ -10,7 +10,7 @@ from .rasterizer import (  # noqa: F401
     BackwardOutput, CameraInfo, ForwardOutput, FrameBuffers, GaussianModel, ProjectionBackwardOutput,
     ProjectionOutput, RasterizeBackwardOutput, RenderOutput, RenderSettings, SortingOutput,
     evaluate_sh_backward_cuda, evaluate_sh_cuda, project_backward, project_gaussians, rasterize_backward,
-    rasterize_forward, render, render_backward, sort_gaussians,
+    rasterize_forward, render, render_backward, render_image, ImageBuffers, sort_gaussians,
 )
 from .training import (  # noqa: F401
     AdamConfig, DensificationStats, FusedAdam, MCMCConfig, PositionLRConfig, mcmc_inject_noise, mcmc_noise_lr, SyntheticTrainer, TargetUploader, TrainConfig, active_sh_degree_for_step, combined_loss,
@@ -18,6 +18,10 @@ from .training import (  # noqa: F401
 )
 from .synth import Scene, default_camera, ring_cameras, synth  # noqa: F401
 from .ply_io import read_gaussian_ply, write_gaussian_ply  # noqa: F401
+from .density import (  # noqa: F401
+    DensificationConfig, DensificationController, DensificationResult, MCMCStats, mcmc_relocate,
+    mcmc_should_relocate,
+)
 from .parallel import (  # noqa: F401
     allreduce_step, arena_layout, fold_step_stats, grad_scale_for, shard_views, sparse_allreduce_step,
 )

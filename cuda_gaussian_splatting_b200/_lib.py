@@ -32,6 +32,17 @@ class CugsView(C.Structure):
     ]
 
 
+class CugsDensifyConfig(C.Structure):  # cugs_densify_config_t
+    _fields_ = [
+        ("grad_threshold", C.c_float),
+        ("size_threshold", C.c_float),
+        ("opacity_threshold", C.c_float),
+        ("apply_size_pruning", C.c_int32),
+        ("max_screen_size", C.c_float),
+        ("ws_threshold", C.c_float),
+    ]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _SZ = C.c_size_t
@@ -77,6 +88,14 @@ SIGNATURES = {
                                          C.POINTER(_I64), C.POINTER(_F), _F, _F, _F, _F, _F, _F, _F, _F]),
     "cugs_b200_mcmc_inject_noise": (_INT, [_P, _P, _I64, _P, _P, _P, _F, _F, _F, C.c_uint64, C.c_uint32, _P]),
     "cugs_b200_accumulate_stats": (_INT, [_P, _P, _I64, _P, _P, _P, _P, _P]),
+    "cugs_b200_densify_temp_bytes": (_SZ, [_I64]),
+    "cugs_b200_densify_classify": (_INT, [_P, _P, _I64, _P, _P, _P, _P, _P, C.POINTER(CugsDensifyConfig), _P,
+                                           C.POINTER(_I64), _P, _SZ]),
+    "cugs_b200_densify_apply": (_INT, [_P, _P, _I64, _I64, _INT, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
+                                        C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.c_uint64, _P, _P, _SZ]),
+    "cugs_b200_mcmc_relocate_temp_bytes": (_SZ, [_I64]),
+    "cugs_b200_mcmc_relocate": (_INT, [_P, _P, _I64, _INT, _P, _P, _P, _P, _P, _F, _I64, _F, C.c_uint64, C.c_uint32,
+                                        _P, _P, C.POINTER(_I64), _P, _SZ]),
 }
 
 _lib = None

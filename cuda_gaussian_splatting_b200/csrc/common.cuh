@@ -207,4 +207,40 @@ inline ViewParams make_view_params(const cugs_view_t* v) {
     return p;
 }
 
+// ---- counter-based random numbers (MCMC noise, split / relocation jitter) ----------------------
+// Philox-4x32-10; the caller chooses key = seed and a counter that names the draw (Gaussian index,
+// step, purpose), so results do not depend on the launch shape and every rank of a view-parallel
+// run draws the same numbers.
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
+                                              unsigned k1, unsigned (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// three standard normals (Box-Muller on 24-bit uniforms in (0,1)) and one spare uniform
+__device__ __forceinline__ void philox_normal3(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
+                                               unsigned k1, float& z0, float& z1, float& z2,
+                                               float* spare_uniform = nullptr) {
+    unsigned r[4];
+    philox4x32_10(c0, c1, c2, c3, k0, k1, r);
+    const float u0 = ((float)(r[0] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float u1 = ((float)(r[1] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float u2 = ((float)(r[2] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float u3 = ((float)(r[3] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+    float s0, cs0, s1, cs1;
+    sincospif(2.0f * u1, &s0, &cs0);
+    sincospif(2.0f * u3, &s1, &cs1);
+    z0 = ra * cs0; z1 = ra * s0; z2 = rb * cs1;
+    if (spare_uniform) *spare_uniform = u3;
+}
+
 }  // namespace cugs

@@ -210,13 +210,15 @@ k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
             }
         }
         reinterpret_cast<float2*>(means_2d)[i] = make_float2(o_x, o_y);
-        depths[i] = o_depth;
-        cov_2d_inv[i * 3 + 0] = o_a;
-        cov_2d_inv[i * 3 + 1] = o_b;
-        cov_2d_inv[i * 3 + 2] = o_c;
+        if (depths != nullptr) {  // null on a render-only frame (the packed record carries what the blend needs)
+            depths[i] = o_depth;
+            cov_2d_inv[i * 3 + 0] = o_a;
+            cov_2d_inv[i * 3 + 1] = o_b;
+            cov_2d_inv[i * 3 + 2] = o_c;
+            opa_act[i] = o_op;
+        }
         radii[i] = o_radius;
         tiles_touched[i] = o_tiles;
-        opa_act[i] = o_op;
         // element of the depth sort (tile_binning.cu): depth bits << 32 | index; key 0 for the
         // filler entries of quirk A.2, 0xffffffff (sorts last) when the Gaussian emits no pair
         if (gsort != nullptr) {
@@ -266,7 +268,7 @@ k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                 const float col = fmaxf(v + 0.5f, 0.0f);  // +0.5 (sh.cu:77), clamp_min(0) (projection.cu:284)
                 const int o = q >> 2;                     // = g*3 + channel
                 sRGB[warp][o] = col;
-                if (q < lim) rgb[g0 * 3 + o] = col;
+                if (q < lim && rgb != nullptr) rgb[g0 * 3 + o] = col;
             }
         }
         __syncwarp();
@@ -283,7 +285,7 @@ k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                 float acc = 0.0f;
                 for (int k = 0; k < na; ++k) acc += c[k] * Y[k];
                 col[ch] = fmaxf(acc + 0.5f, 0.0f);
-                rgb[i * 3 + ch] = col[ch];
+                if (rgb != nullptr) rgb[i * 3 + ch] = col[ch];
             }
         }
         c_r = col[0]; c_g = col[1]; c_b = col[2];
@@ -630,6 +632,8 @@ extern "C" int cugs_b200_preprocess_fwd(cugs_handle_t* h, void* stream, int64_t 
                                         float* means_2d, float* depths, float* cov_2d_inv,
                                         int32_t* radii, int32_t* tiles_touched, float* rgb,
                                         float* opacities_act, float* packed, uint32_t* depth_minmax) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    CUGS_REQUIRE(h, n == 0 || (depths && cov_2d_inv && rgb && opacities_act), "null output");
     return cugs_preprocess_fwd_launch(h, stream, n, v, positions, rotations, scales, opacities, sh_coeffs, means_2d,
                                       depths, cov_2d_inv, radii, tiles_touched, rgb, opacities_act, packed,
                                       depth_minmax, nullptr);
@@ -645,8 +649,11 @@ int cugs_preprocess_fwd_launch(cugs_handle_t* h, void* stream, int64_t n, const 
     if (int e = check_view(h, v)) return e;
     if (n == 0) return CUGS_OK;
     CUGS_REQUIRE(h, positions && rotations && scales && opacities && sh_coeffs, "null input");
-    CUGS_REQUIRE(h, means_2d && depths && cov_2d_inv && radii && tiles_touched && rgb && opacities_act,
-                 "null output");
+    CUGS_REQUIRE(h, means_2d && radii && tiles_touched, "null output");
+    // render-only frames (cugs_b200_render_plan): the four backward-only arrays are all null
+    const bool all = depths && cov_2d_inv && rgb && opacities_act;
+    const bool none = !depths && !cov_2d_inv && !rgb && !opacities_act;
+    CUGS_REQUIRE(h, all || (none && packed != nullptr), "null output");
     const ViewParams vp = make_view_params(v);
     const unsigned grid = (unsigned)((n + kPreBlock - 1) / kPreBlock);
     cudaStream_t s = (cudaStream_t)stream;

@@ -302,39 +302,14 @@ k_adam_multi(AdamGroups G, int64_t total_chunks, float b1, float b2, float eps, 
 // Philox-4x32-10 keyed by (seed) with counter (Gaussian index, step), so every rank of a
 // view-parallel run draws the same noise and the replicas stay bit-identical.
 // ================================================================================================
-__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
-                                              unsigned k1, unsigned (&out)[4]) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
 __global__ void __launch_bounds__(256)
 k_mcmc_noise(int64_t n, float* __restrict__ positions, const float* __restrict__ scales,
              const float* __restrict__ opacities, float noise_lr, float gate_k, float gate_t, unsigned seed_lo,
              unsigned seed_hi, unsigned step, float* __restrict__ normals_out /* optional [N,3] */) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    unsigned r[4];
-    philox4x32_10((unsigned)i, (unsigned)((uint64_t)i >> 32), step, 0x3c6ef372u, seed_lo, seed_hi, r);
-    // uniforms in (0, 1): 24 random bits + 0.5
-    const float u0 = ((float)(r[0] >> 8) + 0.5f) * 5.9604644775390625e-08f;
-    const float u1 = ((float)(r[1] >> 8) + 0.5f) * 5.9604644775390625e-08f;
-    const float u2 = ((float)(r[2] >> 8) + 0.5f) * 5.9604644775390625e-08f;
-    const float u3 = ((float)(r[3] >> 8) + 0.5f) * 5.9604644775390625e-08f;
-    const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
-    float s0, c0, s1, c1;
-    sincospif(2.0f * u1, &s0, &c0);
-    sincospif(2.0f * u3, &s1, &c1);
-    const float z0 = ra * c0, z1 = ra * s0, z2 = rb * c1;
-    (void)s1;
+    float z0, z1, z2;
+    philox_normal3((unsigned)i, (unsigned)((uint64_t)i >> 32), step, 0x3c6ef372u, seed_lo, seed_hi, z0, z1, z2);
     const float sg = 1.0f / (1.0f + expf(-opacities[i]));
     const float gate = 1.0f / (1.0f + expf(gate_k * (sg - gate_t)));  // sigmoid(-k (sg - t))
     const float f = noise_lr * gate;

@@ -534,6 +534,63 @@ def render(model: GaussianModel, camera: CameraInfo, settings: RenderSettings,
                         b.opacities_act, b.gaussian_indices[:P], b.tile_ranges, _workspace=b.workspace)
 
 
+class ImageBuffers:
+    """Device buffers of a render-only frame (no backward-only arrays): what render_image reuses."""
+
+    def __init__(self, n: int, width: int, height: int, device):
+        f = dict(dtype=torch.float32, device=device)
+        i = dict(dtype=torch.int32, device=device)
+        self.n, self.width, self.height = n, width, height
+        self.means_2d = torch.empty((n, 2), **f)
+        self.radii = torch.empty((n,), **i)
+        self.color = torch.empty((height, width, 3), **f)
+        self.final_T = torch.empty((height, width), **f)
+        self.n_contrib = torch.empty((height, width), **i)
+        self.tile_ranges = torch.empty((num_tiles(width, height), 2), **i)
+        lib = _lib.load_library()
+        self.workspace = torch.empty((lib.cugs_b200_render_workspace_bytes(n, 0),), dtype=torch.uint8, device=device)
+        self.gaussian_indices = torch.empty((1,), **i)
+        self.p_capacity = 0
+
+    ensure_capacity = FrameBuffers.ensure_capacity
+
+
+def render_image(model: GaussianModel, camera: CameraInfo, settings: RenderSettings,
+                 buffers: Optional[ImageBuffers] = None):
+    """Render-only entry point for the callers that never run the backward pass -- evaluate()
+    (training/metrics.cpp:131) and Viewer::render_frame (viewer/viewer.cpp:645-669) consume only
+    ``color``, ``final_T`` and ``n_contrib``. Same kernels and same pixels as render(); depths,
+    cov_2d_inv, rgb and opacities_act are not materialised. Returns (color, final_T, n_contrib)."""
+    _check(model.is_valid(), "GaussianModel is not valid")
+    _check(model.positions.is_cuda, "GaussianModel must be on CUDA device")
+    n = model.num_gaussians()
+    if n == 0:
+        out = render(model, camera, settings)
+        return out.color, out.final_T, out.n_contrib
+    dev = model.positions.device
+    lib, h = _lib_and_handle(dev)
+    s = _stream(dev)
+    active = min(settings.active_sh_degree, model.max_sh_degree())
+    pos, rot, scl, opa, sh = map(_f32c, (model.positions, model.rotations, model.scales, model.opacities,
+                                         model.sh_coeffs))
+    v = make_view(camera, settings, active, sh.shape[2])
+    b = buffers if buffers is not None else ImageBuffers(n, camera.width, camera.height, dev)
+    _check(b.n == n and b.width == camera.width and b.height == camera.height,
+           "ImageBuffers do not match the model / camera")
+    p = C.c_int64(0)
+    st = lib.cugs_b200_render_plan(h, s, n, C.byref(v), _ptr(pos), _ptr(rot), _ptr(scl), _ptr(opa), _ptr(sh),
+                                   _ptr(b.means_2d), None, None, _ptr(b.radii), None, None, _ptr(b.workspace),
+                                   b.workspace.numel(), C.byref(p))
+    _lib.check(h, st, "cugs_b200_render_plan")
+    P = int(p.value)
+    b.ensure_capacity(P)
+    st = lib.cugs_b200_render_finish(h, s, n, P, C.byref(v), _ptr(b.means_2d), None, None, _ptr(b.radii), None, None,
+                                     b.gaussian_indices.data_ptr(), _ptr(b.tile_ranges), _ptr(b.color),
+                                     _ptr(b.final_T), _ptr(b.n_contrib), _ptr(b.workspace), b.workspace.numel())
+    _lib.check(h, st, "cugs_b200_render_finish")
+    return b.color, b.final_T, b.n_contrib
+
+
 def render_backward(dL_dcolor: torch.Tensor, render_out: RenderOutput, model: GaussianModel,
                     camera: CameraInfo, settings: RenderSettings, buffers: Optional[FrameBuffers] = None,
                     stats: Optional[Sequence[torch.Tensor]] = None, accumulate: bool = False,

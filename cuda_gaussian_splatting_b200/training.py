@@ -124,7 +124,12 @@ class AdamConfig:  # optimizer/adam.hpp:30-41
 
 
 @dataclass
-class MCMCConfig:  # the per-step fields of optimizer/mcmc_densification.hpp:27-51
+class MCMCConfig:  # optimizer/mcmc_densification.hpp:27-51 (without the VRAM guard)
+    relocate_from: int = 500
+    relocate_until: int = 15000
+    relocate_every: int = 100
+    dead_opacity_threshold: float = 0.005
+    relocate_cap: float = 0.05
     noise_lr_init: float = 5e5
     noise_lr_final: float = 1e3
     noise_lr_max_steps: int = 30000
@@ -182,6 +187,26 @@ class FusedAdam:
         self.grad_scale = 1.0
         self.mcmc_lambda_opacity = 0.0  # > 0: MCMC regulariser gradient added inside the launch
         self.mcmc_lambda_scale = 0.0
+
+    def rebind(self, model: GaussianModel, m=None, v=None) -> None:
+        """Point the optimizer at the (resized) tensors of ``model``. Without moments this equals the
+        reference's rebuild after densification (trainer.cpp:281-283: a new FusedAdam, zero moments, step
+        count 0); with ``m``/``v`` (five tensors each, e.g. from cugs_b200_densify_apply) the state and the
+        step count are carried over."""
+        self.model = model
+        self._params = [model.positions, model.sh_coeffs, model.opacities, model.scales, model.rotations]
+        for p in self._params:
+            _check(p.is_cuda and p.is_contiguous() and p.dtype == torch.float32,
+                   "FusedAdam: params must be contiguous f32 CUDA tensors")
+        if m is None or v is None:
+            self.m = [torch.zeros_like(p) for p in self._params]
+            self.v = [torch.zeros_like(p) for p in self._params]
+            self.step_count = 0
+        else:
+            for p, mi, vi in zip(self._params, m, v):
+                _check(mi.shape == p.shape and vi.shape == p.shape, "FusedAdam.rebind: moment shape mismatch")
+            self.m, self.v = list(m), list(v)
+        self.grads = [None] * 5
 
     def apply_gradients(self, grads: BackwardOutput) -> None:  # fused_adam.cu:113-120
         self.grads = [grads.dL_dpositions, grads.dL_dsh_coeffs, grads.dL_dopacities, grads.dL_dscales,
@@ -266,6 +291,11 @@ class TrainConfig:  # the fields of training/trainer.hpp:38-75 that reach the ho
     adam: AdamConfig = field(default_factory=AdamConfig)
     densify: bool = True  # accumulate the ADC statistics every step (trainer.cpp:269)
     mcmc: Optional["MCMCConfig"] = None  # MCMC mode (trainer.cpp:232-237, :246-266): regulariser + noise, no ADC stats
+    # model resizing on schedule (trainer.cpp:253-303); None = fixed N (the measured configurations)
+    densification: Optional[object] = None   # density.DensificationConfig: ADC clone / split / prune + opacity reset
+    mcmc_relocation: bool = False            # MCMC mode: relocate dead Gaussians on the MCMCConfig schedule
+    scene_extent: float = 1.0
+    carry_optimizer_state: bool = False      # False = the reference's optimizer rebuild after densification
 
 
 class SyntheticTrainer:
@@ -290,9 +320,16 @@ class SyntheticTrainer:
         if self.config.mcmc is not None:
             self.optimizer.mcmc_lambda_opacity = self.config.mcmc.lambda_opacity
             self.optimizer.mcmc_lambda_scale = self.config.mcmc.lambda_scale
-        self.stats = DensificationStats(n, model.positions.device)
+        if self.config.densification is not None and self.config.mcmc is None:
+            from .density import DensificationController
+            self.stats = DensificationController(self.config.densification, self.config.scene_extent, n,
+                                                 model.positions.device)
+        else:
+            self.stats = DensificationStats(n, model.positions.device)
         self._RenderSettings = RenderSettings
+        self._FrameBuffers = FrameBuffers
         self.last_scalars = None
+        self.last_density_event = None
 
     def train_step(self, step: int) -> torch.Tensor:
         from .parallel import fold_step_stats, sparse_allreduce_step
@@ -328,8 +365,28 @@ class SyntheticTrainer:
         self.optimizer.apply_gradients(BackwardOutput(b.dL_dpositions, b.dL_drotations, b.dL_dscales,
                                                       b.dL_dopacities, b.dL_dsh_coeffs, b.dL_dmeans_2d))
         self.optimizer.step()
+        self.last_density_event = None
         if cfg.mcmc is not None:  # position noise every iteration, after the optimizer step (trainer.cpp:251)
             mcmc_inject_noise(self.model, step, cfg.mcmc)
+            if cfg.mcmc_relocation:
+                from .density import mcmc_relocate, mcmc_should_relocate
+                if mcmc_should_relocate(step, cfg.mcmc):                 # :254-265; N constant, optimizer untouched
+                    mcmc_relocate(self.model, step, cfg.mcmc, cfg.scene_extent, want_stats=False)
+                    self.last_density_event = "relocate"
+        elif cfg.densification is not None:
+            # every rank holds the same statistics (all-reduced) and draws the same Philox numbers, so the
+            # replicas take identical decisions and stay bit-identical without any extra exchange
+            ctrl = self.stats
+            if ctrl.should_densify(step):                                # :272-296
+                res = ctrl.densify(self.model, step, optimizer=self.optimizer,
+                                   carry_optimizer_state=cfg.carry_optimizer_state)
+                self.last_density_event = res
+                if self.model.num_gaussians() != b.n:
+                    cam0 = self.cameras[0]
+                    self.buffers = self._FrameBuffers(self.model.num_gaussians(), cam0.width, cam0.height,
+                                                      int(self.model.sh_coeffs.shape[2]), self.model.positions.device)
+            if ctrl.should_reset_opacity(step):                          # :299-302
+                ctrl.reset_opacity(self.model)
         self.last_scalars = scal_sum / float(len(self.cameras))
         return self.last_scalars
 

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CUGS_B200_ABI_VERSION 5 /* bump on ANY signature change: callers compare it with cugs_b200_abi_version() */
+#define CUGS_B200_ABI_VERSION 6 /* bump on ANY signature change: callers compare it with cugs_b200_abi_version() */
 #define CUGS_TILE 16 /* rasterizer/sorting.hpp:16 kTileSize */
 
 enum {
@@ -183,7 +183,12 @@ int cugs_b200_preprocess_bwd(cugs_handle_t* h, void* stream, int64_t n, const cu
  * overwritten (it is a per-view quantity, optimizer/densification.cpp:77).
  * touch_mask (optional, [N] i32): 1 where this view gave the Gaussian a non-zero 2-D gradient, else
  * 0 (OR-ed into the previous content when accumulate = 1). Rows with mask 0 have all-zero parameter
- * gradients; the view-parallel gradient exchange below only moves the other rows. */
+ * gradients; the view-parallel gradient exchange below only moves the other rows.
+ * Render-only frames (evaluation / viewer callers, training/metrics.cpp:131, viewer/viewer.cpp:645-669,
+ * which consume color / final_T / n_contrib only): pass NULL for ALL FOUR of depths, cov_2d_inv, rgb
+ * and opacities_act to render_plan and render_finish; those backward-only arrays are then not
+ * written (the blend reads the packed records of the workspace). Such a frame cannot be passed to
+ * render_backward. */
 size_t cugs_b200_render_workspace_bytes(int64_t n, int64_t p_capacity);
 int cugs_b200_render_plan(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
                           const float* positions, const float* rotations, const float* scales,
@@ -262,6 +267,60 @@ int cugs_b200_mcmc_inject_noise(cugs_handle_t* h, void* stream, int64_t n, float
 int cugs_b200_accumulate_stats(cugs_handle_t* h, void* stream, int64_t n,
                                const float* dL_dmeans_2d, const int32_t* radii, float* grad_accum,
                                float* grad_count, float* max_radii);
+
+/* ---- model-resizing steps on a schedule ---------------------------------------
+ * ADC densification, DensificationController::densify (optimizer/densification.cpp:94-329), as two
+ * calls around the host policy:
+ *   densify_classify  one pass over scales / opacities / the three accumulators -> flags[N] (u8, OR of
+ *                     CUGS_DENSIFY_*: the clone mask :351-370, the split mask :372-399, and KEEP = passes
+ *                     compute_keep_mask :401-444; a row with SPLIT is dropped whatever its KEEP bit,
+ *                     :296-303) and the three counts {kept originals, clones, splits} on the host (one sync; the reference has
+ *                     three .item() reads). The caller may clear CLONE / SPLIT bits afterwards (budget caps,
+ *                     :122-139) before calling apply.
+ *   densify_apply     stable stream compaction of the five parameter arrays (Adam group order: positions,
+ *                     sh_coeffs, opacities, scales, rotations) into dst, n_out = kept + clones + 2 * splits
+ *                     rows in the reference's order [kept originals | clones | first children | second
+ *                     children]; children: scale - log(1.6), position + N(0,1) * exp(new scale) (:243-253),
+ *                     normals = Philox-4x32-10(seed; source row, child), optionally returned in
+ *                     split_normals_out [2 * splits, 3]. src_m/src_v/dst_m/dst_v (each NULL or five
+ *                     pointers): Adam moments carried over for kept rows and zeroed for new rows (the
+ *                     reference rebuilds the optimizer, i.e. zeroes all of them: pass src_* = NULL for that).
+ * temp: cugs_b200_densify_temp_bytes(n) bytes of device scratch, the same buffer for both calls. */
+#define CUGS_DENSIFY_KEEP 1
+#define CUGS_DENSIFY_CLONE 2
+#define CUGS_DENSIFY_SPLIT 4
+typedef struct cugs_densify_config {
+    float grad_threshold;     /* DensificationConfig::grad_threshold, densification.hpp:31 */
+    float size_threshold;     /* percent_dense * scene_extent, densification.cpp:366 */
+    float opacity_threshold;  /* densification.hpp:32 */
+    int32_t apply_size_pruning; /* opacity_reset_every > 0 && step > opacity_reset_every, densification.cpp:416-417 */
+    float max_screen_size;    /* (float)max_screen_size; <= 0 disables the screen-size test, :421 */
+    float ws_threshold;       /* 0.1 * scene_extent, :438 */
+} cugs_densify_config_t;
+size_t cugs_b200_densify_temp_bytes(int64_t n);
+int cugs_b200_densify_classify(cugs_handle_t* h, void* stream, int64_t n, const float* scales,
+                               const float* opacities, const float* grad_accum, const float* grad_count,
+                               const float* max_radii, const cugs_densify_config_t* cfg, uint8_t* flags,
+                               int64_t* counts_host, void* temp, size_t temp_bytes);
+int cugs_b200_densify_apply(cugs_handle_t* h, void* stream, int64_t n, int64_t n_out, int num_coeffs,
+                            const uint8_t* flags, const float* const* src, float* const* dst,
+                            const float* const* src_m, const float* const* src_v, float* const* dst_m,
+                            float* const* dst_v, uint64_t seed, float* split_normals_out, void* temp,
+                            size_t temp_bytes);
+/* MCMCController::relocate (optimizer/mcmc_densification.cpp:56-138), in place: the first max_relocate
+ * dead Gaussians (sigmoid(opacity) < dead_threshold, in index order) each take over an alive Gaussian
+ * drawn with probability proportional to sigmoid(opacity) (with replacement): SH and rotation copied,
+ * position + N(0,1) * scene_extent * 0.01, scale - log(10), opacity = logit(0.01). Nothing happens when
+ * there is no dead or no alive Gaussian. Draws are Philox-4x32-10(seed; index, step): identical on every
+ * rank of a view-parallel run. source_out (optional [N] i32): chosen source per Gaussian, -1 = untouched;
+ * normals_out (optional [N,3]); counts_host (optional): {dead, relocated} -- non-NULL makes the call
+ * blocking, as the reference's .item() is. temp: cugs_b200_mcmc_relocate_temp_bytes(n). */
+size_t cugs_b200_mcmc_relocate_temp_bytes(int64_t n);
+int cugs_b200_mcmc_relocate(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs, float* positions,
+                            float* sh_coeffs, float* opacities, float* scales, float* rotations,
+                            float dead_threshold, int64_t max_relocate, float scene_extent, uint64_t seed,
+                            uint32_t step, int32_t* source_out, float* normals_out, int64_t* counts_host,
+                            void* temp, size_t temp_bytes);
 
 /* ---- view-parallel gradient exchange (no reference counterpart: the reference is single-GPU) ----
  * Compaction of the gradient rows of the touched Gaussians around the all-reduce. touch: [N] i32

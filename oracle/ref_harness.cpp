@@ -246,6 +246,45 @@ std::vector<T> ref_accumulate_gradients(const T& dL_dmeans_2d, const T& radii, i
     return {ctrl.grad_accum_, ctrl.grad_count_, ctrl.max_radii_2d_};
 }
 
+// DensificationController::densify (optimizer/densification.cpp:94-329) on given accumulators.
+// cfg = {grad_threshold, opacity_threshold, percent_dense, max_screen_size, max_gaussians, opacity_reset_every}
+// -> {positions, sh_coeffs, opacities, rotations, scales, stats[cloned, split, pruned, before, after]}
+std::vector<T> ref_densify(const T& pos, const T& sh, const T& opa, const T& rot, const T& scl, const T& grad_accum,
+                           const T& grad_count, const T& max_radii, double scene_extent, int step,
+                           const std::vector<double>& cfg) {
+    cugs::DensificationConfig c;
+    c.grad_threshold = static_cast<float>(cfg[0]);
+    c.opacity_threshold = static_cast<float>(cfg[1]);
+    c.percent_dense = static_cast<float>(cfg[2]);
+    c.max_screen_size = static_cast<int>(cfg[3]);
+    c.max_gaussians = static_cast<int>(cfg[4]);
+    c.opacity_reset_every = static_cast<int>(cfg[5]);
+    c.min_vram_headroom_mb = 0.0f;
+    cugs::DensificationController ctrl(c, static_cast<float>(scene_extent));
+    ctrl.grad_accum_ = grad_accum.clone();
+    ctrl.grad_count_ = grad_count.clone();
+    ctrl.max_radii_2d_ = max_radii.clone();
+    auto model = make_model(pos.clone(), sh.clone(), opa.clone(), rot.clone(), scl.clone());
+    const auto st = ctrl.densify(model, step);
+    return {model.positions, model.sh_coeffs, model.opacities, model.rotations, model.scales,
+            torch::tensor({st.num_cloned, st.num_split, st.num_pruned, st.num_before, st.num_after})};
+}
+
+// MCMCController::relocate (optimizer/mcmc_densification.cpp:56-138)
+// -> {positions, sh_coeffs, opacities, rotations, scales, stats[relocated, dead, total]}
+std::vector<T> ref_mcmc_relocate(const T& pos, const T& sh, const T& opa, const T& rot, const T& scl,
+                                 double scene_extent, double dead_threshold, double cap) {
+    cugs::MCMCConfig c;
+    c.dead_opacity_threshold = static_cast<float>(dead_threshold);
+    c.relocate_cap = static_cast<float>(cap);
+    c.min_vram_headroom_mb = 0.0f;
+    cugs::MCMCController ctrl(c, static_cast<float>(scene_extent));
+    auto model = make_model(pos.clone(), sh.clone(), opa.clone(), rot.clone(), scl.clone());
+    const auto st = ctrl.relocate(model, 1000);
+    return {model.positions, model.sh_coeffs, model.opacities, model.rotations, model.scales,
+            torch::tensor({st.num_relocated, st.num_dead, st.num_total})};
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -266,6 +305,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("mcmc_inject_noise", &ref_mcmc_inject_noise);
     m.def("mcmc_noise_lr", &ref_mcmc_noise_lr);
     m.def("accumulate_gradients", &ref_accumulate_gradients);
+    m.def("densify", &ref_densify);
+    m.def("mcmc_relocate", &ref_mcmc_relocate);
     m.def("evaluate_sh_cuda", &cugs::evaluate_sh_cuda);
     m.def("evaluate_sh_cpu", &cugs::evaluate_sh_cpu);
     m.def("evaluate_sh_backward_cuda", &cugs::evaluate_sh_backward_cuda);

@@ -1,0 +1,45 @@
+"""Host logic of the model-resizing schedules (CPU only): the schedule predicates ported from the
+reference's own tests (tests/test_densification.cpp:48-104, tests/test_mcmc.cpp:46-82) and the
+threshold arithmetic handed to the kernels."""
+import numpy as np
+
+import cuda_gaussian_splatting_b200 as cugs
+
+
+def test_should_densify_boundaries():  # test_densification.cpp:48-80
+    ctrl = cugs.DensificationController(cugs.DensificationConfig(densify_from=500, densify_until=15000,
+                                                                 densify_every=100), 10.0, 0, "cpu")
+    for s in (0, 100, 400, 499, 501, 550, 999, 15100, 20000):
+        assert not ctrl.should_densify(s), s
+    for s in (500, 600, 1000, 14900, 15000):
+        assert ctrl.should_densify(s), s
+
+
+def test_should_reset_opacity():  # test_densification.cpp:82-104
+    ctrl = cugs.DensificationController(cugs.DensificationConfig(densify_from=500, opacity_reset_every=3000), 10.0, 0,
+                                        "cpu")
+    assert not ctrl.should_reset_opacity(0)
+    assert all(ctrl.should_reset_opacity(s) for s in (3000, 6000, 9000))
+    assert not ctrl.should_reset_opacity(3001) and not ctrl.should_reset_opacity(4000)
+    off = cugs.DensificationController(cugs.DensificationConfig(opacity_reset_every=0), 10.0, 0, "cpu")
+    assert not off.should_reset_opacity(3000)
+
+
+def test_should_relocate_boundaries():  # test_mcmc.cpp:46-82
+    cfg = cugs.MCMCConfig(relocate_from=500, relocate_until=15000, relocate_every=100)
+    for s in (0, 100, 499, 501, 550, 15100, 20000):
+        assert not cugs.mcmc_should_relocate(s, cfg), s
+    for s in (500, 600, 1000, 15000):
+        assert cugs.mcmc_should_relocate(s, cfg), s
+
+
+def test_native_thresholds_follow_the_reference_arithmetic():
+    ctrl = cugs.DensificationController(cugs.DensificationConfig(), 7.3, 0, "cpu")
+    early, late = ctrl._native_config(3000), ctrl._native_config(3001)
+    assert early.apply_size_pruning == 0 and late.apply_size_pruning == 1      # step > opacity_reset_every (:416-417)
+    assert np.float32(early.size_threshold) == np.float32(0.01) * np.float32(7.3)   # percent_dense * extent, float
+    assert np.float32(early.ws_threshold) == np.float32(0.1) * np.float32(7.3)
+    assert early.max_screen_size == 20.0 and np.float32(early.grad_threshold) == np.float32(0.0002)
+    assert ctrl._native_config(10**6).apply_size_pruning == 1
+    off = cugs.DensificationController(cugs.DensificationConfig(opacity_reset_every=0), 1.0, 0, "cpu")
+    assert off._native_config(10**6).apply_size_pruning == 0

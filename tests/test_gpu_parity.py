@@ -802,3 +802,33 @@ def test_sparse_gradient_rows_equal_dense_over_several_steps(torch):
         assert float((rs - rd).double().norm() / rd.double().norm()) <= 1e-5
         frac = float(mask.float().mean())
         assert 0.0 < frac < 0.9
+
+
+# ================================================================================================
+# render-only entry point (evaluation / viewer callers)
+# ================================================================================================
+@pytest.mark.parametrize("name", ["small", "adversarial", "deg1_c4", "giant_splats"])
+def test_render_image_equals_render_bitwise(torch, name):
+    scene, deg = get_scene(name)
+    m = to_torch(scene)
+    st = cugs.RenderSettings((0.2, 0.1, 0.4), deg, 1.0)
+    full = cugs.render(m, scene.camera, st)
+    bufs = cugs.ImageBuffers(scene.n, scene.camera.width, scene.camera.height, m.positions.device)
+    for _ in range(2):  # second call reuses the buffers (viewer loop)
+        color, final_T, n_contrib = cugs.render_image(m, scene.camera, st, bufs)
+    torch.cuda.synchronize()
+    assert np.array_equal(np_(color).view(np.uint32), np_(full.color).view(np.uint32))
+    assert np.array_equal(np_(final_T).view(np.uint32), np_(full.final_T).view(np.uint32))
+    assert np.array_equal(np_(n_contrib), np_(full.n_contrib))
+    # a half-null set of backward-only arrays is an argument error, not a crash
+    import ctypes as C
+    from cuda_gaussian_splatting_b200 import rasterizer as R
+    lib, h = R._lib_and_handle(m.positions.device)
+    v = R.make_view(scene.camera, st, deg, m.sh_coeffs.shape[2])
+    p = C.c_int64(0)
+    rc = lib.cugs_b200_render_plan(h, R._stream(m.positions.device), scene.n, C.byref(v), m.positions.data_ptr(),
+                                   m.rotations.data_ptr(), m.scales.data_ptr(), m.opacities.data_ptr(),
+                                   m.sh_coeffs.data_ptr(), bufs.means_2d.data_ptr(), None, None, bufs.radii.data_ptr(),
+                                   full.rgb.data_ptr(), None, bufs.workspace.data_ptr(), bufs.workspace.numel(),
+                                   C.byref(p))
+    assert rc < 0 and b"null output" in lib.cugs_b200_last_error(h)
