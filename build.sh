@@ -3,7 +3,7 @@
 # in-tree: cuda_gaussian_splatting_b200/libcugs_b200.so. No torch headers -> seconds per file.
 set -euo pipefail
 cd "$(dirname "$0")"
-SRC=cuda_gaussian_splatting_b200/csrc
+SRC=${SRCDIR:-cuda_gaussian_splatting_b200/csrc}
 OUT=cuda_gaussian_splatting_b200
 LIBNAME=${LIBNAME:-libcugs_b200.so}
 OBJ=${OBJDIR:-build/obj}

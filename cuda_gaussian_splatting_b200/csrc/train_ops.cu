@@ -20,88 +20,197 @@ namespace cugs {
 constexpr int kLossTile = 16;
 constexpr int kHalo = 5;
 constexpr int kLossIn = kLossTile + 2 * kHalo;  // 26
+constexpr int kInStride = 28;                   // padded planar row: every 4-column run starts 16-byte aligned
+constexpr int kRun = 4;                         // outputs per work item along the filter direction
+constexpr int kRunIn = kRun + 10;               // inputs a run needs (11 taps)
+constexpr int kHItems = kLossIn * 3 * (kLossTile / kRun);      // horizontal work items: (row, run, channel), row fastest
+constexpr int kVItems = kLossTile * 3 * (kLossTile / kRun);    // vertical work items: (column*3+channel, run)
+constexpr int kCC = kLossTile * 3;                             // interleaved output columns of a tile (48)
+// Shared-memory layouts are chosen for conflict-free VECTOR accesses in both passes:
+//   inputs   [channel][row][28]: horizontal items of one quarter-warp are 8 consecutive rows; a row stride
+//            of 28 floats (= -4 mod 32 banks) makes their LDS.128 tile all 32 banks;
+//   filtered [map][column*3+channel][28] (row fastest): the horizontal pass stores with consecutive rows in
+//            consecutive lanes, the vertical pass reads its 14 rows with LDS.128, 8 consecutive columns
+//            again tiling the banks.
 
 struct SsimWindow {
     float w[11];  // separable factor of the reference's 2-D window (loss.cpp:57-70)
 };
 
+// Both passes are separable 11-tap filters over a 16x16 tile + halo staged in shared memory. Shared
+// memory bandwidth, not FP32, bounds a tap-by-tap version (11 LDS per output and map), so every work
+// item filters a RUN of 4 outputs from 14 inputs held in registers (3.5 LDS per output, vector loads
+// in the horizontal direction: the input tiles are stored planar per channel with padded rows).
+__device__ __forceinline__ void load_run(const float* __restrict__ row, float (&v)[kRunIn]) {
+    const float4 q0 = *reinterpret_cast<const float4*>(row);
+    const float4 q1 = *reinterpret_cast<const float4*>(row + 4);
+    const float4 q2 = *reinterpret_cast<const float4*>(row + 8);
+    const float2 q3 = *reinterpret_cast<const float2*>(row + 12);
+    v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
+    v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+    v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w;
+    v[12] = q3.x; v[13] = q3.y;
+}
+
+__device__ __forceinline__ void h_item(int item, int& r, int& run, int& ch) {
+    r = item % kLossIn;
+    const int t = item / kLossIn;
+    run = t & 3;
+    ch = t >> 2;
+}
+
+// out[o] = sum_k w[k] * v[o + k], k ascending (the summation order of the tap-by-tap loop)
+__device__ __forceinline__ void filter_run(const SsimWindow& win, const float (&v)[kRunIn], float (&out)[kRun]) {
+#pragma unroll
+    for (int o = 0; o < kRun; ++o) out[o] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRunIn; ++j) {
+#pragma unroll
+        for (int o = 0; o < kRun; ++o) {
+            const int k = j - o;
+            if (k >= 0 && k < 11) out[o] = fmaf(win.w[k], v[j], out[o]);
+        }
+    }
+}
+
+// tile + halo of kImgs interleaved [H,W,3] images -> planar shared memory, zero outside the image
+// (conv2d padding = 5, loss.cpp:102-103). A row of the tile is 78 contiguous floats in global memory;
+// thread t owns one of them (t % 78) in every third row (t / 78), so all index arithmetic is hoisted
+// out of the loop and the 9 x kImgs loads of a thread are independent (in flight together).
+template <int kImgs>
+__device__ __forceinline__ void load_tiles_planar(const float* const (&img)[kImgs], int width, int height, int tx0,
+                                                  int ty0, float (*const (&dst)[kImgs])[kLossIn][kInStride]) {
+    constexpr int kRowF = kLossIn * 3;  // 78
+    const int t = threadIdx.x;
+    const int rsub = t / kRowF, cc = t - rsub * kRowF;
+    if (rsub >= 3) return;  // 234 of the 256 threads load
+    const int col = cc / 3, ch = cc - col * 3;
+    const int gx = tx0 - kHalo + col;
+    const bool x_ok = gx >= 0 && gx < width;
+    const int64_t g0 = ((int64_t)(ty0 - kHalo + rsub) * width + (tx0 - kHalo)) * 3 + cc;
+    const int64_t gstep = (int64_t)3 * width * 3;
+    float v[kImgs][9];
+#pragma unroll
+    for (int it = 0; it < 9; ++it) {
+        const int r = rsub + 3 * it;
+        const int gy = ty0 - kHalo + r;
+        const bool ok = x_ok && r < kLossIn && gy >= 0 && gy < height;
+#pragma unroll
+        for (int m = 0; m < kImgs; ++m) v[m][it] = ok ? __ldg(img[m] + g0 + it * gstep) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < 9; ++it) {
+        const int r = rsub + 3 * it;
+        if (r < kLossIn) {
+#pragma unroll
+            for (int m = 0; m < kImgs; ++m) dst[m][ch][r][col] = v[m][it];
+        }
+    }
+}
+
 // pass 1: local moments -> SSIM map value (summed) and the three partial-derivative maps
 //   g1 = dS/dmu_x, g2 = dS/dE[x^2], g3 = dS/dE[xy]   (raw moments held fixed)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_ssim_moments(int width, int height, SsimWindow win, const float* __restrict__ x_img,
                const float* __restrict__ y_img, float* __restrict__ g1, float* __restrict__ g2,
                float* __restrict__ g3, double* __restrict__ sums /* [2]: sum|x-y|, sum S */,
                float* __restrict__ ssim_map /* optional [H,W]: channel mean of S (loss.cpp:123) */) {
-    __shared__ float sx[kLossIn][kLossIn * 3];
-    __shared__ float sy[kLossIn][kLossIn * 3];
-    // four moment maps: mu_x, mu_y, E[x^2 + y^2], E[xy] (only the SUM of the two variances is needed)
-    __shared__ float sh[4][kLossIn][kLossTile * 3];
+    __shared__ __align__(16) float sx[3][kLossIn][kInStride];
+    __shared__ __align__(16) float sy[3][kLossIn][kInStride];
+    // four moment maps: mu_x, mu_y, E[x^2 + y^2], E[xy] (only the SUM of the two variances is needed),
+    // horizontally filtered, channel-interleaved so that the vertical pass reads them conflict-free
+    __shared__ __align__(16) float sh[4][kCC][kInStride];
     __shared__ float s_red[2][8];
 
     const int tx0 = blockIdx.x * kLossTile, ty0 = blockIdx.y * kLossTile;
-    // load tile + halo, zero padding outside the image (conv2d padding=5, loss.cpp:102-103)
-    for (int e = threadIdx.x; e < kLossIn * kLossIn * 3; e += 256) {
-        const int r = e / (kLossIn * 3), cc = e % (kLossIn * 3);
-        const int gx = tx0 - kHalo + cc / 3, gy = ty0 - kHalo + r, ch = cc % 3;
-        float vx = 0.f, vy = 0.f;
-        if (gx >= 0 && gx < width && gy >= 0 && gy < height) {
-            const int64_t gi = ((int64_t)gy * width + gx) * 3 + ch;
-            vx = x_img[gi];
-            vy = y_img[gi];
-        }
-        sx[r][cc] = vx;
-        sy[r][cc] = vy;
+    {
+        const float* const imgs[2] = {x_img, y_img};
+        float (*const dsts[2])[kLossIn][kInStride] = {sx, sy};
+        load_tiles_planar<2>(imgs, width, height, tx0, ty0, dsts);
     }
     __syncthreads();
-    // horizontal pass: 26 rows x 16 columns x 3 channels, five moments each
-    for (int e = threadIdx.x; e < kLossIn * kLossTile * 3; e += 256) {
-        const int r = e / (kLossTile * 3), cc = e % (kLossTile * 3);
-        const int col = cc / 3, ch = cc % 3;
-        float mx = 0.f, my = 0.f, qq = 0.f, xy = 0.f;
+    // horizontal pass: (26 rows x 4 runs x 3 channels) items, four moments each
+    for (int item = threadIdx.x; item < kHItems; item += 256) {
+        int r, run, ch;
+        h_item(item, r, run, ch);
+        float a[kRunIn], b[kRunIn], p[kRunIn], q[kRunIn], o4[kRun];
+        load_run(&sx[ch][r][run * kRun], a);
+        load_run(&sy[ch][r][run * kRun], b);
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float a = sx[r][(col + k) * 3 + ch], b = sy[r][(col + k) * 3 + ch], w = win.w[k];
-            mx = fmaf(w, a, mx);
-            my = fmaf(w, b, my);
-            qq = fmaf(w, fmaf(a, a, b * b), qq);
-            xy = fmaf(w, a * b, xy);
+        for (int j = 0; j < kRunIn; ++j) {
+            p[j] = fmaf(a[j], a[j], b[j] * b[j]);
+            q[j] = a[j] * b[j];
         }
-        sh[0][r][cc] = mx; sh[1][r][cc] = my; sh[2][r][cc] = qq; sh[3][r][cc] = xy;
+        float* o0 = &sh[0][run * kRun * 3 + ch][r];
+        filter_run(win, a, o4);
+#pragma unroll
+        for (int o = 0; o < kRun; ++o) o0[o * 3 * kInStride] = o4[o];
+        filter_run(win, b, o4);
+#pragma unroll
+        for (int o = 0; o < kRun; ++o) o0[(kCC + o * 3) * kInStride] = o4[o];
+        filter_run(win, p, o4);
+#pragma unroll
+        for (int o = 0; o < kRun; ++o) o0[(2 * kCC + o * 3) * kInStride] = o4[o];
+        filter_run(win, q, o4);
+#pragma unroll
+        for (int o = 0; o < kRun; ++o) o0[(3 * kCC + o * 3) * kInStride] = o4[o];
     }
     __syncthreads();
-    // vertical pass + SSIM
-    const int lx = threadIdx.x % kLossTile, ly = threadIdx.x / kLossTile;
-    const int gx = tx0 + lx, gy = ty0 + ly;
+    // vertical pass + SSIM: (48 interleaved columns x 4 runs of 4 rows) items
     float l1_local = 0.f, s_local = 0.f;
-    float s_pixel = 0.f;
-    if (gx < width && gy < height) {
-        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    float* s_S = &sy[0][0][0];  // per (pixel, channel) S for the optional map; sy is dead after the l1 term below
+    float S_keep[kRun];
+    bool have_item = false;
+    int it_cc = 0, it_run = 0;
+    if (threadIdx.x < kVItems) {
+        have_item = true;
+        const int cc = threadIdx.x % (kLossTile * 3), run = threadIdx.x / (kLossTile * 3);
+        it_cc = cc; it_run = run;
+        const int col = cc / 3, ch = cc - col * 3;
+        float m[4][kRun];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            float mx = 0.f, my = 0.f, qq = 0.f, xy = 0.f;
-#pragma unroll
-            for (int k = 0; k < 11; ++k) {
-                const float w = win.w[k];
-                mx = fmaf(w, sh[0][ly + k][lx * 3 + ch], mx);
-                my = fmaf(w, sh[1][ly + k][lx * 3 + ch], my);
-                qq = fmaf(w, sh[2][ly + k][lx * 3 + ch], qq);
-                xy = fmaf(w, sh[3][ly + k][lx * 3 + ch], xy);
-            }
-            const float sxy = xy - mx * my;
-            const float A1 = 2.0f * mx * my + C1, A2 = 2.0f * sxy + C2;
-            const float B1 = mx * mx + my * my + C1, B2 = (qq - mx * mx - my * my) + C2;  // sigma_x^2 + sigma_y^2 + C2
-            const float inv = 1.0f / (B1 * B2);
-            const float S = A1 * A2 * inv;
-            const int64_t gi = ((int64_t)gy * width + gx) * 3 + ch;
-            // dS/dmu_x = (A1' A2 + A1 A2')/(B1 B2) - S (B1'/B1 + B2'/B2)
-            g1[gi] = (2.0f * my * A2 - 2.0f * my * A1) * inv - S * (2.0f * mx / B1 - 2.0f * mx / B2);
-            g2[gi] = -S / B2;
-            g3[gi] = 2.0f * A1 * inv;
-            s_local += S;
-            s_pixel += S;
-            l1_local += fabsf(sx[ly + kHalo][(lx + kHalo) * 3 + ch] - sy[ly + kHalo][(lx + kHalo) * 3 + ch]);
+        for (int k = 0; k < 4; ++k) {
+            float v[kRunIn];
+            load_run(&sh[k][cc][run * kRun], v);
+            filter_run(win, v, m[k]);
         }
-        if (ssim_map != nullptr) ssim_map[(int64_t)gy * width + gx] = s_pixel / 3.0f;
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+        const int gx = tx0 + col;
+#pragma unroll
+        for (int o = 0; o < kRun; ++o) {
+            const int ly = run * kRun + o, gy = ty0 + ly;
+            S_keep[o] = 0.f;
+            if (gx < width && gy < height) {
+                const float mx = m[0][o], my = m[1][o], qq = m[2][o], xy = m[3][o];
+                const float sxy = xy - mx * my;
+                const float A1 = 2.0f * mx * my + C1, A2 = 2.0f * sxy + C2;
+                const float B1 = mx * mx + my * my + C1, B2 = (qq - mx * mx - my * my) + C2;  // sigma_x^2 + sigma_y^2 + C2
+                const float inv = __frcp_rn(B1 * B2);  // one reciprocal: 1/B1 = B2 inv, 1/B2 = B1 inv
+                const float S = A1 * A2 * inv;
+                const float rB1 = B2 * inv, rB2 = B1 * inv;
+                const int64_t gi = ((int64_t)gy * width + gx) * 3 + ch;
+                // dS/dmu_x = (A1' A2 + A1 A2')/(B1 B2) - S (B1'/B1 + B2'/B2)
+                g1[gi] = 2.0f * my * (A2 - A1) * inv - 2.0f * mx * S * (rB1 - rB2);
+                g2[gi] = -S * rB2;
+                g3[gi] = 2.0f * A1 * inv;
+                s_local += S;
+                S_keep[o] = S;
+                l1_local += fabsf(sx[ch][ly + kHalo][col + kHalo] - sy[ch][ly + kHalo][col + kHalo]);
+            }
+        }
+    }
+    if (ssim_map != nullptr) {  // uniform branch
+        __syncthreads();
+        if (have_item) {
+#pragma unroll
+            for (int o = 0; o < kRun; ++o) s_S[(it_run * kRun + o) * (kLossTile * 3) + it_cc] = S_keep[o];
+        }
+        __syncthreads();
+        const int lx = threadIdx.x % kLossTile, ly = threadIdx.x / kLossTile;
+        if (tx0 + lx < width && ty0 + ly < height) {
+            const float* t = &s_S[ly * (kLossTile * 3) + lx * 3];
+            ssim_map[(int64_t)(ty0 + ly) * width + tx0 + lx] = ((t[0] + t[1]) + t[2]) / 3.0f;
+        }
     }
     // block reduction -> one double atomic per block and quantity
 #pragma unroll
@@ -120,57 +229,66 @@ k_ssim_moments(int width, int height, SsimWindow win, const float* __restrict__ 
 }
 
 // pass 2: dL/dx = (1-l) sign(x-y)/n - l/n * (W*g1 + 2 x (W*g2) + y (W*g3))
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_ssim_gradient(int width, int height, SsimWindow win, float lambda, const float* __restrict__ x_img,
                 const float* __restrict__ y_img, const float* __restrict__ g1,
                 const float* __restrict__ g2, const float* __restrict__ g3, float* __restrict__ dL_dx) {
-    __shared__ float sg[3][kLossIn][kLossIn * 3];
-    __shared__ float sh[3][kLossIn][kLossTile * 3];
+    __shared__ __align__(16) float sg[3][3][kLossIn][kInStride];  // [map][channel] planar
+    __shared__ __align__(16) float sh[3][kCC][kInStride];
     const int tx0 = blockIdx.x * kLossTile, ty0 = blockIdx.y * kLossTile;
-    for (int e = threadIdx.x; e < kLossIn * kLossIn * 3; e += 256) {
-        const int r = e / (kLossIn * 3), cc = e % (kLossIn * 3);
-        const int gx = tx0 - kHalo + cc / 3, gy = ty0 - kHalo + r, ch = cc % 3;
-        float a = 0.f, b = 0.f, c = 0.f;
-        if (gx >= 0 && gx < width && gy >= 0 && gy < height) {
-            const int64_t gi = ((int64_t)gy * width + gx) * 3 + ch;
-            a = g1[gi]; b = g2[gi]; c = g3[gi];
-        }
-        sg[0][r][cc] = a; sg[1][r][cc] = b; sg[2][r][cc] = c;
+    {
+        const float* const imgs[3] = {g1, g2, g3};
+        float (*const dsts[3])[kLossIn][kInStride] = {sg[0], sg[1], sg[2]};
+        load_tiles_planar<3>(imgs, width, height, tx0, ty0, dsts);
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < kLossIn * kLossTile * 3; e += 256) {
-        const int r = e / (kLossTile * 3), cc = e % (kLossTile * 3);
-        const int col = cc / 3, ch = cc % 3;
-        float a = 0.f, b = 0.f, c = 0.f;
+    // the centre pixels of this thread's vertical run, fetched now so that their latency hides behind
+    // the two filter passes
+    const int cc = threadIdx.x % (kLossTile * 3), run = threadIdx.x / (kLossTile * 3);
+    const int col = cc / 3, ch = cc - col * 3;
+    const int gx = tx0 + col;
+    float xc[kRun], yc[kRun];
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float w = win.w[k];
-            a = fmaf(w, sg[0][r][(col + k) * 3 + ch], a);
-            b = fmaf(w, sg[1][r][(col + k) * 3 + ch], b);
-            c = fmaf(w, sg[2][r][(col + k) * 3 + ch], c);
-        }
-        sh[0][r][cc] = a; sh[1][r][cc] = b; sh[2][r][cc] = c;
+    for (int o = 0; o < kRun; ++o) {
+        const int gy = ty0 + run * kRun + o;
+        const bool ok = threadIdx.x < kVItems && gx < width && gy < height;
+        const int64_t gi = ((int64_t)gy * width + gx) * 3 + ch;
+        xc[o] = ok ? __ldg(x_img + gi) : 0.f;
+        yc[o] = ok ? __ldg(y_img + gi) : 0.f;
     }
     __syncthreads();
-    const int lx = threadIdx.x % kLossTile, ly = threadIdx.x / kLossTile;
-    const int gx = tx0 + lx, gy = ty0 + ly;
-    if (gx >= width || gy >= height) return;
+    for (int item = threadIdx.x; item < kHItems; item += 256) {
+        int r, hrun, hch;
+        h_item(item, r, hrun, hch);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float a[kRunIn], o4[kRun];
+            load_run(&sg[k][hch][r][hrun * kRun], a);
+            filter_run(win, a, o4);
+            float* o0 = &sh[k][hrun * kRun * 3 + hch][r];
+#pragma unroll
+            for (int o = 0; o < kRun; ++o) o0[o * 3 * kInStride] = o4[o];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x >= kVItems) return;
+    float m[3][kRun];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v[kRunIn];
+        load_run(&sh[k][cc][run * kRun], v);
+        filter_run(win, v, m[k]);
+    }
+    if (gx >= width) return;
     const float inv_n = 1.0f / (3.0f * (float)width * (float)height);
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        float a = 0.f, b = 0.f, c = 0.f;
-#pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float w = win.w[k];
-            a = fmaf(w, sh[0][ly + k][lx * 3 + ch], a);
-            b = fmaf(w, sh[1][ly + k][lx * 3 + ch], b);
-            c = fmaf(w, sh[2][ly + k][lx * 3 + ch], c);
-        }
+    for (int o = 0; o < kRun; ++o) {
+        const int gy = ty0 + run * kRun + o;
+        if (gy >= height) break;
         const int64_t gi = ((int64_t)gy * width + gx) * 3 + ch;
-        const float xv = x_img[gi], yv = y_img[gi];
+        const float xv = xc[o], yv = yc[o];
         const float d = xv - yv;
         const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-        const float dssim = a + 2.0f * xv * b + yv * c;
+        const float dssim = m[0][o] + 2.0f * xv * m[1][o] + yv * m[2][o];
         dL_dx[gi] = (1.0f - lambda) * sgn * inv_n - lambda * inv_n * dssim;
     }
 }
