@@ -73,29 +73,45 @@ k_scan_exclusive(int64_t n, const int* __restrict__ in, int* __restrict__ out,
         block_sum += s;
     }
 
-    // decoupled look-back (thread 0 of the block; the chain is short because blocks are ticketed)
-    if (threadIdx.x == 0) {
+    // decoupled look-back by warp 0: 32 predecessors per round trip (one per lane), consumed up to the
+    // nearest inclusive prefix; a window with an unpublished status in front of that prefix is re-read
+    if (warp == 0) {
         int64_t excl = 0;
         if (bid == 0) {
-            status[0] = kFlagPrefix | (uint64_t)block_sum;
+            if (lane == 0) status[0] = kFlagPrefix | (uint64_t)block_sum;
         } else {
-            status[bid] = kFlagAggregate | (uint64_t)block_sum;
-            __threadfence();
+            if (lane == 0) {
+                status[bid] = kFlagAggregate | (uint64_t)block_sum;
+                __threadfence();
+            }
             int64_t j = (int64_t)bid - 1;
             while (true) {
-                const uint64_t s = status[j];
-                if (s & kFlagPrefix) { excl += (int64_t)(s & kValueMask); break; }
-                if (s & kFlagAggregate) { excl += (int64_t)(s & kValueMask); --j; }
+                const int64_t idx = j - lane;
+                uint64_t st = 2ull << 62;  // in front of block 0: an inclusive prefix of zero
+                if (idx >= 0) st = status[idx];
+                const unsigned pref = __ballot_sync(kFull, (st & kFlagPrefix) != 0);
+                const unsigned none = __ballot_sync(kFull, (st & (kFlagPrefix | kFlagAggregate)) == 0);
+                const int first = pref ? __ffs(pref) - 1 : 31;  // last lane that is consumed this round
+                const unsigned need = (first == 31) ? kFull : ((2u << first) - 1);
+                if (none & need) continue;
+                int64_t val = (lane <= first) ? (int64_t)(st & kValueMask) : 0;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(kFull, val, d);
+                excl += val;
+                if (pref) break;
+                j -= 32;
             }
-            status[bid] = kFlagPrefix | (uint64_t)(excl + block_sum);
+            if (lane == 0) status[bid] = kFlagPrefix | (uint64_t)(excl + block_sum);
         }
-        s_prefix = excl;
-        if ((int64_t)(bid + 1) * kScanTile >= n) {  // last logical block
-            const int64_t total = excl + block_sum;
-            if (total_dev) *total_dev = total;
-            if (total_pinned) {
-                total_pinned[0] = total;
-                if (aux_pair) total_pinned[1] = (int64_t)((uint64_t)aux_pair[0] | ((uint64_t)aux_pair[1] << 32));
+        if (lane == 0) {
+            s_prefix = excl;
+            if ((int64_t)(bid + 1) * kScanTile >= n) {  // last logical block
+                const int64_t total = excl + block_sum;
+                if (total_dev) *total_dev = total;
+                if (total_pinned) {
+                    total_pinned[0] = total;
+                    if (aux_pair) total_pinned[1] = (int64_t)((uint64_t)aux_pair[0] | ((uint64_t)aux_pair[1] << 32));
+                }
             }
         }
     }
