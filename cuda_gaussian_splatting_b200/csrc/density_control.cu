@@ -240,7 +240,8 @@ constexpr int kRelBlock = 1024;
 // per block of 1024 Gaussians: number of dead ones and the summed sampling weight of the alive ones
 __global__ void __launch_bounds__(kRelBlock)
 k_relocate_classify(int64_t n, const float* __restrict__ opacities, float dead_threshold,
-                    unsigned* __restrict__ block_dead, double* __restrict__ block_weight) {
+                    unsigned* __restrict__ block_dead, double* __restrict__ block_weight,
+                    double* __restrict__ warp_weight /* [blocks * 32] */) {
     __shared__ unsigned s_dead;
     __shared__ double s_w[kRelBlock / 32];
     if (threadIdx.x == 0) s_dead = 0;
@@ -260,6 +261,7 @@ k_relocate_classify(int64_t n, const float* __restrict__ opacities, float dead_t
     if ((threadIdx.x & 31) == 0) {
         if (b) atomicAdd(&s_dead, (unsigned)__popc(b));
         s_w[threadIdx.x >> 5] = acc;
+        warp_weight[(size_t)blockIdx.x * (kRelBlock / 32) + (threadIdx.x >> 5)] = acc;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -323,11 +325,13 @@ k_relocate_scan(int64_t nb, unsigned* __restrict__ block_dead, double* __restric
 
 // thread per Gaussian; a dead one whose rank among the dead is below the cap draws its source from the
 // alive ones with probability proportional to sigmoid(opacity) (inverse cdf: block level by binary
-// search over the scanned block sums, then a walk over the 1024 weights of that block). Only reads the
+// search over the scanned block sums, then a walk over the block's 32 warp sums and over the 32 weights
+// of that warp). Only reads the
 // model: the copies happen in k_relocate_copy, so that every walk sees the opacities of before the call.
 __global__ void __launch_bounds__(kRelBlock)
 k_relocate_select(int64_t n, const float* __restrict__ opacities, float dead_threshold, int64_t max_relocate,
-                  const unsigned* __restrict__ block_dead_off, const double* __restrict__ block_cdf, int64_t nb,
+                  const unsigned* __restrict__ block_dead_off, const double* __restrict__ block_cdf,
+                  const double* __restrict__ warp_weight, int64_t nb,
                   const unsigned long long* __restrict__ totals, const double* __restrict__ total_weight,
                   unsigned seed_lo, unsigned seed_hi, unsigned step, int32_t* __restrict__ source) {
     __shared__ unsigned s_wcnt[kRelBlock / 32];
@@ -355,16 +359,28 @@ k_relocate_select(int64_t n, const float* __restrict__ opacities, float dead_thr
                 if (block_cdf[mid] > target) hi = mid; else lo = mid + 1;
             }
             double acc = lo > 0 ? block_cdf[lo - 1] : 0.0;
-            const int64_t j0 = lo * kRelBlock, j1 = min(n, j0 + (int64_t)kRelBlock);
-            int64_t last_alive = -1;
-            for (int64_t j = j0; j < j1; ++j) {
-                const float w = sigmoid_ref(opacities[j]);
-                if (w < dead_threshold) continue;
-                last_alive = j;
-                acc += (double)w;
-                if (acc > target) { src = j; break; }
+            const double* ww = warp_weight + lo * (kRelBlock / 32);
+            int wsel = -1, wlast = -1;
+            for (int k = 0; k < kRelBlock / 32; ++k) {
+                const double wk = ww[k];
+                if (wk <= 0.0) continue;
+                wlast = k;
+                if (acc + wk > target) { wsel = k; break; }
+                acc += wk;
             }
-            if (src < 0) src = last_alive;  // summation-order rounding at the end of the block
+            if (wsel < 0) { wsel = wlast; acc -= (wlast >= 0 ? ww[wlast] : 0.0); }  // rounding at the block's end
+            int64_t last_alive = -1;
+            if (wsel >= 0) {
+                const int64_t j0 = lo * kRelBlock + (int64_t)wsel * 32, j1 = min(n, j0 + 32);
+                for (int64_t j = j0; j < j1; ++j) {
+                    const float w = sigmoid_ref(opacities[j]);
+                    if (w < dead_threshold) continue;
+                    last_alive = j;
+                    acc += (double)w;
+                    if (acc > target) { src = j; break; }
+                }
+            }
+            if (src < 0) src = last_alive;  // summation-order rounding at the end of the warp
         }
     }
     source[i] = (int32_t)src;
@@ -479,7 +495,8 @@ extern "C" int cugs_b200_densify_apply(cugs_handle_t* h, void* stream, int64_t n
 
 extern "C" size_t cugs_b200_mcmc_relocate_temp_bytes(int64_t n) {
     const size_t nb = (size_t)((n + kRelBlock - 1) / kRelBlock) + 1;
-    return 256 + au(nb * sizeof(unsigned)) + au(nb * sizeof(double)) + au((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+    return 256 + au(nb * sizeof(unsigned)) + au(nb * sizeof(double)) + au(nb * (kRelBlock / 32) * sizeof(double)) +
+           au((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
 }
 
 extern "C" int cugs_b200_mcmc_relocate(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs, float* positions,
@@ -503,16 +520,19 @@ extern "C" int cugs_b200_mcmc_relocate(cugs_handle_t* h, void* stream, int64_t n
     double* total_weight = reinterpret_cast<double*>(base + 64);
     unsigned* block_dead = reinterpret_cast<unsigned*>(base + 256);
     double* block_cdf = reinterpret_cast<double*>(base + 256 + au((size_t)(nb + 1) * sizeof(unsigned)));
+    double* warp_weight = reinterpret_cast<double*>(reinterpret_cast<char*>(block_cdf) +
+                                                    au((size_t)(nb + 1) * sizeof(double)));
     int32_t* source = source_out ? source_out
-                                 : reinterpret_cast<int32_t*>(reinterpret_cast<char*>(block_cdf) +
-                                                              au((size_t)(nb + 1) * sizeof(double)));
-    k_relocate_classify<<<(unsigned)nb, kRelBlock, 0, s>>>(n, opacities, dead_threshold, block_dead, block_cdf);
+                                 : reinterpret_cast<int32_t*>(reinterpret_cast<char*>(warp_weight) +
+                                                              au((size_t)(nb + 1) * (kRelBlock / 32) * sizeof(double)));
+    k_relocate_classify<<<(unsigned)nb, kRelBlock, 0, s>>>(n, opacities, dead_threshold, block_dead, block_cdf,
+                                                           warp_weight);
     CUGS_LAUNCH_CHECK(h, "k_relocate_classify");
     k_relocate_scan<<<1, 1024, 0, s>>>(nb, block_dead, block_cdf, totals, total_weight,
                                        counts_host ? h->pinned + 4 : nullptr, n, max_relocate);
     CUGS_LAUNCH_CHECK(h, "k_relocate_scan");
     k_relocate_select<<<(unsigned)nb, kRelBlock, 0, s>>>(n, opacities, dead_threshold, max_relocate, block_dead,
-                                                         block_cdf, nb, totals, total_weight, (unsigned)seed,
+                                                         block_cdf, warp_weight, nb, totals, total_weight, (unsigned)seed,
                                                          (unsigned)(seed >> 32), step, source);
     CUGS_LAUNCH_CHECK(h, "k_relocate_select");
     const float log_shrink = std::log(10.0f);            // mcmc_densification.cpp:126
