@@ -130,3 +130,79 @@ def test_trainer_sequence_same_caller_code_two_libraries(ref, dropin, torch):
     assert abs(ld[0] - lr_[0]) <= 1e-5
     for a, b in zip(r[1:], d[1:]):
         assert float((a - b).abs().mean()) <= 2e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# the schedule-driven callers: DensificationController / MCMCController defined by the wrapper
+# ------------------------------------------------------------------------------------------------
+def density_inputs(torch, n=12000, seed=3):
+    scene = cugs.synth(n, 320, 240, seed=seed)
+    m = to_torch(scene)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    count = torch.randint(0, 6, (n,), device="cuda", generator=g).float()
+    accum = torch.rand((n,), device="cuda", generator=g) * 8e-4 * count.clamp_min(1) * (count > 0)
+    radii = torch.randint(0, 41, (n,), device="cuda", generator=g).float()
+    m.opacities[torch.rand((n,), device="cuda", generator=g) < 0.05] = -7.0
+    extent = float(torch.exp(m.scales).max(dim=1).values.median()) / 0.01
+    return m, accum, count, radii, extent
+
+
+@pytest.mark.parametrize("step,max_gaussians", [(600, 0), (3100, 0), (700, 12100)])
+def test_densify_same_call_two_libraries(ref, dropin, torch, step, max_gaussians):
+    m, accum, count, radii, extent = density_inputs(torch)
+    args = (m.positions, m.sh_coeffs, m.opacities, m.rotations, m.scales, accum, count, radii, extent, step,
+            [0.0002, 0.005, 0.01, 20, max_gaussians, 3000])
+    r, d = ref.densify(*args), dropin.densify(*args)
+    assert r[5].tolist() == d[5].tolist()                     # cloned, split, pruned, before, after
+    cloned, split, pruned, before, after = r[5].tolist()
+    assert cloned > 0 and pruned > 0 and (split > 0 or max_gaussians > 0)
+    head = after - 2 * split
+    for k in range(5):
+        assert r[k].shape == d[k].shape
+        assert torch.equal(r[k][:head].view(torch.int32), d[k][:head].view(torch.int32))   # kept + cloned rows
+    for k in (1, 2, 3, 4):                                    # children: sh, opacity, rotation, scale are copies
+        assert torch.equal(r[k][head:].view(torch.int32), d[k][head:].view(torch.int32))
+    if split:
+        # child position = parent + N(0,1) * exp(new scale): normalised residuals of both libraries are N(0,1)
+        s_new = d[4][head:]
+        for lib in (r, d):
+            parents = lib[0][head:] - 0  # children
+            z = (parents[:split] - parents[split:]) / torch.exp(s_new[:split]) / 2 ** 0.5   # difference of two draws
+            assert abs(float(z.mean())) < 5 / (3 * split) ** 0.5 and abs(float(z.std()) - 1) < 0.06
+
+
+def test_mcmc_controller_same_call_two_libraries(ref, dropin, torch):
+    scene = cugs.synth(40000, 320, 240, seed=9)
+    m = to_torch(scene)
+    m.opacities[::9] = -8.0
+    args = (m.positions, m.sh_coeffs, m.opacities, m.rotations, m.scales)
+    r, d = ref.mcmc_relocate(*args, 4.0, 0.005, 0.05), dropin.mcmc_relocate(*args, 4.0, 0.005, 0.05)
+    assert r[5].tolist() == d[5].tolist() and r[5].tolist()[0] == 2000
+    moved_r, moved_d = (r[2] != m.opacities).squeeze(1), (d[2] != m.opacities).squeeze(1)
+    assert torch.equal(moved_r, moved_d)                       # the same (first `cap`) dead Gaussians move
+    for k in range(5):
+        assert torch.equal(r[k][~moved_r].view(torch.int32), d[k][~moved_r].view(torch.int32))
+    assert torch.equal(r[2].view(torch.int32), d[2].view(torch.int32))   # logit(0.01) everywhere it moved
+    # regulariser: loss and both gradients (autograd there, closed form here)
+    rr, dd = ref.mcmc_regularization(*args, 0.01, 0.02), dropin.mcmc_regularization(*args, 0.01, 0.02)
+    assert abs(float(rr[0]) - float(dd[0])) <= 1e-6 * max(1.0, abs(float(rr[0])))
+    for a, b_ in zip(rr[1:], dd[1:]):
+        assert a.shape == b_.shape and float((a - b_).abs().max()) <= 1e-6 * float(a.abs().max()) + 1e-12
+    # noise: same learning rate; displacement = lr * exp(scale) * gate * N(0,1) in both
+    for step in (0, 100, 15000, 30000):
+        assert ref.mcmc_noise_lr(step) == dropin.mcmc_noise_lr(step)
+    alive = to_torch(scene)
+    alive.opacities.fill_(-3.0)                                # gate ~ 1 everywhere
+    p_r, p_d = alive.positions.clone(), alive.positions.clone()
+    ref.mcmc_inject_noise(p_r, alive.sh_coeffs, alive.opacities, alive.rotations, alive.scales, 29000)
+    dropin.mcmc_inject_noise(p_d, alive.sh_coeffs, alive.opacities, alive.rotations, alive.scales, 29000)
+    lr = ref.mcmc_noise_lr(29000)
+    for p in (p_r, p_d):
+        z = (p - alive.positions) / (lr * torch.exp(alive.scales))
+        assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1) < 0.03
+    # accumulate_gradients through the controller of either library
+    g2 = torch.randn((40000, 2), device="cuda")
+    rad = torch.randint(0, 5, (40000,), device="cuda", dtype=torch.int32)
+    ra, da = ref.accumulate_gradients(g2, rad, 3), dropin.accumulate_gradients(g2, rad, 3)
+    assert torch.allclose(ra[0], da[0], rtol=1e-6, atol=0)     # sum of norms (torch.norm vs sqrt(x*x + y*y))
+    assert torch.equal(ra[1], da[1]) and torch.equal(ra[2], da[2])   # visibility count, max radius

@@ -4,8 +4,9 @@
 // pointers. It is compiled against the reference's OWN, unmodified headers (the declarations a
 // maintainer already has) and replaces, in the reference's build, rasterizer/rasterizer.cpp,
 // rasterizer/{projection,sorting,forward,backward,projection_backward}.cu, core/{sh,sh_backward}.cu,
-// training/loss.cpp and optimizer/fused_adam.cu. libtorch tensors exist only in this file; no CUDA
-// code here.
+// training/loss.cpp, optimizer/fused_adam.cu and -- the schedule-driven callers that resize the model --
+// optimizer/densification.cpp and optimizer/mcmc_densification.cpp. libtorch tensors exist only in
+// this file; no CUDA code here.
 //
 // Build (what oracle/Makefile.ref's `dropin` target does):
 //   g++ -std=c++20 -I<reference>/src -I<eigen> -I<torch includes> -Iinclude -c wrapper/cugs_b200_dropin.cpp
@@ -22,7 +23,9 @@
 #include "core/sh.hpp"
 #include "core/sh_backward.hpp"
 #include "core/types.hpp"
+#include "optimizer/densification.hpp"
 #include "optimizer/fused_adam.hpp"
+#include "optimizer/mcmc_densification.hpp"
 #include "rasterizer/backward.hpp"
 #include "rasterizer/forward.hpp"
 #include "rasterizer/projection.hpp"
@@ -585,6 +588,217 @@ void FusedAdam::launch_kernel(torch::Tensor& param, const torch::Tensor& grad, t
     cugs_handle_t* h = handle_for(param);
     CUGS_CALL(h, cugs_b200_adam_step(h, current_stream(param), p, g, mm, vv, counts, lrs, config_.beta1, config_.beta2,
                                      config_.eps, bc1, bc2, 1.0f));
+}
+
+// =====================================================================================================
+// optimizer/densification.hpp -- DensificationController on the C ABI (densify = two kernels around the
+// host policy instead of the mask-index / torch::cat chain of optimizer/densification.cpp:94-329)
+// =====================================================================================================
+DensificationController::DensificationController(const DensificationConfig& config, float scene_extent)
+    : config_(config), scene_extent_(scene_extent) {}
+
+bool DensificationController::should_densify(int step) const {
+    const auto& c = config_;
+    return step % c.densify_every == 0 && step >= c.densify_from && step <= c.densify_until;
+}
+
+bool DensificationController::should_reset_opacity(int step) const {
+    const auto& c = config_;
+    return c.opacity_reset_every > 0 && step % c.opacity_reset_every == 0 && step >= c.densify_from;
+}
+
+void DensificationController::reset_accumulators(int64_t n) {
+    const auto opts = torch::TensorOptions().dtype(torch::kFloat32).device(
+        grad_accum_.defined() ? grad_accum_.device() : torch::Device(torch::kCUDA));
+    grad_accum_ = torch::zeros({n}, opts);
+    grad_count_ = torch::zeros({n}, opts);
+    max_radii_2d_ = torch::zeros({n}, opts);
+}
+
+void DensificationController::accumulate_gradients(const torch::Tensor& dL_dmeans_2d, const torch::Tensor& radii) {
+    torch::NoGradGuard no_grad;
+    const int64_t n = dL_dmeans_2d.size(0);
+    if (!grad_accum_.defined() || grad_accum_.size(0) != n) {  // lazy (re-)initialisation
+        grad_accum_ = torch::Tensor();
+        grad_accum_ = torch::zeros({n}, dL_dmeans_2d.options().dtype(torch::kFloat32));
+        grad_count_ = torch::zeros_like(grad_accum_);
+        max_radii_2d_ = torch::zeros_like(grad_accum_);
+    }
+    if (n == 0) return;
+    const auto g = f32c(dL_dmeans_2d);
+    const auto r = radii.contiguous().to(torch::kInt32);
+    cugs_handle_t* h = handle_for(g);
+    CUGS_CALL(h, cugs_b200_accumulate_stats(h, current_stream(g), n, fp(g), ip(r), fp(grad_accum_), fp(grad_count_),
+                                            fp(max_radii_2d_)));
+}
+
+void DensificationController::reset_opacity(GaussianModel& model) {
+    torch::NoGradGuard no_grad;
+    model.opacities.fill_(std::log(0.01f / 0.99f));  // inverse_sigmoid(0.01)
+}
+
+DensificationStats DensificationController::densify(GaussianModel& model, int step) {
+    torch::NoGradGuard no_grad;
+    DensificationStats stats;
+    const int64_t n = model.num_gaussians();
+    stats.num_before = stats.num_after = static_cast<int>(n);
+    if (n == 0) return stats;
+    if (!grad_accum_.defined() || grad_accum_.size(0) != n) {
+        grad_accum_ = torch::zeros({n}, model.positions.options());
+        grad_count_ = torch::zeros_like(grad_accum_);
+        max_radii_2d_ = torch::zeros_like(grad_accum_);
+    }
+    cugs_handle_t* h = handle_for(model.positions);
+    void* stream = current_stream(model.positions);
+    const auto u8 = torch::TensorOptions().dtype(torch::kUInt8).device(model.positions.device());
+
+    cugs_densify_config_t cfg{};
+    cfg.grad_threshold = config_.grad_threshold;
+    cfg.size_threshold = config_.percent_dense * scene_extent_;
+    cfg.opacity_threshold = config_.opacity_threshold;
+    cfg.apply_size_pruning = (config_.opacity_reset_every > 0 && step > config_.opacity_reset_every) ? 1 : 0;
+    cfg.max_screen_size = static_cast<float>(config_.max_screen_size);
+    cfg.ws_threshold = 0.1f * scene_extent_;
+
+    auto pos = f32c(model.positions), sh = f32c(model.sh_coeffs), opa = f32c(model.opacities),
+         scl = f32c(model.scales), rot = f32c(model.rotations);
+    auto flags = torch::empty({n}, u8);
+    auto temp = torch::empty({static_cast<int64_t>(cugs_b200_densify_temp_bytes(n))}, u8);
+    int64_t counts[3] = {0, 0, 0};
+    CUGS_CALL(h, cugs_b200_densify_classify(h, stream, n, fp(scl), fp(opa), fp(grad_accum_), fp(grad_count_),
+                                            fp(max_radii_2d_), &cfg, flags.data_ptr<uint8_t>(), counts,
+                                            temp.data_ptr(), temp.numel()));
+    int64_t kept = counts[0], n_clone = counts[1], n_split = counts[2];
+
+    // budget caps (max_gaussians): the rarely taken host policy, on the flag array. Candidates are ranked
+    // by their average gradient and only the best `budget` keep their bit.
+    auto cap = [&](int bit, int64_t budget) {
+        auto mask = flags.bitwise_and(bit).ne(0);
+        flags.bitwise_and_(static_cast<uint8_t>(~bit & 0xFF));
+        if (budget <= 0) return;
+        auto avg = grad_accum_ / grad_count_.clamp_min(1);
+        auto idx = std::get<1>(avg.masked_fill(~mask, -1.0f).topk(budget));
+        flags.index_put_({idx}, flags.index({idx}).bitwise_or(bit));
+    };
+    bool capped = false;
+    if (config_.max_gaussians > 0) {
+        const int64_t clone_budget = config_.max_gaussians - n;
+        if (n_clone > 0 && n_clone > clone_budget) {
+            cap(CUGS_DENSIFY_CLONE, clone_budget);
+            n_clone = std::max<int64_t>(std::min(n_clone, clone_budget), 0);
+            capped = true;
+        }
+        if (n_split > 0) {
+            const int64_t split_budget = (config_.max_gaussians - (n + n_clone)) / 2;
+            if (n_split > split_budget) {
+                cap(CUGS_DENSIFY_SPLIT, split_budget);
+                n_split = std::max<int64_t>(std::min(n_split, split_budget), 0);
+                capped = true;
+            }
+        }
+    }
+    if (capped)
+        kept = (flags.bitwise_and(CUGS_DENSIFY_KEEP).ne(0) & flags.bitwise_and(CUGS_DENSIFY_SPLIT).eq(0)).sum().item<int64_t>();
+
+    const int64_t n_out = kept + n_clone + 2 * n_split;
+    stats.num_cloned = static_cast<int>(n_clone);
+    stats.num_split = static_cast<int>(n_split);
+    stats.num_pruned = static_cast<int>(n + n_clone + 2 * n_split - n_out);
+    stats.num_after = static_cast<int>(n_out);
+    if (n_clone > 0 || n_split > 0 || n_out != n) {
+        const int C = static_cast<int>(sh.size(2));
+        const auto f32 = model.positions.options().dtype(torch::kFloat32);
+        torch::Tensor dst[5] = {torch::empty({n_out, 3}, f32), torch::empty({n_out, 3, C}, f32),
+                                torch::empty({n_out, 1}, f32), torch::empty({n_out, 3}, f32),
+                                torch::empty({n_out, 4}, f32)};
+        const float* src_p[5] = {fp(pos), fp(sh), fp(opa), fp(scl), fp(rot)};
+        float* dst_p[5] = {fp(dst[0]), fp(dst[1]), fp(dst[2]), fp(dst[3]), fp(dst[4])};
+        static uint64_t call_counter = 0;  // a different Philox stream for every densification
+        const uint64_t seed = 0xD5171F00ull + (static_cast<uint64_t>(step) << 20) + (call_counter++);
+        CUGS_CALL(h, cugs_b200_densify_apply(h, stream, n, n_out, C, flags.data_ptr<uint8_t>(), src_p, dst_p, nullptr,
+                                             nullptr, nullptr, nullptr, seed, nullptr, temp.data_ptr(), temp.numel()));
+        model.positions = dst[0];
+        model.sh_coeffs = dst[1];
+        model.opacities = dst[2];
+        model.scales = dst[3];
+        model.rotations = dst[4];
+    }
+    reset_accumulators(n_out);
+    return stats;
+}
+
+// =====================================================================================================
+// optimizer/mcmc_densification.hpp -- MCMCController on the C ABI
+// =====================================================================================================
+MCMCController::MCMCController(const MCMCConfig& config, float scene_extent)
+    : config_(config), scene_extent_(scene_extent) {}
+
+bool MCMCController::should_relocate(int step) const {
+    const auto& c = config_;
+    return step % c.relocate_every == 0 && step >= c.relocate_from && step <= c.relocate_until;
+}
+
+float MCMCController::noise_lr(int step) const {  // log-linear decay, in float like the reference
+    const auto& c = config_;
+    if (step <= 0) return c.noise_lr_init;
+    if (step >= c.noise_lr_max_steps) return c.noise_lr_final;
+    const float t = static_cast<float>(step) / static_cast<float>(c.noise_lr_max_steps);
+    return c.noise_lr_init * std::exp(t * std::log(c.noise_lr_final / c.noise_lr_init));
+}
+
+namespace {
+constexpr uint64_t kMcmcSeed = 0x5EEDull;  // every rank of a view-parallel run must draw the same numbers
+void check_plain(const GaussianModel& m) {
+    TORCH_CHECK(m.positions.is_cuda() && m.positions.is_contiguous() && m.positions.scalar_type() == torch::kFloat32 &&
+                    m.sh_coeffs.is_contiguous() && m.opacities.is_contiguous() && m.scales.is_contiguous() &&
+                    m.rotations.is_contiguous(),
+                "MCMC ops update the model in place: tensors must be contiguous float32 on CUDA");
+}
+}  // namespace
+
+MCMCStats MCMCController::relocate(GaussianModel& model, int step) {
+    torch::NoGradGuard no_grad;
+    MCMCStats stats;
+    const int64_t n = model.num_gaussians();
+    stats.num_total = static_cast<int>(n);
+    if (n == 0) return stats;
+    check_plain(model);
+    cugs_handle_t* h = handle_for(model.positions);
+    const int64_t max_relocate = static_cast<int>(config_.relocate_cap * n);
+    auto temp = torch::empty({static_cast<int64_t>(cugs_b200_mcmc_relocate_temp_bytes(n))},
+                             torch::TensorOptions().dtype(torch::kUInt8).device(model.positions.device()));
+    int64_t counts[2] = {0, 0};
+    CUGS_CALL(h, cugs_b200_mcmc_relocate(h, current_stream(model.positions), n, static_cast<int>(model.sh_coeffs.size(2)),
+                                         fp(model.positions), fp(model.sh_coeffs), fp(model.opacities), fp(model.scales),
+                                         fp(model.rotations), config_.dead_opacity_threshold, max_relocate, scene_extent_,
+                                         kMcmcSeed, static_cast<uint32_t>(step), nullptr, nullptr, counts, temp.data_ptr(),
+                                         temp.numel()));
+    stats.num_dead = static_cast<int>(counts[0]);
+    stats.num_relocated = static_cast<int>(counts[1]);
+    return stats;
+}
+
+void MCMCController::inject_noise(GaussianModel& model, int step) {
+    torch::NoGradGuard no_grad;
+    const int64_t n = model.num_gaussians();
+    if (n == 0) return;
+    check_plain(model);
+    cugs_handle_t* h = handle_for(model.positions);
+    CUGS_CALL(h, cugs_b200_mcmc_inject_noise(h, current_stream(model.positions), n, fp(model.positions), fp(model.scales),
+                                             fp(model.opacities), noise_lr(step), config_.noise_gate_k,
+                                             config_.noise_gate_t, kMcmcSeed, static_cast<uint32_t>(step), nullptr));
+}
+
+float MCMCController::compute_regularization(const GaussianModel& model, torch::Tensor& reg_dL_dopacities,
+                                             torch::Tensor& reg_dL_dscales) {
+    // loss = lambda_o mean(sigmoid(opacity)) + lambda_s mean(exp(scale)); its gradient in closed form instead of
+    // two autograd graphs. (FusedAdam can also add it inside its own launch: cugs_b200_adam_step_mcmc.)
+    torch::NoGradGuard no_grad;
+    const auto sg = torch::sigmoid(model.opacities);
+    const auto es = torch::exp(model.scales);
+    reg_dL_dopacities = sg * (1.0f - sg) * (config_.lambda_opacity / static_cast<float>(sg.numel()));
+    reg_dL_dscales = es * (config_.lambda_scale / static_cast<float>(es.numel()));
+    return (config_.lambda_opacity * sg.mean() + config_.lambda_scale * es.mean()).item<float>();
 }
 
 }  // namespace cugs
