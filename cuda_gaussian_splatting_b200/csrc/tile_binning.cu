@@ -170,8 +170,12 @@ k_tile_hist_to_ranges(int num_tiles, const unsigned* __restrict__ tile_hist, int
 constexpr size_t kPkSmemBytes = (size_t)kPkTile * 8 + (size_t)kPkRadix * 8 + (size_t)kPkWarps * kPkRadix * 4 +
                                 (size_t)kPkRadix * 4 + 64;
 
-template <bool kLast>
-__global__ void __launch_bounds__(kPkThreads)
+#ifndef CUGS_OS_MINBLOCKS
+#define CUGS_OS_MINBLOCKS 3  // 40 registers (12 B of spills): 3 x 512 threads per SM, sort stage 0.531 -> 0.510 ms (4 blocks: 0.544)
+#endif
+// kBits = digit width of the pass (6, 7, 8), 0 = run-time width
+template <bool kLast, int kBits>
+__global__ void __launch_bounds__(kPkThreads, CUGS_OS_MINBLOCKS)
 k_onesweep_packed(int64_t n, const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
                   int* __restrict__ out32, const unsigned* __restrict__ bin_base,
                   volatile unsigned* __restrict__ lookback, unsigned* __restrict__ ticket, int shift, int bits) {
@@ -214,7 +218,7 @@ k_onesweep_packed(int64_t n, const uint64_t* __restrict__ in, uint64_t* __restri
 #pragma unroll
     for (int i = 0; i < kPkItems; ++i) {
         const unsigned d = pk_digit(e[i], shift, mask);
-        const unsigned peers = match_digit(d, bits);
+        const unsigned peers = kBits > 0 ? match_digit_fixed<(kBits > 0 ? kBits : 1)>(d) : match_digit(d, bits);
         const int leader = __ffs(peers) - 1;
         unsigned old = 0;
         if (lane == leader) old = atomicAdd(&s_warp_hist[warp][d], (unsigned)__popc(peers));
@@ -455,21 +459,29 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
         k_tile_hist_to_ranges<<<1, 1024, 0, s>>>(num_tiles, tile_hist, tile_ranges);
         CUGS_LAUNCH_CHECK(h, "k_tile_hist_to_ranges");
     }
-    CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_onesweep_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kPkSmemBytes));
-    CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_onesweep_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kPkSmemBytes));
     uint64_t* src = a;
     uint64_t* dst = b;
     for (int ps = 0; ps < plan.passes; ++ps) {
         const bool last = (ps == plan.passes - 1) && out32_last != nullptr;
         unsigned* lb = lookback + (size_t)ps * tiles * kPkRadix;
-        if (last)
-            k_onesweep_packed<true><<<(unsigned)tiles, kPkThreads, kPkSmemBytes, s>>>(
-                n, src, dst, out32_last, digit_hist + ps * kPkRadix, lb, tickets + ps, plan.shift[ps], plan.bits[ps]);
-        else
-            k_onesweep_packed<false><<<(unsigned)tiles, kPkThreads, kPkSmemBytes, s>>>(
-                n, src, dst, nullptr, digit_hist + ps * kPkRadix, lb, tickets + ps, plan.shift[ps], plan.bits[ps]);
+#define CUGS_OS_LAUNCH(LAST, BITS)                                                                              \
+    do {                                                                                                        \
+        CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_onesweep_packed<LAST, BITS>,                                    \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPkSmemBytes)); \
+        k_onesweep_packed<LAST, BITS><<<(unsigned)tiles, kPkThreads, kPkSmemBytes, s>>>(                        \
+            n, src, dst, LAST ? out32_last : nullptr, digit_hist + ps * kPkRadix, lb, tickets + ps,             \
+            plan.shift[ps], plan.bits[ps]);                                                                     \
+    } while (0)
+#define CUGS_OS_DISPATCH(LAST)                          \
+    switch (plan.bits[ps]) {                            \
+        case 8: CUGS_OS_LAUNCH(LAST, 8); break;         \
+        case 7: CUGS_OS_LAUNCH(LAST, 7); break;         \
+        case 6: CUGS_OS_LAUNCH(LAST, 6); break;         \
+        default: CUGS_OS_LAUNCH(LAST, 0); break;        \
+    }
+        if (last) { CUGS_OS_DISPATCH(true) } else { CUGS_OS_DISPATCH(false) }
+#undef CUGS_OS_DISPATCH
+#undef CUGS_OS_LAUNCH
         CUGS_LAUNCH_CHECK(h, "k_onesweep_packed");
         uint64_t* t = src; src = dst; dst = t;
     }
