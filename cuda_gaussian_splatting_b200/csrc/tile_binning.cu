@@ -281,17 +281,22 @@ k_onesweep_packed(int64_t n, const uint64_t* __restrict__ in, uint64_t* __restri
                     if (j - k >= 0) v = lookback[(size_t)(j - k) * kPkRadix + tid];
                     st[k] = v;
                 }
-                int consumed = 0;
-                bool stop = false;
+                // branch-free consume: the flags are the two top bits, so "published" is v >= 1<<30 and
+                // "inclusive prefix" is v >= 1<<31. Take entries up to and including the first prefix, or
+                // up to (excluding) the first one that is not published yet.
+                unsigned pubm = 0, prem = 0;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    if (!stop) {
-                        if (st[k] & kPkPrefix) { excl += st[k] & kPkValue; done = true; stop = true; }
-                        else if (st[k] & kPkAggregate) { excl += st[k] & kPkValue; ++consumed; }
-                        else stop = true;  // not published yet: retry from here
-                    }
+                    pubm |= (st[k] >= (1u << 30)) ? (1u << k) : 0u;
+                    prem |= (st[k] >= (2u << 30)) ? (1u << k) : 0u;
                 }
-                j -= consumed;
+                const int first_unpub = __ffs(~pubm) - 1;            // 8 when all eight are published
+                const int first_pref = prem ? __ffs(prem) - 1 : 8;
+                done = first_pref < first_unpub;
+                const int take = done ? first_pref + 1 : min(first_unpub, 8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) excl += (k < take) ? (st[k] & kPkValue) : 0u;
+                j -= take;
             }
             lb[tid] = kPkPrefix | ((excl + bin_count) & kPkValue);
         }
