@@ -93,13 +93,26 @@ k_packed_histogram(int64_t n, const uint64_t* __restrict__ elts, PackedPlan plan
             const int64_t idx = base + (int64_t)i * kPkHistThreads + threadIdx.x;
             if (idx < n) {
                 const unsigned key = (unsigned)(e[i] >> 32);
-                for (int ps = 0; ps < plan.passes; ++ps)
-                    atomicAdd(&s_hist[ps * kPkRadix + ((key >> plan.shift[ps]) & ((1u << plan.bits[ps]) - 1))], 1u);
-                if (kTileHist && key < (unsigned)num_tiles) atomicAdd(&s_tile[key], 1u);
+                if (kTileHist && key < (unsigned)num_tiles) {
+                    // one atomic per pair: the digit histograms are folded out of the tile histogram below
+                    atomicAdd(&s_tile[key], 1u);
+                } else {
+                    for (int ps = 0; ps < plan.passes; ++ps)
+                        atomicAdd(&s_hist[ps * kPkRadix + ((key >> plan.shift[ps]) & ((1u << plan.bits[ps]) - 1))], 1u);
+                }
             }
         }
     }
     __syncthreads();
+    if (kTileHist) {  // every digit of a key is a function of its tile id
+        for (int b = threadIdx.x; b < num_tiles; b += kPkHistThreads) {
+            const unsigned c = s_tile[b];
+            if (c)
+                for (int ps = 0; ps < plan.passes; ++ps)
+                    atomicAdd(&s_hist[ps * kPkRadix + (((unsigned)b >> plan.shift[ps]) & ((1u << plan.bits[ps]) - 1))], c);
+        }
+        __syncthreads();
+    }
     for (int b = threadIdx.x; b < plan.passes * kPkRadix; b += kPkHistThreads) {
         const unsigned c = s_hist[b];
         if (c) atomicAdd(&digit_hist[b], c);
@@ -442,7 +455,7 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
     unsigned* lookback = tile_hist + align_up((size_t)(num_tiles > 0 ? num_tiles : 1) * 4, 256) / 4;
     CUGS_CUDA_TRY(h, cudaMemsetAsync(temp, 0, need, s));
 
-    int hist_blocks = h->sm_count * 2;
+    int hist_blocks = h->sm_count * 3;  // 3 x 512 threads per SM (40 registers, <= 36 KB of shared memory)
     const int64_t hist_tile = (int64_t)kPkHistThreads * kPkHistItems;
     if ((int64_t)hist_blocks * hist_tile > n) hist_blocks = (int)((n + hist_tile - 1) / hist_tile);
     const bool want_ranges = tile_ranges != nullptr && num_tiles > 0;
