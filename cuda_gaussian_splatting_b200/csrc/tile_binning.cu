@@ -387,6 +387,9 @@ k_duplicate_sorted(int64_t n, int width, int height, int ntx, int nty,
     const int wpre = incl - reserved;
     const int total = __shfl_sync(kFull, incl, 31);
     const int64_t base = __shfl_sync(kFull, off, 0);
+    // j / w without a per-pair integer division: one reciprocal per Gaussian, exact for j * w < 2^32
+    // (j < number of tiles <= 48 K, w <= tiles per row)
+    const unsigned magic = (w > 1) ? 0xFFFFFFFFu / (unsigned)w + 1u : 0u;
 
     for (int k0 = 0; k0 < total; k0 += 32) {
         const int k = k0 + lane;
@@ -400,13 +403,15 @@ k_duplicate_sorted(int64_t n, int width, int height, int ntx, int nty,
         const int j = k - __shfl_sync(kFull, wpre, owner);
         const int o_emit = __shfl_sync(kFull, emit, owner);
         const int o_w = __shfl_sync(kFull, w, owner);
+        const unsigned o_magic = __shfl_sync(kFull, magic, owner);
         const int o_tx0 = __shfl_sync(kFull, tx0, owner);
         const int o_ty0 = __shfl_sync(kFull, ty0, owner);
         const unsigned o_g = __shfl_sync(kFull, g, owner);
         if (k < total && base + k < p) {
             uint64_t pair = 0;
             if (j < o_emit) {
-                const int ty = o_ty0 + j / o_w, tx = o_tx0 + j % o_w;  // ty outer, tx inner (:63-64)
+                const int q = (o_w > 1) ? (int)__umulhi((unsigned)j, o_magic) : j;   // j / o_w
+                const int ty = o_ty0 + q, tx = o_tx0 + (j - q * o_w);  // ty outer, tx inner (:63-64)
                 pair = ((uint64_t)(unsigned)(ty * ntx + tx) << 32) | (uint64_t)o_g;
             }
             __stcs(pairs + base + k, pair);
