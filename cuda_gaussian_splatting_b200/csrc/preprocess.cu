@@ -133,7 +133,9 @@ __device__ __forceinline__ int radius_from_cov(const float c2[3], float det) {
 #ifndef CUGS_PRE_MINBLOCKS
 #define CUGS_PRE_MINBLOCKS 4  // 64 registers (52 B of spills), 4 x 256 threads per SM: measured 0.196 ms vs 0.214 ms at 3 blocks
 #endif
-template <bool kVecSH, bool kFull>
+// kDeg3: the active SH degree is 3 (the steady state of training): basis and dot products without the
+// run-time degree tests.
+template <bool kVecSH, bool kFull, bool kDeg3>
 __global__ void __launch_bounds__(kPreBlock, CUGS_PRE_MINBLOCKS)
 k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                  const float* __restrict__ rotations, const float* __restrict__ scales,
@@ -164,9 +166,9 @@ k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
     {
         float dx, dy, dz;
         view_dir(px, py, pz, vp.cam, dx, dy, dz);
-        sh_basis(vp.deg, dx, dy, dz, Y);
+        sh_basis(kDeg3 ? 3 : vp.deg, dx, dy, dz, Y);
     }
-    const int na = (vp.deg + 1) * (vp.deg + 1);
+    const int na = kDeg3 ? 16 : (vp.deg + 1) * (vp.deg + 1);
 
     if (kVecSH) {
         float4* row = reinterpret_cast<float4*>(&sY[warp][lane * kYStride]);
@@ -311,7 +313,7 @@ k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
 // ================================================================================================
 // Backward
 // ================================================================================================
-template <bool kVecSH>
+template <bool kVecSH, bool kDeg3>
 __global__ void __launch_bounds__(kPreBlock)
 k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                  const float* __restrict__ rotations, const float* __restrict__ scales,
@@ -378,9 +380,9 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
     {
         float dx, dy, dz;
         view_dir(px, py, pz, vp.cam, dx, dy, dz);
-        sh_basis(vp.deg, dx, dy, dz, Y);
+        sh_basis(kDeg3 ? 3 : vp.deg, dx, dy, dz, Y);
     }
-    const int na = (vp.deg + 1) * (vp.deg + 1);
+    const int na = kDeg3 ? 16 : (vp.deg + 1) * (vp.deg + 1);
     if (kVecSH) {
         float4* row = reinterpret_cast<float4*>(&sY[warp][lane * kYStride]);
         row[0] = make_float4(Y[0], Y[1], Y[2], Y[3]);
@@ -662,14 +664,16 @@ int cugs_preprocess_fwd_launch(cugs_handle_t* h, void* stream, int64_t n, const 
     const ViewParams vp = make_view_params(v);
     const unsigned grid = (unsigned)((n + kPreBlock - 1) / kPreBlock);
     cudaStream_t s = (cudaStream_t)stream;
-#define CUGS_LAUNCH_PRE(VEC, FULL)                                                                         \
-    k_preprocess_fwd<VEC, FULL><<<grid, kPreBlock, 0, s>>>(                                                \
+#define CUGS_LAUNCH_PRE(VEC, FULL, DEG3)                                                                   \
+    k_preprocess_fwd<VEC, FULL, DEG3><<<grid, kPreBlock, 0, s>>>(                                          \
         n, vp, positions, rotations, scales, opacities, sh_coeffs, means_2d, depths, cov_2d_inv, radii,    \
         tiles_touched, rgb, opacities_act, reinterpret_cast<float4*>(packed), depth_minmax, gsort)
-    if (v->num_coeffs == 16) {
-        if (all) CUGS_LAUNCH_PRE(true, true); else CUGS_LAUNCH_PRE(true, false);
+    if (v->num_coeffs == 16 && v->active_sh_degree == 3) {
+        if (all) CUGS_LAUNCH_PRE(true, true, true); else CUGS_LAUNCH_PRE(true, false, true);
+    } else if (v->num_coeffs == 16) {
+        if (all) CUGS_LAUNCH_PRE(true, true, false); else CUGS_LAUNCH_PRE(true, false, false);
     } else {
-        if (all) CUGS_LAUNCH_PRE(false, true); else CUGS_LAUNCH_PRE(false, false);
+        if (all) CUGS_LAUNCH_PRE(false, true, false); else CUGS_LAUNCH_PRE(false, false, false);
     }
 #undef CUGS_LAUNCH_PRE
     CUGS_LAUNCH_CHECK(h, "k_preprocess_fwd");
@@ -688,15 +692,22 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
                                bool accumulate, int32_t* touch_mask, bool sparse_rows) {
     const ViewParams vp = make_view_params(v);
     const unsigned grid = (unsigned)((n + kPreBlock - 1) / kPreBlock);
-    if (v->num_coeffs == 16)
-        k_preprocess_bwd<true><<<grid, kPreBlock, 0, s>>>(
+    if (v->num_coeffs == 16 && v->active_sh_degree == 3)
+        k_preprocess_bwd<true, true><<<grid, kPreBlock, 0, s>>>(
+            n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
+            dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
+            dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
+            reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate, touch_mask,
+            sparse_rows && touch_mask != nullptr);
+    else if (v->num_coeffs == 16)
+        k_preprocess_bwd<true, false><<<grid, kPreBlock, 0, s>>>(
             n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
             dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
             dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
             reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate, touch_mask,
             sparse_rows && touch_mask != nullptr);
     else
-        k_preprocess_bwd<false><<<grid, kPreBlock, 0, s>>>(
+        k_preprocess_bwd<false, false><<<grid, kPreBlock, 0, s>>>(
             n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
             dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
             dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
