@@ -67,7 +67,8 @@ __device__ __forceinline__ unsigned pk_digit(uint64_t e, int shift, unsigned mas
 // ------------------------------------------------------------------------------------------------
 // histograms: digit histograms of every pass (+ optionally the full per-tile histogram) in ONE read
 // ------------------------------------------------------------------------------------------------
-constexpr int kPkHistThreads = 512;
+constexpr int kPkHistThreads = 1024;  // one fat block per SM: the flush of the tile histogram (one global atomic per
+                                      // block and non-empty tile) is what bounds the pair histogram, not its body
 constexpr int kPkHistItems = 8;
 
 template <bool kTileHist>
@@ -460,7 +461,7 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
     unsigned* lookback = tile_hist + align_up((size_t)(num_tiles > 0 ? num_tiles : 1) * 4, 256) / 4;
     CUGS_CUDA_TRY(h, cudaMemsetAsync(temp, 0, need, s));
 
-    int hist_blocks = h->sm_count * 3;  // 3 x 512 threads per SM (40 registers, <= 36 KB of shared memory)
+    int hist_blocks = h->sm_count;  // 148 x 8160 global atomics in the flush instead of 444 x 8160
     const int64_t hist_tile = (int64_t)kPkHistThreads * kPkHistItems;
     if ((int64_t)hist_blocks * hist_tile > n) hist_blocks = (int)((n + hist_tile - 1) / hist_tile);
     const bool want_ranges = tile_ranges != nullptr && num_tiles > 0;
