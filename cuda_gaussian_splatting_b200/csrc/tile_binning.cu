@@ -148,32 +148,27 @@ __global__ void __launch_bounds__(kPkRadix) k_packed_scan_bins(unsigned* __restr
 // without pairs stay {0, 0}). One block; num_tiles is at most a few ten thousand.
 __global__ void __launch_bounds__(1024)
 k_tile_hist_to_ranges(int num_tiles, const unsigned* __restrict__ tile_hist, int* __restrict__ ranges) {
+    // one pass: every thread owns `per` consecutive tiles (8 at 1080p), so the block scans once
     __shared__ unsigned s_warp[32];
-    __shared__ unsigned s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < num_tiles; base += 1024) {
-        const int t = base + threadIdx.x;
-        const unsigned c = (t < num_tiles) ? tile_hist[t] : 0u;
-        unsigned incl = c;
+    const int per = (num_tiles + 1023) / 1024;
+    const int t0 = threadIdx.x * per, t1 = min(num_tiles, t0 + per);
+    unsigned sum = 0;
+    for (int t = t0; t < t1; ++t) sum += tile_hist[t];
+    unsigned incl = sum;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned o = __shfl_up_sync(kFull, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        unsigned off = s_carry;
-        for (int w = 0; w < warp; ++w) off += s_warp[w];
-        const unsigned start = off + incl - c;
-        if (t < num_tiles) {
-            ranges[2 * t + 0] = c ? (int)start : 0;
-            ranges[2 * t + 1] = c ? (int)(start + c) : 0;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = off + incl;
-        __syncthreads();
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned start = incl - sum;
+    for (int w = 0; w < warp; ++w) start += s_warp[w];
+    for (int t = t0; t < t1; ++t) {
+        const unsigned c = tile_hist[t];
+        reinterpret_cast<int2*>(ranges)[t] = c ? make_int2((int)start, (int)(start + c)) : make_int2(0, 0);
+        start += c;
     }
 }
 
