@@ -33,7 +33,7 @@ def write_gaussian_ply(path: Union[str, Path], model: GaussianModel) -> bool:
     rows = np.zeros((n, len(names)), dtype="<f4")
     rows[:, 0:3] = pos                                   # normals stay zero
     rows[:, 6:9] = sh[:, :, 0]                           # DC: f_dc_ch
-    rows[:, 9:9 + 3 * (c - 1)] = sh[:, :, 1:].transpose(0, 2, 1).reshape(n, -1)  # [k][ch] interleaved
+    rows[:, 9:9 + 3 * (c - 1)] = sh[:, :, 1:].transpose(0, 2, 1).reshape(n, 3 * (c - 1))  # [k][ch] interleaved
     o = 9 + 3 * (c - 1)
     rows[:, o] = opa[:, 0]
     rows[:, o + 1:o + 4] = scl
@@ -91,5 +91,6 @@ def read_gaussian_ply(path: Union[str, Path], device="cpu") -> GaussianModel:
     opa = col("opacity")[:, None]
     scl = np.stack([col(f"scale_{i}") for i in range(3)], axis=1)
     rot = np.stack([col(f"rot_{i}") for i in range(4)], axis=1)
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+    # (np.array copies: the columns are views of the read-only file buffer, a model must own writable memory)
+    t = lambda a: torch.from_numpy(np.array(a, dtype=np.float32, order="C")).to(device)
     return GaussianModel(t(pos), t(sh), t(opa), t(rot), t(scl))

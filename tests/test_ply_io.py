@@ -61,3 +61,21 @@ def test_invalid_model_is_not_written(tmp_path):
     m = model_of(4)
     m.opacities = m.opacities[:-1]
     assert cugs.write_gaussian_ply(tmp_path / "x.ply", m) is False
+
+
+@pytest.mark.parametrize("degree,n", [(3, 50), (0, 20), (2, 30), (3, 0)])
+def test_roundtrip(tmp_path, degree, n):  # tests/test_gaussian_model.cpp:98-160 (degrees 3 / 0 / 2, empty model)
+    import torch
+    c = (degree + 1) ** 2
+    g = torch.Generator().manual_seed(degree * 100 + n)
+    m = cugs.GaussianModel(torch.randn(n, 3, generator=g), torch.randn(n, 3, c, generator=g),
+                           torch.randn(n, 1, generator=g), torch.randn(n, 4, generator=g),
+                           torch.randn(n, 3, generator=g))
+    path = tmp_path / f"d{degree}_{n}.ply"
+    assert cugs.write_gaussian_ply(path, m) and path.exists()
+    back = cugs.read_gaussian_ply(path)
+    assert back.is_valid() and back.num_gaussians() == n and back.max_sh_degree() == degree
+    for a, b in zip((m.positions, m.sh_coeffs, m.opacities, m.rotations, m.scales),
+                    (back.positions, back.sh_coeffs, back.opacities, back.rotations, back.scales)):
+        assert torch.equal(a, b)          # float32 in, float32 on disk: exact
+    back.positions.add_(1.0)              # the loaded model owns writable memory
