@@ -43,3 +43,17 @@ def test_native_thresholds_follow_the_reference_arithmetic():
     assert ctrl._native_config(10**6).apply_size_pruning == 1
     off = cugs.DensificationController(cugs.DensificationConfig(opacity_reset_every=0), 1.0, 0, "cpu")
     assert off._native_config(10**6).apply_size_pruning == 0
+
+
+def test_budget_cap_keeps_the_highest_average_gradients():  # densification.cpp:128-137, :196-213
+    import torch
+    ctrl = cugs.DensificationController(cugs.DensificationConfig(max_gaussians=12), 1.0, 10, "cpu")
+    ctrl.grad_accum = torch.tensor([9., 1., 8., 2., 7., 3., 6., 4., 5., 0.])
+    ctrl.grad_count = torch.tensor([1., 1., 2., 1., 1., 1., 1., 1., 1., 0.])     # averages: 9 1 4 2 7 3 6 4 5 0
+    flags = torch.tensor([3, 3, 3, 1, 3, 5, 5, 1, 3, 1], dtype=torch.uint8)       # KEEP=1, CLONE=2, SPLIT=4
+    ctrl._cap(flags, 2, 3)                                                         # three best clone candidates
+    assert flags.tolist() == [3, 1, 1, 1, 3, 5, 5, 1, 3, 1]                        # rows 0 (9), 4 (7), 8 (5) stay
+    ctrl._cap(flags, 4, 1)                                                         # one split: row 6 (6) beats row 5 (3)
+    assert flags.tolist() == [3, 1, 1, 1, 3, 1, 5, 1, 3, 1]
+    ctrl._cap(flags, 2, 0)                                                         # no budget: all candidates dropped
+    assert flags.tolist() == [1, 1, 1, 1, 1, 1, 5, 1, 1, 1]
