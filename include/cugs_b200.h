@@ -21,8 +21,9 @@
  * word through which render_plan returns P, the error string and the optional stage-timing
  * events); use one handle per host thread. Every kernel is launched on the stream passed in; the
  * only blocking calls are cugs_b200_render_plan and cugs_b200_scan with total_host != NULL (one
- * cudaStreamSynchronize each, the read the reference does at rasterizer/sorting.cu:146) and
- * cugs_b200_get_stage_ms. Two frames may be in flight on two streams through one handle as long as
+ * cudaStreamSynchronize each, the read the reference does at rasterizer/sorting.cu:146),
+ * cugs_b200_densify_classify and cugs_b200_mcmc_relocate with counts_host != NULL (the counts the
+ * reference reads with .item()), and cugs_b200_get_stage_ms. Two frames may be in flight on two streams through one handle as long as
  * each frame's render_finish is called before the next frame's render_plan (bench.py does this).
  * Limits: P < 2^30 pairs, N < 2^31 Gaussians, at most 48 K tiles (7680x4096) on the fused path
  * (CUGS_ERR_UNSUPPORTED otherwise); the stage functions have no tile limit.
