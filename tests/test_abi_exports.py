@@ -61,3 +61,77 @@ def test_no_cpu_fallback_without_gpu():
     model = m.GaussianModel(*(torch.from_numpy(a) for a in (s.positions, s.sh_coeffs, s.opacities, s.rotations, s.scales)))
     with pytest.raises(RuntimeError):
         m.render(model, s.camera, m.RenderSettings())
+
+
+def header_prototypes():
+    """name -> (return type, [parameter declarations]) for every prototype of the header."""
+    text = (ROOT / "include" / "cugs_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"([\w\s\*]+?)\b(cugs_b200_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        ret, name, params = m.group(1).strip(), m.group(2), " ".join(m.group(3).split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        protos[name] = (ret, plist)
+    return protos
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Arity and the pointer / integer / float class of every parameter: a ctypes table that drifts from the
+    header corrupts arguments silently."""
+    import ctypes as C
+    from cuda_gaussian_splatting_b200 import _lib
+    protos = header_prototypes()
+    assert set(protos) == set(declared_symbols())
+    pointer_types = (C.c_void_p, C.c_char_p)
+
+    def kind(ct):
+        if ct is None:
+            return "void"
+        if ct in pointer_types or isinstance(ct, type) and issubclass(ct, (C._Pointer, C.Array)):
+            return "ptr"
+        if ct in (C.c_float, C.c_double):
+            return "float"
+        return "int"
+
+    def ckind(decl):
+        if "*" in decl or "[" in decl:
+            return "ptr"
+        if re.search(r"\b(float|double)\b", decl):
+            return "float"
+        return "int"
+
+    for name, (ret, plist) in protos.items():
+        res, args = _lib.SIGNATURES[name]
+        assert len(args) == len(plist), f"{name}: header has {len(plist)} parameters, ctypes table {len(args)}"
+        for i, (decl, ct) in enumerate(zip(plist, args)):
+            assert ckind(decl) == kind(ct), f"{name}: parameter {i} `{decl}` is bound as {ct}"
+        want = "void" if ret == "void" else ("ptr" if "*" in ret else "int")
+        assert kind(res) == want, f"{name}: return type `{ret}` is bound as {res}"
+        # 64-bit sizes must not be bound as 32-bit ints
+        for decl, ct in zip(plist, args):
+            if re.search(r"\b(int64_t|uint64_t|size_t)\b", decl) and "*" not in decl:
+                assert C.sizeof(ct) == 8, f"{name}: `{decl}` is bound as a {C.sizeof(ct)}-byte integer"
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of the two structs that cross the boundary, as gcc lays them out, against the ctypes
+    mirrors in _lib.py (also proves the header is plain C)."""
+    import ctypes as C
+    import subprocess
+    from cuda_gaussian_splatting_b200 import _lib
+    structs = {"cugs_view_t": _lib.CugsView, "cugs_densify_config_t": _lib.CugsDensifyConfig}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "cugs_b200.h"', "int main(void) {"]
+    for cname, ct in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
