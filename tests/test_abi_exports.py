@@ -135,3 +135,24 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         assert int(got[cname]) == C.sizeof(ct), cname
         for fname, _ in ct._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
+
+
+def test_error_convention_without_a_device():
+    """0 = ok, < 0 = argument error (CUGS_ERR_*), > 0 = cudaError_t; nothing throws, nothing crashes on a
+    null handle (SURVEY 8b error conventions)."""
+    import ctypes as C
+    import torch
+    from cuda_gaussian_splatting_b200 import _lib
+    lib = _lib.load_library()
+    p = C.c_int64(0)
+    assert lib.cugs_b200_scan(None, None, 10, None, None, None, C.byref(p), None, 0) == -1
+    assert lib.cugs_b200_render_plan(None, None, 10, None, *([None] * 11), None, 0, C.byref(p)) == -1
+    assert lib.cugs_b200_accumulate_stats(None, None, 10, None, None, None, None, None) == -1
+    assert lib.cugs_b200_densify_classify(None, None, 10, None, None, None, None, None, None, None, C.byref(p),
+                                          None, 0) == -1
+    assert lib.cugs_b200_mcmc_relocate(None, None, 10, 16, None, None, None, None, None, 0.005, 1, 1.0, 1, 1, None,
+                                       None, None, None, 0) == -1
+    assert lib.cugs_b200_last_error(None) == b"null handle"
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert lib.cugs_b200_create(0, C.byref(h)) > 0 and not h.value      # a cudaError_t, no handle, no fallback
