@@ -156,3 +156,18 @@ def test_error_convention_without_a_device():
     if not torch.cuda.is_available():
         h = C.c_void_p()
         assert lib.cugs_b200_create(0, C.byref(h)) > 0 and not h.value      # a cudaError_t, no handle, no fallback
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing in the package, the wrapper or the C sources may import,
+    link or open it (bench.py and __graft_entry__.smoke() may, as checker / CPU baseline only)."""
+    offenders = []
+    for path in list((ROOT / "cuda_gaussian_splatting_b200").rglob("*")) + list((ROOT / "wrapper").rglob("*")) + \
+            list((ROOT / "include").rglob("*")):
+        if path.is_file() and path.suffix in {".py", ".cu", ".cuh", ".cpp", ".h", ".hpp"}:
+            text = path.read_text(errors="replace")
+            if re.search(r"\boracle_py\b|\bcugs_oracle\b|\bcugs_ref\b|from\s+oracle|import\s+oracle|oracle/_ref", text):
+                offenders.append(str(path.relative_to(ROOT)))
+    assert not offenders, offenders
+    build_sh = (ROOT / "build.sh").read_text()
+    assert "oracle" not in build_sh
