@@ -18,5 +18,5 @@ for f in preprocess binning radix_sort tile_binning blend train_ops grad_exchang
   fi
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
-$NVCC -shared -o "$OUT/$LIBNAME" $OBJ/preprocess.o $OBJ/binning.o $OBJ/radix_sort.o $OBJ/tile_binning.o $OBJ/blend.o $OBJ/train_ops.o $OBJ/grad_exchange.o $OBJ/density_control.o $OBJ/api.o -lcudart
+$NVCC -Wno-deprecated-gpu-targets -shared -o "$OUT/$LIBNAME" $OBJ/preprocess.o $OBJ/binning.o $OBJ/radix_sort.o $OBJ/tile_binning.o $OBJ/blend.o $OBJ/train_ops.o $OBJ/grad_exchange.o $OBJ/density_control.o $OBJ/api.o -lcudart
 echo "built $OUT/$LIBNAME"
