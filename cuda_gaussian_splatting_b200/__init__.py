@@ -10,7 +10,7 @@ from .rasterizer import (  # noqa: F401
     BackwardOutput, CameraInfo, ForwardOutput, FrameBuffers, GaussianModel, ProjectionBackwardOutput,
     ProjectionOutput, RasterizeBackwardOutput, RenderOutput, RenderSettings, SortingOutput,
     evaluate_sh_backward_cuda, evaluate_sh_cuda, project_backward, project_gaussians, rasterize_backward,
-    rasterize_forward, render, render_backward, render_image, ImageBuffers, sort_gaussians,
+    rasterize_forward, render, render_backward, render_image, ImageBuffers, sort_gaussians, count_evaluations,
 )
 from .training import (  # noqa: F401
     AdamConfig, DensificationStats, FusedAdam, MCMCConfig, PositionLRConfig, mcmc_inject_noise, mcmc_noise_lr, SyntheticTrainer, TargetUploader, TrainConfig, active_sh_degree_for_step, combined_loss,

@@ -66,13 +66,19 @@ SIGNATURES = {
     "cugs_b200_duplicate_with_keys": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "cugs_b200_sort_temp_bytes": (_SZ, [_I64]),
     "cugs_b200_sort_pairs": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P, _P, _P, _SZ]),
+    "cugs_b200_sort_packed_passes": (_INT, [_INT]),
+    "cugs_b200_sort_packed_temp_bytes": (_SZ, [_I64, _INT, _INT]),
+    "cugs_b200_sort_packed": (_INT, [_P, _P, _I64, _INT, _P, _P, _P, _INT, _P, _P, _SZ, _P]),
     "cugs_b200_tile_ranges": (_INT, [_P, _P, _I64, _P, _INT, _P]),
     "cugs_b200_blend_fwd": (_INT, [_P, _P, _VP] + [_P] * 10),
     "cugs_b200_blend_bwd": (_INT, [_P, _P, _I64, _VP] + [_P] * 15),
+    "cugs_b200_count_evaluations": (_INT, [_P, _P, _VP] + [_P] * 7),
     "cugs_b200_preprocess_bwd": (_INT, [_P, _P, _I64, _VP] + [_P] * 19),
     "cugs_b200_render_workspace_bytes": (_SZ, [_I64, _I64]),
+    "cugs_b200_render_forward": (_INT, [_P, _P, _I64, _I64, _VP] + [_P] * 16 + [_P, _SZ, _P, _SZ, _P]),
     "cugs_b200_render_plan": (_INT, [_P, _P, _I64, _VP] + [_P] * 11 + [_P, _SZ, C.POINTER(_I64)]),
-    "cugs_b200_render_finish": (_INT, [_P, _P, _I64, _I64, _VP] + [_P] * 11 + [_P, _SZ]),
+    "cugs_b200_render_pair_scratch_bytes": (_SZ, [_I64]),
+    "cugs_b200_render_finish": (_INT, [_P, _P, _I64, _I64, _VP] + [_P] * 11 + [_P, _SZ, _P, _SZ]),
     "cugs_b200_render_backward": (_INT, [_P, _P, _I64, _VP] + [_P] * 25 + [_INT, _P, _SZ]),
     "cugs_b200_compact_grad_floats": (_I64, [_I64, _INT]),
     "cugs_b200_gather_grad_rows": (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, C.POINTER(_P), _P, _P]),
@@ -81,7 +87,7 @@ SIGNATURES = {
     "cugs_b200_set_stage_timing": (_INT, [_P, _INT]),
     "cugs_b200_get_stage_ms": (_INT, [_P, C.POINTER(_F)]),
     "cugs_b200_loss_workspace_bytes": (_SZ, [_INT, _INT]),
-    "cugs_b200_loss_l1_ssim": (_INT, [_P, _P, _INT, _INT, _F, _P, _P, _P, _P, _P, _SZ, _P]),
+    "cugs_b200_loss_l1_ssim": (_INT, [_P, _P, _INT, _INT, _F, _INT, _P, _P, _P, _P, _P, _SZ, _P]),
     "cugs_b200_adam_step": (_INT, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
                                     C.POINTER(_I64), C.POINTER(_F), _F, _F, _F, _F, _F, _F]),
     "cugs_b200_adam_step_mcmc": (_INT, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),

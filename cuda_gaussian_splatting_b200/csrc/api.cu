@@ -11,21 +11,25 @@ using namespace cugs;
 
 // internal launchers implemented in the other translation units
 int cugs_scan_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, const int32_t* tiles_touched,
-                     int32_t* offsets, int64_t* total_dev, bool to_pinned, void* scan_temp,
+                     int32_t* offsets, int64_t* total_dev, int64_t* total_pinned, void* scan_temp,
                      const unsigned* aux_pair, const uint64_t* gather);
 int cugs_preprocess_fwd_launch(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
                                const float* positions, const float* rotations, const float* scales,
                                const float* opacities, const float* sh_coeffs, float* means_2d, float* depths,
                                float* cov_2d_inv, int32_t* radii, int32_t* tiles_touched, float* rgb,
                                float* opacities_act, float* packed, uint32_t* depth_minmax, uint64_t* gsort);
+// (depth_minmax is an optional output of the public stage function only; the fused path sorts all 32
+//  depth bits on the N Gaussians -- see DESIGN.md "what was costed and not built")
 // tile_binning.cu
 size_t cugs_packed_sort_temp_bytes(int64_t n, int passes, int num_tiles);
 int cugs_packed_passes(int key_bits);
 int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, uint64_t* a, uint64_t* b,
-                     int* out32_last, int num_tiles, int* tile_ranges, void* temp, size_t temp_bytes);
+                     int* out32_last, int num_tiles, int* tile_ranges, void* temp, size_t temp_bytes,
+                     const int64_t* n_dev);
 int cugs_duplicate_sorted(cugs_handle_t* h, cudaStream_t s, int64_t n, int width, int height,
                           const uint64_t* sorted_elts, const float* means_2d, const int32_t* radii,
-                          const int32_t* tiles_touched, const int32_t* offsets_sorted, int64_t p, uint64_t* pairs);
+                          const int32_t* tiles_touched, const int32_t* offsets_sorted, int64_t p, uint64_t* pairs,
+                          const int64_t* p_dev);
 int cugs_blend_bwd_accumulate(cugs_handle_t* h, cudaStream_t s, int64_t n, const cugs_view_t* v,
                               const int32_t* tile_ranges, const int32_t* gaussian_idx,
                               const float* means_2d, const float* cov_2d_inv, const float* rgb,
@@ -65,9 +69,11 @@ extern "C" int cugs_b200_create(int device, cugs_handle_t** out) {
     h->sm_count = prop.multiProcessorCount;
     h->err[0] = 0;
     h->pinned = nullptr;
-    e = cudaHostAlloc(reinterpret_cast<void**>(&h->pinned), 64, cudaHostAllocMapped | cudaHostAllocPortable);
+    e = cudaHostAlloc(reinterpret_cast<void**>(&h->pinned), kPinnedWords * sizeof(int64_t),
+                      cudaHostAllocMapped | cudaHostAllocPortable);
     if (e != cudaSuccess) { delete h; return (int)e; }
-    std::memset(h->pinned, 0, 64);
+    std::memset(h->pinned, 0, kPinnedWords * sizeof(int64_t));
+    h->pinned_seq = 0;
     h->timing = false;
     h->launches = 0;
     h->last_sort_passes = 0;
@@ -162,10 +168,26 @@ struct FrameWorkspace {
     uint64_t* pairs_b;      // [Pcap]
     void* psort_temp;
     size_t psort_temp_bytes;
-    size_t total_bytes;
+    size_t head_bytes, pair_bytes, total_bytes;
 };
 
 constexpr int kMaxTilesForWorkspace = 48 * 1024;  // tile histogram lives in shared memory (<= 192 KB)
+
+// the P-sized regions (pair ping-pong buffers + the pair sort's look-back state)
+void carve_pairs(FrameWorkspace& w, void* base, int64_t pcap) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += align_up(bytes ? bytes : 16, 256);
+        return p;
+    };
+    const size_t pp = (size_t)(pcap > 0 ? pcap : 0);
+    w.pairs_a = static_cast<uint64_t*>(take(pp * 8));
+    w.pairs_b = static_cast<uint64_t*>(take(pp * 8));
+    w.psort_temp_bytes = cugs_packed_sort_temp_bytes(pcap, 4, kMaxTilesForWorkspace);
+    w.psort_temp = take(w.psort_temp_bytes);
+    w.pair_bytes = off;
+}
 
 FrameWorkspace carve(void* base, int64_t n, int64_t pcap) {
     FrameWorkspace w{};
@@ -175,7 +197,7 @@ FrameWorkspace carve(void* base, int64_t n, int64_t pcap) {
         off += align_up(bytes ? bytes : 16, 256);
         return p;
     };
-    const size_t nn = (size_t)(n > 0 ? n : 0), pp = (size_t)(pcap > 0 ? pcap : 0);
+    const size_t nn = (size_t)(n > 0 ? n : 0);
     // N-sized regions first: their addresses do not depend on the pair capacity, so plan, finish
     // and render_backward of one frame agree on them whatever P turns out to be.
     w.packed = static_cast<float*>(take(nn * 48));
@@ -188,12 +210,10 @@ FrameWorkspace carve(void* base, int64_t n, int64_t pcap) {
     w.gsort_temp_bytes = cugs_packed_sort_temp_bytes(n, 4, 0);
     w.gsort_temp = take(w.gsort_temp_bytes);
     w.grad_acc = static_cast<float*>(take(nn * 48));
-    // P-sized scratch, live only inside render_finish
-    w.pairs_a = static_cast<uint64_t*>(take(pp * 8));
-    w.pairs_b = static_cast<uint64_t*>(take(pp * 8));
-    w.psort_temp_bytes = cugs_packed_sort_temp_bytes(pcap, 4, kMaxTilesForWorkspace);
-    w.psort_temp = take(w.psort_temp_bytes);
-    w.total_bytes = off;
+    w.head_bytes = off;
+    // P-sized scratch, live only inside render_finish: the tail of the same block, or a separate one
+    carve_pairs(w, base ? static_cast<char*>(base) + off : nullptr, pcap);
+    w.total_bytes = off + w.pair_bytes;
     return w;
 }
 
@@ -209,9 +229,81 @@ extern "C" size_t cugs_b200_render_workspace_bytes(int64_t n, int64_t p_capacity
     return carve(nullptr, n, p_capacity).total_bytes;
 }
 
+extern "C" size_t cugs_b200_render_pair_scratch_bytes(int64_t p_capacity) {
+    FrameWorkspace w{};
+    carve_pairs(w, nullptr, p_capacity);
+    return w.pair_bytes;
+}
+
 // ------------------------------------------------------------------------------------------------
-// render: plan (preprocess + scan, returns P) and finish (dup + sort + ranges + blend)
+// render: front (preprocess + depth sort + scan -> P on the device) and back (dup + tile sort +
+// ranges + blend, every launch sized on a pair CAPACITY and reading P on the device). The public
+// entry points are plan (= front + ONE blocking read of P, as the reference), finish (= back with
+// capacity = the P the caller read), and render_forward (= front + back, no host round trip).
 // ------------------------------------------------------------------------------------------------
+static int forward_front(cugs_handle_t* h, cudaStream_t s, int64_t n, const cugs_view_t* v, const float* positions,
+                         const float* rotations, const float* scales, const float* opacities,
+                         const float* sh_coeffs, float* means_2d, float* depths, float* cov_2d_inv,
+                         int32_t* radii, float* rgb, float* opacities_act, const FrameWorkspace& w,
+                         int64_t* total_pinned) {
+    mark(h, 0, s);
+    if (int e = cugs_preprocess_fwd_launch(h, s, n, v, positions, rotations, scales, opacities, sh_coeffs, means_2d,
+                                           depths, cov_2d_inv, radii, w.tiles_touched, rgb, opacities_act, w.packed,
+                                           nullptr, w.gsort_a))
+        return e;
+    mark(h, 1, s);
+    // depth sort of the N Gaussians (the depth-bit passes of the reference's 64-bit sort, hoisted
+    // in front of duplicateWithKeys), then the scan of tiles_touched in depth order
+    if (int e = cugs_packed_sort(h, s, n, 32, w.gsort_a, w.gsort_b, nullptr, 0, nullptr, w.gsort_temp,
+                                 w.gsort_temp_bytes, nullptr))
+        return e;
+    mark(h, 11, s);
+    if (int e = cugs_scan_launch(h, s, n, w.tiles_touched, w.offsets, w.total_dev, total_pinned, w.scan_temp,
+                                 nullptr, w.gsort_a))
+        return e;
+    mark(h, 2, s);
+    return CUGS_OK;
+}
+
+// p_cap = capacity of gaussian_idx and of the workspace's pair buffers; the pair count itself is read
+// on the device from w.total_dev (written by the scan) and clamped to p_cap
+static int forward_back(cugs_handle_t* h, cudaStream_t s, int64_t n, int64_t p_cap, const cugs_view_t* v,
+                        const float* means_2d, const float* cov_2d_inv, const int32_t* radii, const float* rgb,
+                        const float* opacities_act, int32_t* gaussian_idx, int32_t* tile_ranges, float* color,
+                        float* final_T, int32_t* n_contrib, const FrameWorkspace& w) {
+    const int ntx = (v->width + kTile - 1) / kTile, nty = (v->height + kTile - 1) / kTile;
+    const int num_tiles = ntx * nty;
+    mark(h, 3, s);
+    if (num_tiles > kMaxTilesForWorkspace)
+        return set_error(h, CUGS_ERR_UNSUPPORTED, "%d tiles > %d is not supported by the fused path", num_tiles,
+                         kMaxTilesForWorkspace);
+    if (n > 0 && p_cap > 0) {
+        if (int e = cugs_duplicate_sorted(h, s, n, v->width, v->height, w.gsort_a, means_2d, radii, w.tiles_touched,
+                                          w.offsets, p_cap, w.pairs_a, w.total_dev))
+            return e;
+        mark(h, 4, s);
+        const int tile_bits = ceil_log2(num_tiles);
+        h->last_sort_passes = 4 + cugs_packed_passes(tile_bits);
+        h->last_sort_key_bits = 32 + tile_bits;
+        // tile histogram -> tile ranges, and the stable sort of the pairs by tile id; the last pass
+        // writes the Gaussian indices straight into the caller's buffer
+        if (int e = cugs_packed_sort(h, s, p_cap, tile_bits, w.pairs_a, w.pairs_b, gaussian_idx, num_tiles,
+                                     tile_ranges, w.psort_temp, w.psort_temp_bytes, w.total_dev))
+            return e;
+        mark(h, 5, s);
+    } else {
+        mark(h, 4, s);
+        mark(h, 5, s);
+        CUGS_CUDA_TRY(h, cudaMemsetAsync(tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(int), s));
+    }
+    mark(h, 6, s);
+    if (int e = cugs_b200_blend_fwd(h, s, v, tile_ranges, gaussian_idx, means_2d, cov_2d_inv, rgb, opacities_act,
+                                    n > 0 ? w.packed : nullptr, color, final_T, n_contrib))
+        return e;
+    mark(h, 7, s);
+    return CUGS_OK;
+}
+
 extern "C" int cugs_b200_render_plan(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
                                      const float* positions, const float* rotations,
                                      const float* scales, const float* opacities,
@@ -231,24 +323,12 @@ extern "C" int cugs_b200_render_plan(cugs_handle_t* h, void* stream, int64_t n, 
     cudaStream_t s = (cudaStream_t)stream;
     // the N-sized regions come first in the layout, so carving with pcap = 0 addresses them
     const FrameWorkspace w = carve(workspace, n, 0);
-    mark(h, 0, s);
-    if (int e = cugs_preprocess_fwd_launch(h, stream, n, v, positions, rotations, scales, opacities, sh_coeffs,
-                                           means_2d, depths, cov_2d_inv, radii, w.tiles_touched, rgb,
-                                           opacities_act, w.packed, nullptr, w.gsort_a))
+    int64_t* slot = cugs_pinned_slot(h);  // this frame's own pinned word
+    if (int e = forward_front(h, s, n, v, positions, rotations, scales, opacities, sh_coeffs, means_2d, depths,
+                              cov_2d_inv, radii, rgb, opacities_act, w, slot))
         return e;
-    mark(h, 1, s);
-    // depth sort of the N Gaussians (the depth-bit passes of the reference's 64-bit sort, hoisted
-    // in front of duplicateWithKeys), then the scan of tiles_touched in depth order
-    if (int e = cugs_packed_sort(h, s, n, 32, w.gsort_a, w.gsort_b, nullptr, 0, nullptr, w.gsort_temp,
-                                 w.gsort_temp_bytes))
-        return e;
-    mark(h, 11, s);
-    if (int e = cugs_scan_launch(h, s, n, w.tiles_touched, w.offsets, w.total_dev, true, w.scan_temp, nullptr,
-                                 w.gsort_a))
-        return e;
-    mark(h, 2, s);
     CUGS_CUDA_TRY(h, cudaStreamSynchronize(s));  // the one blocking read (reference: sorting.cu:146)
-    *p_host = h->pinned[0];
+    *p_host = *slot;
     return CUGS_OK;
 }
 
@@ -257,57 +337,90 @@ extern "C" int cugs_b200_render_finish(cugs_handle_t* h, void* stream, int64_t n
                                        const float* cov_2d_inv, const int32_t* radii, const float* rgb,
                                        const float* opacities_act, int32_t* gaussian_idx,
                                        int32_t* tile_ranges, float* color, float* final_T,
-                                       int32_t* n_contrib, void* workspace, size_t workspace_bytes) {
+                                       int32_t* n_contrib, void* workspace, size_t workspace_bytes,
+                                       void* pair_scratch, size_t pair_scratch_bytes) {
+    (void)depths;
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, v != nullptr && v->width > 0 && v->height > 0, "bad view");
     CUGS_REQUIRE(h, n >= 0 && p >= 0, "n and p must be >= 0");
     CUGS_REQUIRE(h, tile_ranges && color && final_T && n_contrib, "null output");
     CUGS_REQUIRE(h, p == 0 || gaussian_idx != nullptr, "gaussian_idx is null");
-    const int ntx = (v->width + kTile - 1) / kTile, nty = (v->height + kTile - 1) / kTile;
-    const int num_tiles = ntx * nty;
     cudaStream_t s = (cudaStream_t)stream;
     FrameWorkspace w{};
     if (n > 0) {
         CUGS_REQUIRE(h, workspace != nullptr, "workspace is null");
-        if (workspace_bytes < cugs_b200_render_workspace_bytes(n, p))
+        const int64_t in_ws = pair_scratch ? 0 : p;  // pair buffers: the tail of the workspace, or a separate block
+        if (workspace_bytes < cugs_b200_render_workspace_bytes(n, in_ws))
             return set_error(h, CUGS_ERR_WORKSPACE, "workspace too small for N=%lld P=%lld: %zu < %zu",
-                             (long long)n, (long long)p, workspace_bytes,
-                             cugs_b200_render_workspace_bytes(n, p));
-        w = carve(workspace, n, p);
+                             (long long)n, (long long)in_ws, workspace_bytes,
+                             cugs_b200_render_workspace_bytes(n, in_ws));
+        w = carve(workspace, n, in_ws);
+        if (pair_scratch) {
+            if (pair_scratch_bytes < cugs_b200_render_pair_scratch_bytes(p))
+                return set_error(h, CUGS_ERR_WORKSPACE, "pair scratch too small for P=%lld: %zu < %zu", (long long)p,
+                                 pair_scratch_bytes, cugs_b200_render_pair_scratch_bytes(p));
+            carve_pairs(w, pair_scratch, p);
+        }
     }
-    mark(h, 3, s);
-    if (num_tiles > kMaxTilesForWorkspace)
-        return set_error(h, CUGS_ERR_UNSUPPORTED, "%d tiles > %d is not supported by the fused path", num_tiles,
-                         kMaxTilesForWorkspace);
-    if (p > 0) {
-        if (h->pinned[0] != p)
-            return set_error(h, CUGS_ERR_INVALID_ARG, "p = %lld does not match the plan of this frame (%lld)",
-                             (long long)p, (long long)h->pinned[0]);
-        if (int e = cugs_duplicate_sorted(h, s, n, v->width, v->height, w.gsort_a, means_2d, radii, w.tiles_touched,
-                                          w.offsets, p, w.pairs_a))
+    // p is the CAPACITY the caller sized gaussian_idx for (= the P that render_plan returned); the
+    // kernels read the frame's own pair count from the workspace, so a stale or foreign p can only
+    // truncate the frame, never make a kernel run past a buffer
+    return forward_back(h, s, n, p, v, means_2d, cov_2d_inv, radii, rgb, opacities_act, gaussian_idx, tile_ranges,
+                        color, final_T, n_contrib, w);
+}
+
+namespace cugs {
+// {P, P > capacity} -> the caller's status words (device memory; copied to the host whenever the caller
+// wants to look, e.g. once per step)
+__global__ void k_publish_pairs(const int64_t* __restrict__ total_dev, int64_t p_cap, int64_t* __restrict__ status) {
+    const int64_t p = *total_dev;
+    status[0] = p;
+    status[1] = p > p_cap ? 1 : 0;
+}
+}  // namespace cugs
+
+extern "C" int cugs_b200_render_forward(cugs_handle_t* h, void* stream, int64_t n, int64_t p_capacity,
+                                        const cugs_view_t* v, const float* positions, const float* rotations,
+                                        const float* scales, const float* opacities, const float* sh_coeffs,
+                                        float* means_2d, float* depths, float* cov_2d_inv, int32_t* radii,
+                                        float* rgb, float* opacities_act, int32_t* gaussian_idx,
+                                        int32_t* tile_ranges, float* color, float* final_T, int32_t* n_contrib,
+                                        void* workspace, size_t workspace_bytes, void* pair_scratch,
+                                        size_t pair_scratch_bytes, int64_t* status_dev) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    CUGS_REQUIRE(h, v != nullptr && v->width > 0 && v->height > 0, "bad view");
+    CUGS_REQUIRE(h, n >= 0 && p_capacity >= 0, "n and p_capacity must be >= 0");
+    CUGS_REQUIRE(h, tile_ranges && color && final_T && n_contrib, "null output");
+    CUGS_REQUIRE(h, p_capacity == 0 || gaussian_idx != nullptr, "gaussian_idx is null");
+    cudaStream_t s = (cudaStream_t)stream;
+    FrameWorkspace w{};
+    if (n > 0) {
+        CUGS_REQUIRE(h, workspace != nullptr, "workspace is null");
+        const int64_t in_ws = pair_scratch ? 0 : p_capacity;
+        if (workspace_bytes < cugs_b200_render_workspace_bytes(n, in_ws))
+            return set_error(h, CUGS_ERR_WORKSPACE, "workspace too small for N=%lld capacity=%lld: %zu < %zu",
+                             (long long)n, (long long)in_ws, workspace_bytes,
+                             cugs_b200_render_workspace_bytes(n, in_ws));
+        w = carve(workspace, n, in_ws);
+        if (pair_scratch) {
+            if (pair_scratch_bytes < cugs_b200_render_pair_scratch_bytes(p_capacity))
+                return set_error(h, CUGS_ERR_WORKSPACE, "pair scratch too small for capacity=%lld: %zu < %zu",
+                                 (long long)p_capacity, pair_scratch_bytes,
+                                 cugs_b200_render_pair_scratch_bytes(p_capacity));
+            carve_pairs(w, pair_scratch, p_capacity);
+        }
+        if (int e = forward_front(h, s, n, v, positions, rotations, scales, opacities, sh_coeffs, means_2d, depths,
+                                  cov_2d_inv, radii, rgb, opacities_act, w, nullptr))
             return e;
-        mark(h, 4, s);
-        const int tile_bits = ceil_log2(num_tiles);
-        h->last_sort_passes = 4 + cugs_packed_passes(tile_bits);
-        h->last_sort_key_bits = 32 + tile_bits;
-        // tile histogram -> tile ranges, and the stable sort of the pairs by tile id; the last pass
-        // writes the Gaussian indices straight into the caller's buffer
-        if (int e = cugs_packed_sort(h, s, p, tile_bits, w.pairs_a, w.pairs_b, gaussian_idx, num_tiles, tile_ranges,
-                                     w.psort_temp, w.psort_temp_bytes))
-            return e;
-        mark(h, 5, s);
-    } else {
-        mark(h, 4, s);
-        mark(h, 5, s);
-        CUGS_CUDA_TRY(h, cudaMemsetAsync(tile_ranges, 0, (size_t)num_tiles * 2 * sizeof(int), s));
+        if (status_dev) {
+            k_publish_pairs<<<1, 1, 0, s>>>(w.total_dev, p_capacity, status_dev);
+            CUGS_LAUNCH_CHECK(h, "k_publish_pairs");
+        }
+    } else if (status_dev) {
+        CUGS_CUDA_TRY(h, cudaMemsetAsync(status_dev, 0, 2 * sizeof(int64_t), s));
     }
-    mark(h, 6, s);
-    if (int e = cugs_b200_blend_fwd(h, stream, v, tile_ranges, gaussian_idx, means_2d, cov_2d_inv, rgb,
-                                    opacities_act, n > 0 ? w.packed : nullptr, color, final_T, n_contrib)) {
-        return e;
-    }
-    mark(h, 7, s);
-    return CUGS_OK;
+    return forward_back(h, s, n, p_capacity, v, means_2d, cov_2d_inv, radii, rgb, opacities_act, gaussian_idx,
+                        tile_ranges, color, final_T, n_contrib, w);
 }
 
 extern "C" int cugs_b200_render_backward(

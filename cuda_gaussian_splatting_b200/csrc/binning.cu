@@ -233,15 +233,14 @@ extern "C" size_t cugs_b200_scan_temp_bytes(int64_t n) {
 }
 
 int cugs_scan_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, const int32_t* tiles_touched,
-                     int32_t* offsets, int64_t* total_dev, bool to_pinned, void* scan_temp,
+                     int32_t* offsets, int64_t* total_dev, int64_t* total_pinned, void* scan_temp,
                      const unsigned* aux_pair, const uint64_t* gather) {
     const int64_t blocks = (n + kScanTile - 1) / kScanTile;
     CUGS_CUDA_TRY(h, cudaMemsetAsync(scan_temp, 0, cugs_b200_scan_temp_bytes(n), s));
     unsigned* ticket = reinterpret_cast<unsigned*>(scan_temp);
     uint64_t* status = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(scan_temp) + 16);
     k_scan_exclusive<<<(unsigned)blocks, kScanBlock, 0, s>>>(n, tiles_touched, offsets, ticket, status,
-                                                             total_dev, to_pinned ? h->pinned : nullptr,
-                                                             aux_pair, gather);
+                                                             total_dev, total_pinned, aux_pair, gather);
     CUGS_LAUNCH_CHECK(h, "k_scan_exclusive");
     return CUGS_OK;
 }
@@ -261,12 +260,14 @@ extern "C" int cugs_b200_scan(cugs_handle_t* h, void* stream, int64_t n, const i
     if (scan_temp_bytes < cugs_b200_scan_temp_bytes(n))
         return set_error(h, CUGS_ERR_WORKSPACE, "scan_temp too small: %zu < %zu", scan_temp_bytes,
                          cugs_b200_scan_temp_bytes(n));
-    if (int e = cugs_scan_launch(h, s, n, tiles_touched, offsets, total_dev, total_host != nullptr,
-                                 scan_temp, nullptr, nullptr))
+    // every blocking call gets its own pinned word (a ring), so that a scan issued between the plan and
+    // the finish of a frame, or by another stream, cannot overwrite a count somebody still has to read
+    int64_t* slot = total_host ? cugs_pinned_slot(h) : nullptr;
+    if (int e = cugs_scan_launch(h, s, n, tiles_touched, offsets, total_dev, slot, scan_temp, nullptr, nullptr))
         return e;
     if (total_host) {
         CUGS_CUDA_TRY(h, cudaStreamSynchronize(s));  // the one blocking read (sorting.cu:146)
-        *total_host = h->pinned[0];
+        *total_host = *slot;
     }
     return CUGS_OK;
 }

@@ -537,6 +537,98 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
 #undef CUGS_ALL_DONE
 }
 
+// ================================================================================================
+// work counter (measurement only, never inside a timed region): the number of (pixel, Gaussian)
+// evaluations the REFERENCE traversal performs, split into alpha-rejected and contributing ones --
+// E_fwd by forward.cu:121-157 (a pixel walks its tile's list front to back until T < 1/255), E_bwd by
+// backward.cu:117-145 (back to front until more than n_contrib alpha-passing Gaussians were met).
+// These are the work units of SURVEY 8(d): 15 FLOP + 1 EX2 per rejected evaluation, 24 FLOP + 1 EX2 per
+// contributing forward evaluation, 55 FLOP + 1 EX2 + 1 RCP per contributing backward evaluation.
+// One thread per pixel, one 256-thread CTA per tile, plain reference arithmetic.
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+k_count_evaluations(int ntx, int width, int height, const int* __restrict__ tile_ranges,
+                    const int* __restrict__ gaussian_idx, const float* __restrict__ means_2d,
+                    const float* __restrict__ conic, const float* __restrict__ opa,
+                    const int* __restrict__ n_contrib, unsigned long long* __restrict__ counts /* [4] */) {
+    __shared__ float s_x[256], s_y[256], s_a[256], s_b[256], s_c[256], s_o[256];
+    __shared__ unsigned long long s_cnt[4];
+    const int tile = blockIdx.x;
+    const int tile_x = tile % ntx, tile_y = tile / ntx;
+    const int px = tile_x * kTile + (threadIdx.x & 15), py = tile_y * kTile + (threadIdx.x >> 4);
+    const bool inside = px < width && py < height;
+    const float pxf = (float)px + 0.5f, pyf = (float)py + 0.5f;
+    const int2 range = reinterpret_cast<const int2*>(tile_ranges)[tile];
+    const int count = range.y - range.x;
+    const int nb = (count + 255) / 256;
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
+    unsigned long long c_rej = 0, c_con = 0, b_rej = 0, b_con = 0;
+
+    auto stage = [&](int b) {
+        const int li = range.x + b * 256 + threadIdx.x;
+        if (li < range.y) {
+            const int g = gaussian_idx[li];
+            s_x[threadIdx.x] = means_2d[(int64_t)g * 2];
+            s_y[threadIdx.x] = means_2d[(int64_t)g * 2 + 1];
+            s_a[threadIdx.x] = conic[(int64_t)g * 3];
+            s_b[threadIdx.x] = conic[(int64_t)g * 3 + 1];
+            s_c[threadIdx.x] = conic[(int64_t)g * 3 + 2];
+            s_o[threadIdx.x] = opa[g];
+        }
+    };
+    auto alpha_of = [&](int j, bool& rejected) {
+        const float dx = pxf - s_x[j], dy = pyf - s_y[j];
+        float s1, s2;
+        const float power = blend_power4(dx, dy, s_a[j], s_b[j], mul_rn(dy, s_b[j]), mul_rn(dy, s_c[j]), s1, s2);
+        if (power > 0.0f) { rejected = true; return 0.0f; }
+        const float alpha = fminf(mul_rn(s_o[j], expf(power)), 0.99f);
+        rejected = alpha < kAlphaMin;
+        return alpha;
+    };
+
+    // forward traversal
+    float T = 1.0f;
+    bool done = !inside;
+    for (int b = 0; b < nb; ++b) {
+        __syncthreads();
+        stage(b);
+        __syncthreads();
+        if (!done) {
+            const int bc = min(256, count - b * 256);
+            for (int j = 0; j < bc; ++j) {
+                bool rej;
+                const float alpha = alpha_of(j, rej);
+                if (rej) { ++c_rej; continue; }
+                ++c_con;
+                T = mul_rn(T, add_rn(1.0f, -alpha));
+                if (T < kTMin) { done = true; break; }
+            }
+        }
+    }
+    // backward traversal
+    const int max_contrib = inside ? n_contrib[(int64_t)py * width + px] : 0;
+    int found = 0;
+    done = !inside;
+    for (int b = nb - 1; b >= 0; --b) {
+        __syncthreads();
+        stage(b);
+        __syncthreads();
+        if (!done) {
+            const int bc = min(256, count - b * 256);
+            for (int j = bc - 1; j >= 0; --j) {
+                bool rej;
+                (void)alpha_of(j, rej);
+                if (rej) { ++b_rej; continue; }
+                if (++found > max_contrib) { ++b_rej; done = true; break; }  // evaluated, then dropped (:142-145)
+                ++b_con;
+            }
+        }
+    }
+    atomicAdd(&s_cnt[0], c_rej); atomicAdd(&s_cnt[1], c_con); atomicAdd(&s_cnt[2], b_rej); atomicAdd(&s_cnt[3], b_con);
+    __syncthreads();
+    if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
 // grad_acc [N,12] -> the four public arrays of RasterizeBackwardOutput (backward.hpp:13-18)
 __global__ void __launch_bounds__(256)
 k_unpack_grads(int64_t n, const float4* __restrict__ acc, float* __restrict__ dL_drgb,
@@ -596,6 +688,24 @@ int cugs_blend_bwd_accumulate(cugs_handle_t* h, cudaStream_t s, int64_t n, const
             ntx, v->width, v->height, v->bg[0], v->bg[1], v->bg[2], tile_ranges, gaussian_idx, nullptr,
             means_2d, cov_2d_inv, rgb, opacities_act, dL_dcolor, final_T, n_contrib, grad_acc);
     CUGS_LAUNCH_CHECK(h, "k_blend_bwd");
+    return CUGS_OK;
+}
+
+extern "C" int cugs_b200_count_evaluations(cugs_handle_t* h, void* stream, const cugs_view_t* v,
+                                           const int32_t* tile_ranges, const int32_t* gaussian_idx,
+                                           const float* means_2d, const float* cov_2d_inv,
+                                           const float* opacities_act, const int32_t* n_contrib,
+                                           uint64_t* counts4_dev) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    CUGS_REQUIRE(h, v != nullptr && v->width > 0 && v->height > 0, "bad view");
+    CUGS_REQUIRE(h, tile_ranges && means_2d && cov_2d_inv && opacities_act && n_contrib && counts4_dev, "null pointer");
+    const int ntx = (v->width + kTile - 1) / kTile, nty = (v->height + kTile - 1) / kTile;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUGS_CUDA_TRY(h, cudaMemsetAsync(counts4_dev, 0, 4 * sizeof(uint64_t), s));
+    k_count_evaluations<<<ntx * nty, 256, 0, s>>>(ntx, v->width, v->height, tile_ranges, gaussian_idx, means_2d,
+                                                  cov_2d_inv, opacities_act, n_contrib,
+                                                  reinterpret_cast<unsigned long long*>(counts4_dev));
+    CUGS_LAUNCH_CHECK(h, "k_count_evaluations");
     return CUGS_OK;
 }
 

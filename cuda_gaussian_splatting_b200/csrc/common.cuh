@@ -13,7 +13,9 @@
 struct cugs_handle {
     int device;
     int sm_count;
-    int64_t* pinned;      // mapped pinned host words {P, depth_min|depth_max<<32, ...}
+    int64_t* pinned;      // mapped pinned host words: [0,16) fixed slots (4..6 densify / relocate counts),
+                          // [16, 16 + kPinnedRing) a ring of one-shot slots for the blocking count reads
+    unsigned pinned_seq;  // next ring slot
     char err[512];
     // optional per-stage timing of the fused entry points (cugs_b200_set_stage_timing)
     bool timing;
@@ -24,6 +26,12 @@ struct cugs_handle {
 };
 
 namespace cugs {
+
+constexpr int kPinnedWords = 80;
+constexpr int kPinnedRing = 64;
+// one-shot pinned word for a blocking device->host count (render_plan, scan): the ring is long enough
+// for every frame that can be in flight through one handle
+inline int64_t* cugs_pinned_slot(cugs_handle* h) { return h->pinned + 16 + (h->pinned_seq++ % kPinnedRing); }
 
 constexpr int kTile = CUGS_TILE;
 constexpr unsigned kFull = 0xffffffffu;

@@ -73,10 +73,13 @@ constexpr int kPkHistItems = 8;
 
 template <bool kTileHist>
 __global__ void __launch_bounds__(kPkHistThreads)
-k_packed_histogram(int64_t n, const uint64_t* __restrict__ elts, PackedPlan plan,
+k_packed_histogram(int64_t n_cap, const int64_t* __restrict__ n_dev, const uint64_t* __restrict__ elts, PackedPlan plan,
                    unsigned* __restrict__ digit_hist /* [passes][256] */, int num_tiles,
                    unsigned* __restrict__ tile_hist /* [num_tiles] */) {
     extern __shared__ unsigned s_hist[];  // [passes*256] (+ [num_tiles])
+    // element count: host value, or (capacity-sized launch, no host round trip) the device word
+    // written by the scan, clamped to the capacity of the buffers
+    const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
     unsigned* s_tile = s_hist + plan.passes * kPkRadix;
     const int total_bins = plan.passes * kPkRadix + (kTileHist ? num_tiles : 0);
     for (int b = threadIdx.x; b < total_bins; b += kPkHistThreads) s_hist[b] = 0;
@@ -185,9 +188,13 @@ constexpr size_t kPkSmemBytes = (size_t)kPkTile * 8 + (size_t)kPkRadix * 8 + (si
 // kBits = digit width of the pass (6, 7, 8), 0 = run-time width
 template <bool kLast, int kBits>
 __global__ void __launch_bounds__(kPkThreads, CUGS_OS_MINBLOCKS)
-k_onesweep_packed(int64_t n, const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
-                  int* __restrict__ out32, const unsigned* __restrict__ bin_base,
+k_onesweep_packed(int64_t n_cap, const int64_t* __restrict__ n_dev, const uint64_t* __restrict__ in,
+                  uint64_t* __restrict__ out, int* __restrict__ out32, const unsigned* __restrict__ bin_base,
                   volatile unsigned* __restrict__ lookback, unsigned* __restrict__ ticket, int shift, int bits) {
+    // capacity-sized launch: exactly ceil(n / kPkTile) blocks pass this test and take tickets
+    // 0 .. tiles-1, so the look-back chain is the same as with a grid sized on the host
+    const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
+    if ((int64_t)blockIdx.x * kPkTile >= n) return;
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint64_t* s_elts = reinterpret_cast<uint64_t*>(s_raw);                   // [kPkTile]
     int64_t* s_bin_global = reinterpret_cast<int64_t*>(s_elts + kPkTile);     // global index = [d] + slot
@@ -351,8 +358,11 @@ __global__ void __launch_bounds__(kDupBlock)
 k_duplicate_sorted(int64_t n, int width, int height, int ntx, int nty,
                    const uint64_t* __restrict__ sorted_elts, const float* __restrict__ means_2d,
                    const int* __restrict__ radii, const int* __restrict__ tiles_touched,
-                   const int* __restrict__ offsets /* in sorted order */, int64_t p,
-                   uint64_t* __restrict__ pairs) {
+                   const int* __restrict__ offsets /* in sorted order */, int64_t p_cap,
+                   const int64_t* __restrict__ p_dev, uint64_t* __restrict__ pairs) {
+    // pairs beyond the capacity of the caller's buffers are dropped (the frame is then flagged as
+    // overflowed by the scan's P > capacity, see cugs_b200_render_forward)
+    const int64_t p = p_dev ? min(*p_dev, p_cap) : p_cap;
     const int lane = threadIdx.x & 31;
     const int64_t s0 = ((int64_t)blockIdx.x * (kDupBlock / 32) + (threadIdx.x >> 5)) * 32;
     if (s0 >= n) return;
@@ -436,8 +446,11 @@ int cugs_packed_passes(int key_bits) { return make_packed_plan(key_bits).passes;
 //                    are then NOT materialised); else the result is in (passes odd ? b : a)
 //   tile_ranges    : if non-null (num_tiles > 0) the full key histogram is taken in the same read
 //                    as the digit histograms and turned into [start,end) ranges
+//   n_dev          : if non-null, n is only the CAPACITY of a / b / out32_last and the element count is
+//                    min(*n_dev, n), read on the device (no host round trip: launches are sized on n)
 int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, uint64_t* a, uint64_t* b,
-                     int* out32_last, int num_tiles, int* tile_ranges, void* temp, size_t temp_bytes) {
+                     int* out32_last, int num_tiles, int* tile_ranges, void* temp, size_t temp_bytes,
+                     const int64_t* n_dev) {
     const PackedPlan plan = make_packed_plan(key_bits);
     if (n >= (1ll << 30))
         return set_error(h, CUGS_ERR_UNSUPPORTED, "n = %lld >= 2^30 elements is not supported", (long long)n);
@@ -466,10 +479,11 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
             return set_error(h, CUGS_ERR_UNSUPPORTED, "%d tiles exceed the shared-memory tile histogram", num_tiles);
         CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_packed_histogram<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)hist_smem));
-        k_packed_histogram<true><<<hist_blocks, kPkHistThreads, hist_smem, s>>>(n, a, plan, digit_hist, num_tiles,
-                                                                                tile_hist);
+        k_packed_histogram<true><<<hist_blocks, kPkHistThreads, hist_smem, s>>>(n, n_dev, a, plan, digit_hist,
+                                                                                num_tiles, tile_hist);
     } else {
-        k_packed_histogram<false><<<hist_blocks, kPkHistThreads, hist_smem, s>>>(n, a, plan, digit_hist, 0, nullptr);
+        k_packed_histogram<false><<<hist_blocks, kPkHistThreads, hist_smem, s>>>(n, n_dev, a, plan, digit_hist, 0,
+                                                                                 nullptr);
     }
     CUGS_LAUNCH_CHECK(h, "k_packed_histogram");
     k_packed_scan_bins<<<plan.passes, kPkRadix, 0, s>>>(digit_hist);
@@ -488,7 +502,7 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
         CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_onesweep_packed<LAST, BITS>,                                    \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPkSmemBytes)); \
         k_onesweep_packed<LAST, BITS><<<(unsigned)tiles, kPkThreads, kPkSmemBytes, s>>>(                        \
-            n, src, dst, LAST ? out32_last : nullptr, digit_hist + ps * kPkRadix, lb, tickets + ps,             \
+            n, n_dev, src, dst, LAST ? out32_last : nullptr, digit_hist + ps * kPkRadix, lb, tickets + ps,      \
             plan.shift[ps], plan.bits[ps]);                                                                     \
     } while (0)
 #define CUGS_OS_DISPATCH(LAST)                          \
@@ -509,12 +523,36 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
 
 int cugs_duplicate_sorted(cugs_handle_t* h, cudaStream_t s, int64_t n, int width, int height,
                           const uint64_t* sorted_elts, const float* means_2d, const int32_t* radii,
-                          const int32_t* tiles_touched, const int32_t* offsets_sorted, int64_t p, uint64_t* pairs) {
+                          const int32_t* tiles_touched, const int32_t* offsets_sorted, int64_t p, uint64_t* pairs,
+                          const int64_t* p_dev) {
     if (n == 0 || p == 0) return CUGS_OK;
     const int ntx = (width + kTile - 1) / kTile, nty = (height + kTile - 1) / kTile;
     const unsigned grid = (unsigned)((n + kDupBlock - 1) / kDupBlock);
     k_duplicate_sorted<<<grid, kDupBlock, 0, s>>>(n, width, height, ntx, nty, sorted_elts, means_2d, radii,
-                                                  tiles_touched, offsets_sorted, p, pairs);
+                                                  tiles_touched, offsets_sorted, p, p_dev, pairs);
     CUGS_LAUNCH_CHECK(h, "k_duplicate_sorted");
     return CUGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// public stage entry points of the packed sort (declared in include/cugs_b200.h)
+// ------------------------------------------------------------------------------------------------
+extern "C" int cugs_b200_sort_packed_passes(int key_bits) { return cugs_packed_passes(key_bits); }
+
+extern "C" size_t cugs_b200_sort_packed_temp_bytes(int64_t n, int key_bits, int num_tiles) {
+    return cugs_packed_sort_temp_bytes(n, cugs_packed_passes(key_bits), num_tiles);
+}
+
+extern "C" int cugs_b200_sort_packed(cugs_handle_t* h, void* stream, int64_t n, int key_bits, uint64_t* elts_a,
+                                     uint64_t* elts_b, int32_t* out32_last, int num_tiles, int32_t* tile_ranges,
+                                     void* temp, size_t temp_bytes, const int64_t* n_dev) {
+    CUGS_REQUIRE(h, h != nullptr, "handle is null");
+    CUGS_REQUIRE(h, n >= 0, "n must be >= 0");
+    CUGS_REQUIRE(h, key_bits >= 0 && key_bits <= 32, "key_bits must be in 0..32");
+    CUGS_REQUIRE(h, num_tiles >= 0 && (tile_ranges == nullptr || num_tiles > 0), "tile_ranges needs num_tiles > 0");
+    CUGS_REQUIRE(h, tile_ranges == nullptr || key_bits >= 32 || (int64_t)num_tiles <= (1ll << key_bits),
+                 "num_tiles exceeds 2^key_bits");
+    CUGS_REQUIRE(h, n == 0 || (elts_a && elts_b && temp), "null pointer");
+    return cugs_packed_sort(h, (cudaStream_t)stream, n, key_bits, elts_a, elts_b, out32_last, num_tiles, tile_ranges,
+                            temp, temp_bytes, n_dev);
 }

@@ -302,20 +302,138 @@ __global__ void k_loss_finalize(int width, int height, float lambda, const doubl
     scalars3[2] = (float)ss;
 }
 
-static SsimWindow make_window() {
-    // loss.cpp:57-70: float 1-D gaussian (sigma 1.5) / sum; 2-D = outer product / its sum
-    float k[11], sum = 0.f;
-    for (int i = 0; i < 11; ++i) {
-        const float x = (float)(i - 5);
+// ------------------------------------------------------------------------------------------------
+// any odd window (loss.hpp:33-44 lets the caller choose window_size; loss.cpp:88-124): the tuned kernels
+// above are specialised for the default 11 taps, these two cover every other odd size 3..kMaxWindow with
+// the same two-pass formulation (moments -> S and its three partial-derivative maps; gradient = the
+// window applied to those maps). One thread per (pixel, channel), separable factor in constant-bank
+// kernel arguments, direct w x w accumulation with the row factor hoisted: a fall-back for evaluation
+// callers (metrics with a different window), not a tuned path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxWindow = 33;
+struct SsimWindowAny {
+    int size;
+    float w[kMaxWindow];
+};
+
+__global__ void __launch_bounds__(256)
+k_ssim_moments_any(int width, int height, SsimWindowAny win, const float* __restrict__ x_img,
+                   const float* __restrict__ y_img, float* __restrict__ g1, float* __restrict__ g2,
+                   float* __restrict__ g3, double* __restrict__ sums, float* __restrict__ ssim_map) {
+    __shared__ float s_red[2][8];
+    const int64_t total = (int64_t)width * height * 3;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float l1_local = 0.f, s_local = 0.f;
+    if (e < total) {
+        const int ch = (int)(e % 3);
+        const int64_t pix = e / 3;
+        const int gx = (int)(pix % width), gy = (int)(pix / width);
+        const int half = win.size / 2;
+        float mx = 0.f, my = 0.f, qq = 0.f, xy = 0.f;
+        for (int dy = -half; dy <= half; ++dy) {
+            const int yy = gy + dy;
+            if (yy < 0 || yy >= height) continue;  // zero padding (conv2d padding = window / 2)
+            float rx = 0.f, ry = 0.f, rq = 0.f, rxy = 0.f;
+            for (int dx = -half; dx <= half; ++dx) {
+                const int xx = gx + dx;
+                if (xx < 0 || xx >= width) continue;
+                const int64_t gi = ((int64_t)yy * width + xx) * 3 + ch;
+                const float a = __ldg(x_img + gi), b = __ldg(y_img + gi), w = win.w[dx + half];
+                rx = fmaf(w, a, rx);
+                ry = fmaf(w, b, ry);
+                rq = fmaf(w, fmaf(a, a, b * b), rq);
+                rxy = fmaf(w, a * b, rxy);
+            }
+            const float wy = win.w[dy + half];
+            mx = fmaf(wy, rx, mx); my = fmaf(wy, ry, my); qq = fmaf(wy, rq, qq); xy = fmaf(wy, rxy, xy);
+        }
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+        const float sxy = xy - mx * my;
+        const float A1 = 2.0f * mx * my + C1, A2 = 2.0f * sxy + C2;
+        const float B1 = mx * mx + my * my + C1, B2 = (qq - mx * mx - my * my) + C2;
+        const float inv = __frcp_rn(B1 * B2);
+        const float S = A1 * A2 * inv;
+        const float rB1 = B2 * inv, rB2 = B1 * inv;
+        g1[e] = 2.0f * my * (A2 - A1) * inv - 2.0f * mx * S * (rB1 - rB2);
+        g2[e] = -S * rB2;
+        g3[e] = 2.0f * A1 * inv;
+        s_local = S;
+        l1_local = fabsf(__ldg(x_img + e) - __ldg(y_img + e));
+        if (ssim_map != nullptr) {  // channel mean: the three channels of a pixel sit in adjacent lanes / threads
+            // (written by the channel-0 thread after a neighbour exchange through global memory would race:
+            //  use an atomic on a map the host zeroed)
+            atomicAdd(&ssim_map[pix], S / 3.0f);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        l1_local += __shfl_xor_sync(kFull, l1_local, d);
+        s_local += __shfl_xor_sync(kFull, s_local, d);
+    }
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = l1_local; s_red[1][threadIdx.x >> 5] = s_local; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += (double)s_red[0][w]; b += (double)s_red[1][w]; }
+        atomicAdd(&sums[0], a);
+        atomicAdd(&sums[1], b);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ssim_gradient_any(int width, int height, SsimWindowAny win, float lambda, const float* __restrict__ x_img,
+                    const float* __restrict__ y_img, const float* __restrict__ g1, const float* __restrict__ g2,
+                    const float* __restrict__ g3, float* __restrict__ dL_dx) {
+    const int64_t total = (int64_t)width * height * 3;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int ch = (int)(e % 3);
+    const int64_t pix = e / 3;
+    const int gx = (int)(pix % width), gy = (int)(pix / width);
+    const int half = win.size / 2;
+    float m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    for (int dy = -half; dy <= half; ++dy) {
+        const int yy = gy + dy;
+        if (yy < 0 || yy >= height) continue;
+        float r1 = 0.f, r2 = 0.f, r3 = 0.f;
+        for (int dx = -half; dx <= half; ++dx) {
+            const int xx = gx + dx;
+            if (xx < 0 || xx >= width) continue;
+            const int64_t gi = ((int64_t)yy * width + xx) * 3 + ch;
+            const float w = win.w[dx + half];
+            r1 = fmaf(w, __ldg(g1 + gi), r1);
+            r2 = fmaf(w, __ldg(g2 + gi), r2);
+            r3 = fmaf(w, __ldg(g3 + gi), r3);
+        }
+        const float wy = win.w[dy + half];
+        m1 = fmaf(wy, r1, m1); m2 = fmaf(wy, r2, m2); m3 = fmaf(wy, r3, m3);
+    }
+    const float inv_n = 1.0f / (3.0f * (float)width * (float)height);
+    const float xv = __ldg(x_img + e), yv = __ldg(y_img + e);
+    const float d = xv - yv;
+    const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+    dL_dx[e] = (1.0f - lambda) * sgn * inv_n - lambda * inv_n * (m1 + 2.0f * xv * m2 + yv * m3);
+}
+
+// loss.cpp:57-70 for any size: float 1-D gaussian (sigma 1.5) / sum; 2-D = outer product / its sum
+static void window_factor(int size, float* out) {
+    float k[kMaxWindow], sum = 0.f;
+    const int half = size / 2;
+    for (int i = 0; i < size; ++i) {
+        const float x = (float)(i - half);
         k[i] = std::exp(-x * x / (2.0f * 1.5f * 1.5f));
         sum += k[i];
     }
-    for (int i = 0; i < 11; ++i) k[i] = k[i] / sum;
+    for (int i = 0; i < size; ++i) k[i] = k[i] / sum;
     double s2 = 0.0;
-    for (int i = 0; i < 11; ++i)
-        for (int j = 0; j < 11; ++j) s2 += (double)(k[i] * k[j]);
+    for (int i = 0; i < size; ++i)
+        for (int j = 0; j < size; ++j) s2 += (double)(k[i] * k[j]);
+    for (int i = 0; i < size; ++i) out[i] = (float)((double)k[i] / std::sqrt(s2));
+}
+
+static SsimWindow make_window() {
     SsimWindow w;
-    for (int i = 0; i < 11; ++i) w.w[i] = (float)((double)k[i] / std::sqrt(s2));
+    window_factor(11, w.w);
     return w;
 }
 
@@ -467,10 +585,15 @@ extern "C" size_t cugs_b200_loss_workspace_bytes(int width, int height) {
 }
 
 extern "C" int cugs_b200_loss_l1_ssim(cugs_handle_t* h, void* stream, int width, int height, float lambda,
-                                      const float* rendered, const float* target, float* dL_dcolor,
-                                      float* scalars3, void* workspace, size_t workspace_bytes, float* ssim_map) {
+                                      int window_size, const float* rendered, const float* target,
+                                      float* dL_dcolor, float* scalars3, void* workspace, size_t workspace_bytes,
+                                      float* ssim_map) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, width > 0 && height > 0, "image size must be positive");
+    CUGS_REQUIRE(h, window_size % 2 == 1, "window_size must be odd");                 // loss.cpp:91
+    CUGS_REQUIRE(h, window_size >= 3, "window_size must be >= 3");                    // loss.cpp:92
+    if (window_size > kMaxWindow)
+        return set_error(h, CUGS_ERR_UNSUPPORTED, "window_size %d > %d is not supported", window_size, kMaxWindow);
     CUGS_REQUIRE(h, rendered && target && scalars3 && workspace, "null pointer");
     if (workspace_bytes < cugs_b200_loss_workspace_bytes(width, height))
         return set_error(h, CUGS_ERR_WORKSPACE, "loss workspace too small: %zu < %zu", workspace_bytes,
@@ -483,6 +606,24 @@ extern "C" int cugs_b200_loss_l1_ssim(cugs_handle_t* h, void* stream, int width,
     float* g2 = g1 + plane;
     float* g3 = g2 + plane;
     CUGS_CUDA_TRY(h, cudaMemsetAsync(sums, 0, 64, s));
+    if (window_size != 11) {  // generic window: the fall-back kernels
+        SsimWindowAny wa;
+        wa.size = window_size;
+        for (int i = 0; i < kMaxWindow; ++i) wa.w[i] = 0.f;
+        window_factor(window_size, wa.w);
+        const unsigned blocks = (unsigned)((plane + 255) / 256);
+        if (ssim_map) CUGS_CUDA_TRY(h, cudaMemsetAsync(ssim_map, 0, (size_t)width * height * sizeof(float), s));
+        k_ssim_moments_any<<<blocks, 256, 0, s>>>(width, height, wa, rendered, target, g1, g2, g3, sums, ssim_map);
+        CUGS_LAUNCH_CHECK(h, "k_ssim_moments_any");
+        if (dL_dcolor) {
+            k_ssim_gradient_any<<<blocks, 256, 0, s>>>(width, height, wa, lambda, rendered, target, g1, g2, g3,
+                                                       dL_dcolor);
+            CUGS_LAUNCH_CHECK(h, "k_ssim_gradient_any");
+        }
+        k_loss_finalize<<<1, 1, 0, s>>>(width, height, lambda, sums, scalars3);
+        CUGS_LAUNCH_CHECK(h, "k_loss_finalize");
+        return CUGS_OK;
+    }
     const dim3 grid((width + kLossTile - 1) / kLossTile, (height + kLossTile - 1) / kLossTile);
     k_ssim_moments<<<grid, 256, 0, s>>>(width, height, win, rendered, target, g1, g2, g3, sums, ssim_map);
     CUGS_LAUNCH_CHECK(h, "k_ssim_moments");

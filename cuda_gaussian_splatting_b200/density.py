@@ -73,7 +73,7 @@ class DensificationController(DensificationStats):
         model.opacities.fill_(RESET_OPACITY)
 
     def reset_accumulators(self, n: int, device) -> None:  # densification.cpp:344-349
-        DensificationStats.__init__(self, n, device)
+        self._reset(n, device)
 
     # ---- classification ----
     def _native_config(self, step: int) -> CugsDensifyConfig:

@@ -443,7 +443,11 @@ class FrameBuffers:
         self.n_contrib = torch.empty((height, width), **i)
         self.tile_ranges = torch.empty((num_tiles(width, height), 2), **i)
         self.gaussian_indices = torch.empty((max(p_capacity, 1),), **i)
-        self.workspace = torch.empty((1,), dtype=torch.uint8, device=device)
+        # frame arena: the N-sized head (packed blend records, binning state, 2-D gradient accumulator) has a
+        # fixed size; the P-sized pair scratch is a separate block that grows without touching the head
+        lib = _lib.load_library()
+        self.workspace = torch.empty((lib.cugs_b200_render_workspace_bytes(n, 0),), dtype=torch.uint8, device=device)
+        self.pair_scratch = torch.empty((1,), dtype=torch.uint8, device=device)
         self.p_capacity = 0
         self.ensure_capacity(max(p_capacity, 1))
         # gradients: ONE contiguous arena laid out as the five Adam groups (fused_adam.cu:94-97:
@@ -474,26 +478,41 @@ class FrameBuffers:
         self.grad_compact = None                                  # lazily allocated by parallel.sparse_allreduce_step
         self.touch_offsets = None
         self.dL_dmeans_2d = torch.empty((n, 2), **f)
+        # frames rendered without the host round trip (render(..., sync=False)): {P, overflowed} on the device
+        # and its pinned host copy, refreshed by fetch_status()
+        self.status_dev = torch.zeros((2,), dtype=torch.int64, device=device)
+        self.status_host = torch.zeros((2,), dtype=torch.int64).pin_memory() if torch.device(device).type == "cuda" \
+            else torch.zeros((2,), dtype=torch.int64)
+
+    def fetch_status(self, non_blocking: bool = True) -> None:
+        """Queue the device->host copy of {P, overflowed} of the last sync=False frame on the current stream."""
+        self.status_host.copy_(self.status_dev, non_blocking=non_blocking)
+
+    def last_pairs(self):
+        """(P, overflowed) of the last fetched frame; valid once the stream that ran fetch_status() is synchronised."""
+        return int(self.status_host[0]), bool(int(self.status_host[1]))
 
     def ensure_capacity(self, p: int) -> None:
         if p <= self.p_capacity:
             return
         lib = _lib.load_library()
         cap = int(p * 1.25) + 1024
-        old = self.workspace
-        self.workspace = torch.empty((lib.cugs_b200_render_workspace_bytes(self.n, cap),), dtype=torch.uint8,
-                                     device=old.device)
-        # the N-sized head (packed records, tile counts, offsets) must survive a re-size
-        keep = min(old.numel(), lib.cugs_b200_render_workspace_bytes(self.n, 0))
-        if old.numel() > 1:
-            self.workspace[:keep].copy_(old[:keep])
-        self.gaussian_indices = torch.empty((cap,), dtype=torch.int32, device=old.device)
+        dev = self.workspace.device
+        self.pair_scratch = torch.empty((lib.cugs_b200_render_pair_scratch_bytes(cap),), dtype=torch.uint8, device=dev)
+        self.gaussian_indices = torch.empty((cap,), dtype=torch.int32, device=dev)
         self.p_capacity = cap
 
 
 def render(model: GaussianModel, camera: CameraInfo, settings: RenderSettings,
-           buffers: Optional[FrameBuffers] = None) -> RenderOutput:
-    """rasterizer.hpp:57-60 / rasterizer.cpp:22-113."""
+           buffers: Optional[FrameBuffers] = None, sync: bool = True) -> RenderOutput:
+    """rasterizer.hpp:57-60 / rasterizer.cpp:22-113.
+
+    ``sync=False`` (needs ``buffers`` whose pair capacity was established by an earlier frame or by
+    ``ensure_capacity``): nothing blocks -- the pair count P stays on the device, every launch is sized on the
+    buffers' capacity (cugs_b200_render_forward), ``gaussian_indices`` is returned at full capacity (entries
+    beyond P are not written; the kernels never read them) and ``buffers.status_dev`` receives {P, overflowed}.
+    Call ``buffers.fetch_status()`` and check ``buffers.last_pairs()`` after a synchronisation point (e.g. once per
+    step): an overflowed frame must be re-rendered (``sync=True`` grows the capacity)."""
     _check(model.is_valid(), "GaussianModel is not valid")
     _check(model.positions.is_cuda, "GaussianModel must be on CUDA device")
     dev = model.positions.device
@@ -517,6 +536,17 @@ def render(model: GaussianModel, camera: CameraInfo, settings: RenderSettings,
     v = make_view(camera, settings, active, sh.shape[2])
     b = buffers if buffers is not None else FrameBuffers(n, W, H, sh.shape[2], dev)
     _check(b.n == n and b.width == W and b.height == H, "FrameBuffers do not match the model / camera")
+    if not sync:
+        _check(buffers is not None and b.p_capacity > 1, "sync=False needs FrameBuffers with an established pair capacity")
+        st = lib.cugs_b200_render_forward(
+            h, s, n, b.p_capacity, C.byref(v), _ptr(pos), _ptr(rot), _ptr(scl), _ptr(opa), _ptr(sh), _ptr(b.means_2d),
+            _ptr(b.depths), _ptr(b.cov_2d_inv), _ptr(b.radii), _ptr(b.rgb), _ptr(b.opacities_act),
+            b.gaussian_indices.data_ptr(), _ptr(b.tile_ranges), _ptr(b.color), _ptr(b.final_T), _ptr(b.n_contrib),
+            _ptr(b.workspace), b.workspace.numel(), _ptr(b.pair_scratch), b.pair_scratch.numel(),
+            b.status_dev.data_ptr())
+        _lib.check(h, st, "cugs_b200_render_forward")
+        return RenderOutput(b.color, b.final_T, b.n_contrib, b.means_2d, b.depths, b.cov_2d_inv, b.radii, b.rgb,
+                            b.opacities_act, b.gaussian_indices[:b.p_capacity], b.tile_ranges, _workspace=b.workspace)
     p = C.c_int64(0)
     st = lib.cugs_b200_render_plan(h, s, n, C.byref(v), _ptr(pos), _ptr(rot), _ptr(scl), _ptr(opa), _ptr(sh),
                                    _ptr(b.means_2d), _ptr(b.depths), _ptr(b.cov_2d_inv), _ptr(b.radii),
@@ -528,10 +558,30 @@ def render(model: GaussianModel, camera: CameraInfo, settings: RenderSettings,
     st = lib.cugs_b200_render_finish(h, s, n, P, C.byref(v), _ptr(b.means_2d), _ptr(b.depths), _ptr(b.cov_2d_inv),
                                      _ptr(b.radii), _ptr(b.rgb), _ptr(b.opacities_act),
                                      b.gaussian_indices.data_ptr(), _ptr(b.tile_ranges), _ptr(b.color),
-                                     _ptr(b.final_T), _ptr(b.n_contrib), _ptr(b.workspace), b.workspace.numel())
+                                     _ptr(b.final_T), _ptr(b.n_contrib), _ptr(b.workspace), b.workspace.numel(),
+                                     _ptr(b.pair_scratch), b.pair_scratch.numel())
     _lib.check(h, st, "cugs_b200_render_finish")
     return RenderOutput(b.color, b.final_T, b.n_contrib, b.means_2d, b.depths, b.cov_2d_inv, b.radii, b.rgb,
                         b.opacities_act, b.gaussian_indices[:P], b.tile_ranges, _workspace=b.workspace)
+
+
+def count_evaluations(render_out: RenderOutput, camera: CameraInfo) -> dict:
+    """MEASUREMENT ONLY: the (pixel, Gaussian) evaluations the reference's traversal performs on this frame,
+    split into alpha-rejected and contributing ones, forward (rasterizer/forward.cu:121-157) and backward
+    (rasterizer/backward.cu:117-145) -- the work units of the blend kernels' FP32 / MUFU roofline.
+    Blocks (one device->host copy of four counters)."""
+    r = render_out
+    dev = r.color.device
+    lib, h = _lib_and_handle(dev)
+    v = make_view(camera, RenderSettings(), 0, 1)
+    counts = torch.zeros((4,), dtype=torch.int64, device=dev)
+    st = lib.cugs_b200_count_evaluations(h, _stream(dev), C.byref(v), _ptr(r.tile_ranges),
+                                         r.gaussian_indices.data_ptr(), _ptr(r.means_2d), _ptr(r.cov_2d_inv),
+                                         _ptr(r.opacities_act), _ptr(r.n_contrib), counts.data_ptr())
+    _lib.check(h, st, "cugs_b200_count_evaluations")
+    c = [int(x) for x in counts.cpu()]
+    return {"fwd_rejected": c[0], "fwd_contributing": c[1], "bwd_rejected": c[2], "bwd_contributing": c[3],
+            "E_fwd": c[0] + c[1], "E_bwd": c[2] + c[3]}
 
 
 class ImageBuffers:
@@ -549,6 +599,7 @@ class ImageBuffers:
         self.tile_ranges = torch.empty((num_tiles(width, height), 2), **i)
         lib = _lib.load_library()
         self.workspace = torch.empty((lib.cugs_b200_render_workspace_bytes(n, 0),), dtype=torch.uint8, device=device)
+        self.pair_scratch = torch.empty((1,), dtype=torch.uint8, device=device)
         self.gaussian_indices = torch.empty((1,), **i)
         self.p_capacity = 0
 
@@ -586,7 +637,8 @@ def render_image(model: GaussianModel, camera: CameraInfo, settings: RenderSetti
     b.ensure_capacity(P)
     st = lib.cugs_b200_render_finish(h, s, n, P, C.byref(v), _ptr(b.means_2d), None, None, _ptr(b.radii), None, None,
                                      b.gaussian_indices.data_ptr(), _ptr(b.tile_ranges), _ptr(b.color),
-                                     _ptr(b.final_T), _ptr(b.n_contrib), _ptr(b.workspace), b.workspace.numel())
+                                     _ptr(b.final_T), _ptr(b.n_contrib), _ptr(b.workspace), b.workspace.numel(),
+                                     _ptr(b.pair_scratch), b.pair_scratch.numel())
     _lib.check(h, st, "cugs_b200_render_finish")
     return b.color, b.final_T, b.n_contrib
 

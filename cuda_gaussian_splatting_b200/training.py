@@ -42,10 +42,14 @@ _loss_ws: dict = {}
 
 
 def combined_loss_with_grad(rendered: torch.Tensor, target: torch.Tensor, lambda_: float = 0.2,
-                            want_grad: bool = True, ssim_map: Optional[torch.Tensor] = None):
+                            want_grad: bool = True, ssim_map: Optional[torch.Tensor] = None,
+                            window_size: int = 11):
     """One fused pass: returns (scalars[3] = {loss, l1, mean ssim} on device, dL/d(rendered)).
-    ``ssim_map`` (optional [H,W] output) receives what the reference's ``ssim()`` returns."""
+    ``ssim_map`` (optional [H,W] output) receives what the reference's ``ssim()`` returns.
+    ``window_size``: any odd size >= 3 (loss.cpp:91-92); 11 is the default of every reference caller."""
     _validate_pair(rendered, target)
+    _check(window_size % 2 == 1, f"window_size must be odd, got {window_size}")      # loss.cpp:91
+    _check(window_size >= 3, f"window_size must be >= 3, got {window_size}")          # loss.cpp:92
     dev = rendered.device
     lib, h = _lib_and_handle(dev)
     H, W = int(rendered.shape[0]), int(rendered.shape[1])
@@ -56,7 +60,7 @@ def combined_loss_with_grad(rendered: torch.Tensor, target: torch.Tensor, lambda
         _loss_ws[key] = ws
     scalars = torch.empty((3,), dtype=torch.float32, device=dev)
     grad = torch.empty_like(rendered, memory_format=torch.contiguous_format) if want_grad else None
-    st = lib.cugs_b200_loss_l1_ssim(h, _stream(dev), W, H, float(lambda_), _ptr(rendered.contiguous()),
+    st = lib.cugs_b200_loss_l1_ssim(h, _stream(dev), W, H, float(lambda_), int(window_size), _ptr(rendered.contiguous()),
                                     _ptr(target.contiguous()), _ptr(grad), _ptr(scalars), _ptr(ws), ws.numel(),
                                     _ptr(ssim_map))
     _lib.check(h, st, "cugs_b200_loss_l1_ssim")
@@ -71,15 +75,14 @@ def l1_loss(rendered, target) -> torch.Tensor:  # loss.hpp:22
     return combined_loss_with_grad(rendered, target, 0.0, want_grad=False)[0][1]
 
 
-def ssim_loss(rendered, target) -> torch.Tensor:  # loss.hpp:43
-    return 1.0 - combined_loss_with_grad(rendered, target, 1.0, want_grad=False)[0][2]
+def ssim_loss(rendered, target, window_size: int = 11) -> torch.Tensor:  # loss.hpp:43
+    return 1.0 - combined_loss_with_grad(rendered, target, 1.0, want_grad=False, window_size=window_size)[0][2]
 
 
 def ssim(rendered, target, window_size: int = 11) -> torch.Tensor:  # loss.hpp:33 -> [H,W] map
-    _check(window_size == 11, f"only the reference's default window_size = 11 is implemented, got {window_size}")
     _validate_pair(rendered, target)
     m = torch.empty(rendered.shape[:2], dtype=torch.float32, device=rendered.device)
-    combined_loss_with_grad(rendered, target, 1.0, want_grad=False, ssim_map=m)
+    combined_loss_with_grad(rendered, target, 1.0, want_grad=False, ssim_map=m, window_size=window_size)
     return m
 
 
@@ -259,6 +262,12 @@ class DensificationStats:
     """The per-step accumulators of DensificationController (optimizer/densification.cpp:59-88)."""
 
     def __init__(self, n: int, device):
+        self._reset(n, device)
+
+    def _reset(self, n: int, device) -> None:
+        """(Re)allocate the three accumulators as zeros. A plain method, NOT __init__: subclasses
+        (density.DensificationController) have a different constructor signature, so the lazy
+        re-initialisation below must not dispatch to it."""
         self.grad_accum = torch.zeros((n,), dtype=torch.float32, device=device)
         self.grad_count = torch.zeros((n,), dtype=torch.float32, device=device)
         self.max_radii_2d = torch.zeros((n,), dtype=torch.float32, device=device)
@@ -269,7 +278,7 @@ class DensificationStats:
     def accumulate_gradients(self, dL_dmeans_2d: torch.Tensor, radii: torch.Tensor) -> None:
         n = dL_dmeans_2d.shape[0]
         if self.grad_accum.shape[0] != n:  # lazy re-init (:66-68)
-            self.__init__(n, dL_dmeans_2d.device)
+            self._reset(n, dL_dmeans_2d.device)
         if n == 0:
             return
         dev = dL_dmeans_2d.device

@@ -18,8 +18,9 @@
  *   all f32 unless noted, contiguous, row-major, 16-byte aligned base pointers.
  *
  * Threading / streams: a handle belongs to one device and is NOT thread-safe (it owns the pinned
- * word through which render_plan returns P, the error string and the optional stage-timing
- * events); use one handle per host thread. Every kernel is launched on the stream passed in; the
+ * words through which the blocking calls return their counts -- a ring, one word per call, so frames
+ * in flight on several streams and scans issued in between do not disturb each other -- the error
+ * string and the optional stage-timing events); use one handle per host thread. Every kernel is launched on the stream passed in; the
  * only blocking calls are cugs_b200_render_plan and cugs_b200_scan with total_host != NULL (one
  * cudaStreamSynchronize each, the read the reference does at rasterizer/sorting.cu:146),
  * cugs_b200_densify_classify and cugs_b200_mcmc_relocate with counts_host != NULL (the counts the
@@ -38,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CUGS_B200_ABI_VERSION 6 /* bump on ANY signature change: callers compare it with cugs_b200_abi_version() */
+#define CUGS_B200_ABI_VERSION 7 /* bump on ANY signature change: callers compare it with cugs_b200_abi_version() */
 #define CUGS_TILE 16 /* rasterizer/sorting.hpp:16 kTileSize */
 
 enum {
@@ -129,6 +130,23 @@ int cugs_b200_sort_pairs(cugs_handle_t* h, void* stream, int64_t p, int depth_bi
                          uint64_t* keys_in, int32_t* values_in, uint64_t* keys_out,
                          int32_t* values_out, void* temp, size_t temp_bytes);
 
+/* The packed sort of the fused render path, exposed as a stage function (tests, callers that build
+ * their own binning). Stable ascending LSD sort of n packed 8-byte elements by the low key_bits bits of
+ * their HIGH word (the low word is the payload, e.g. tile_id << 32 | gaussian index), 1-4 onesweep passes
+ * of at most 8 bits (cugs_b200_sort_packed_passes). elts_a holds the input and is clobbered; the result
+ * is in elts_b when the number of passes is odd, else in elts_a -- unless out32_last != NULL, in which
+ * case the last pass writes only the low words there and the elements are not materialised.
+ * tile_ranges (optional, needs num_tiles <= 2^key_bits): [num_tiles,2] i32 ranges [start,end) of each key
+ * value in the sorted order, {0,0} for absent keys -- what k_compute_tile_ranges (rasterizer/sorting.cu:
+ * 82-109) derives from the sorted keys, taken here from the key histogram of the same read.
+ * n_dev (optional, device int64): the element count is min(*n_dev, n) read ON THE DEVICE and n is only the
+ * capacity of the buffers; every launch is sized on n, so no host round trip is needed for the count. */
+int cugs_b200_sort_packed_passes(int key_bits);
+size_t cugs_b200_sort_packed_temp_bytes(int64_t n, int key_bits, int num_tiles);
+int cugs_b200_sort_packed(cugs_handle_t* h, void* stream, int64_t n, int key_bits, uint64_t* elts_a,
+                          uint64_t* elts_b, int32_t* out32_last, int num_tiles, int32_t* tile_ranges,
+                          void* temp, size_t temp_bytes, const int64_t* n_dev);
+
 /* ---- stage 4: tile ranges (rasterizer/sorting.cu:82-109); zero-fills tile_ranges first ----- */
 int cugs_b200_tile_ranges(cugs_handle_t* h, void* stream, int64_t p, const uint64_t* keys_sorted,
                           int num_tiles, int32_t* tile_ranges);
@@ -152,6 +170,15 @@ int cugs_b200_blend_bwd(cugs_handle_t* h, void* stream, int64_t n, const cugs_vi
                         const float* final_T, const int32_t* n_contrib, float* dL_drgb,
                         float* dL_dopacity_act, float* dL_dmeans_2d, float* dL_dcov_2d_inv,
                         float* grad_acc);
+/* Measurement only (never on a hot path): counts the (pixel, Gaussian) evaluations of the REFERENCE's
+ * traversal of a frame -- counts4_dev (device, 4 x u64) = {forward alpha-rejected, forward contributing,
+ * backward alpha-rejected, backward contributing}, the work units E_fwd / E_bwd of the blend kernels'
+ * FP32 / MUFU roofline (rasterizer/forward.cu:121-157, rasterizer/backward.cu:117-145). */
+int cugs_b200_count_evaluations(cugs_handle_t* h, void* stream, const cugs_view_t* v,
+                                const int32_t* tile_ranges, const int32_t* gaussian_idx,
+                                const float* means_2d, const float* cov_2d_inv,
+                                const float* opacities_act, const int32_t* n_contrib,
+                                uint64_t* counts4_dev);
 /* preprocess_bwd replaces project_backward (rasterizer/projection_backward.cu:253-344):
  * k_project_backward (:26-247) + directions + evaluate_sh_backward_cuda (core/sh_backward.cu),
  * one launch. rgb = forward output (its sign is the ReLU gate). All outputs fully written.
@@ -191,6 +218,28 @@ int cugs_b200_preprocess_bwd(cugs_handle_t* h, void* stream, int64_t n, const cu
  * written (the blend reads the packed records of the workspace). Such a frame cannot be passed to
  * render_backward. */
 size_t cugs_b200_render_workspace_bytes(int64_t n, int64_t p_capacity);
+/* The workspace has an N-sized head (lives from render_plan to render_backward: cugs_b200_render_workspace_bytes(n, 0))
+ * and a P-sized tail that is only used inside render_finish. A caller that sizes its allocations per frame (the
+ * libtorch wrapper) passes the tail as a SEPARATE block pair_scratch of cugs_b200_render_pair_scratch_bytes(p)
+ * bytes, so that learning P does not force it to re-allocate and copy the head; pair_scratch = NULL means the
+ * tail follows the head inside `workspace` (cugs_b200_render_workspace_bytes(n, p) bytes). */
+size_t cugs_b200_render_pair_scratch_bytes(int64_t p_capacity);
+/* render_forward = render_plan + render_finish WITHOUT the host round trip for P: gaussian_idx and the
+ * workspace are sized for p_capacity pairs, every launch is sized on that capacity and the kernels read
+ * the frame's pair count on the device. Nothing blocks, so a whole training step can be queued ahead or
+ * captured in a CUDA graph (the reference blocks once per frame, rasterizer/sorting.cu:146).
+ * status_dev (optional, DEVICE memory, 2 x int64): receives {P, P > p_capacity}. An overflowed frame is
+ * safe (pairs beyond the capacity are dropped, no kernel runs past a buffer) but its image and gradients
+ * are incomplete: the caller reads the status whenever convenient (e.g. once per step), and re-runs the
+ * frame with a larger capacity. Entries of gaussian_idx beyond P are not written. */
+int cugs_b200_render_forward(cugs_handle_t* h, void* stream, int64_t n, int64_t p_capacity,
+                             const cugs_view_t* v, const float* positions, const float* rotations,
+                             const float* scales, const float* opacities, const float* sh_coeffs,
+                             float* means_2d, float* depths, float* cov_2d_inv, int32_t* radii,
+                             float* rgb, float* opacities_act, int32_t* gaussian_idx,
+                             int32_t* tile_ranges, float* color, float* final_T, int32_t* n_contrib,
+                             void* workspace, size_t workspace_bytes, void* pair_scratch,
+                             size_t pair_scratch_bytes, int64_t* status_dev);
 int cugs_b200_render_plan(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
                           const float* positions, const float* rotations, const float* scales,
                           const float* opacities, const float* sh_coeffs, float* means_2d,
@@ -202,7 +251,7 @@ int cugs_b200_render_finish(cugs_handle_t* h, void* stream, int64_t n, int64_t p
                             const float* cov_2d_inv, const int32_t* radii, const float* rgb,
                             const float* opacities_act, int32_t* gaussian_idx, int32_t* tile_ranges,
                             float* color, float* final_T, int32_t* n_contrib, void* workspace,
-                            size_t workspace_bytes);
+                            size_t workspace_bytes, void* pair_scratch, size_t pair_scratch_bytes);
 int cugs_b200_render_backward(cugs_handle_t* h, void* stream, int64_t n, const cugs_view_t* v,
                               const float* positions, const float* rotations, const float* scales,
                               const float* opacities, const float* sh_coeffs,
@@ -234,10 +283,13 @@ int cugs_b200_get_stage_ms(cugs_handle_t* h, float* ms8);
  * reference gets the gradient from libtorch autograd, training/trainer.cpp:214-217).
  * scalars3 (device) = {loss, l1, mean ssim}. workspace: cugs_b200_loss_workspace_bytes(w,h).
  * ssim_map (optional, may be NULL): [H,W] per-pixel SSIM averaged over the three channels, what
- * cugs::ssim returns (training/loss.cpp:88-124; consumed by training/metrics.cpp:41-46). */
+ * cugs::ssim returns (training/loss.cpp:88-124; consumed by training/metrics.cpp:41-46).
+ * window_size: side of the gaussian window (sigma 1.5), odd, 3..33 (loss.hpp:33-44; loss.cpp:91-92 reject
+ * even sizes and sizes < 3): 11 = the default every training caller uses (tuned kernels); any other size
+ * runs generic fall-back kernels with the same formulation. */
 size_t cugs_b200_loss_workspace_bytes(int width, int height);
 int cugs_b200_loss_l1_ssim(cugs_handle_t* h, void* stream, int width, int height, float lambda,
-                           const float* rendered, const float* target, float* dL_dcolor,
+                           int window_size, const float* rendered, const float* target, float* dL_dcolor,
                            float* scalars3, void* workspace, size_t workspace_bytes, float* ssim_map);
 /* Adam: FusedAdam::step (optimizer/fused_adam.cu:140-164) + k_fused_adam (:44-76) for all five
  * groups in ONE launch. Group order positions, sh_coeffs, opacities, scales, rotations

@@ -57,3 +57,18 @@ def test_budget_cap_keeps_the_highest_average_gradients():  # densification.cpp:
     assert flags.tolist() == [3, 1, 1, 1, 3, 1, 5, 1, 3, 1]
     ctrl._cap(flags, 2, 0)                                                         # no budget: all candidates dropped
     assert flags.tolist() == [1, 1, 1, 1, 1, 1, 5, 1, 1, 1]
+
+
+def test_lazy_resize_keeps_the_controller_intact():
+    """densification.cpp:66-68: accumulate_gradients re-initialises the accumulators when N changed. The
+    re-initialisation must not run the controller's own constructor (config / scene_extent would be
+    clobbered)."""
+    import torch
+    cfg = cugs.DensificationConfig(grad_threshold=0.123)
+    ctrl = cugs.DensificationController(cfg, 7.5, 5, "cpu", seed=99)
+    ctrl.grad_accum += 1.0
+    ctrl.accumulate_gradients(torch.zeros((0, 2)), torch.zeros((0,), dtype=torch.int32))  # resize 5 -> 0, nothing to add
+    assert ctrl.grad_accum.shape == (0,) and ctrl.grad_count.shape == (0,) and ctrl.max_radii_2d.shape == (0,)
+    assert ctrl.config is cfg and ctrl.scene_extent == 7.5 and ctrl.seed == 99
+    ctrl.reset_accumulators(3, "cpu")
+    assert ctrl.grad_accum.shape == (3,) and float(ctrl.grad_accum.sum()) == 0.0 and ctrl.config is cfg

@@ -88,6 +88,10 @@ def test_loss_autograd_and_adam_same_call_two_libraries(ref, dropin, torch):
     assert abs(float(lr_) - float(ld)) <= 1e-5 and abs(float(l1r) - float(l1d)) <= 1e-6 and abs(float(sr) - float(sd)) <= 1e-5
     assert float((gr - gd).abs().max()) <= 1e-3 * float(gr.abs().max())
     assert float((ref.ssim(x, y) - dropin.ssim(x, y)).abs().max()) <= 1e-4   # [H,W] map (metrics.cpp:41-46)
+    for window in (7, 5, 15):                                                  # any odd window (loss.hpp:33-44)
+        assert float((ref.ssim(x, y, window) - dropin.ssim(x, y, window)).abs().max()) <= 1e-4
+    with pytest.raises(RuntimeError):
+        dropin.ssim(x, y, 8)
     with pytest.raises(RuntimeError):  # c10::Error, as tests/test_loss.cpp:143-170 expects
         dropin.combined_loss(x[:, :, :2], y[:, :, :2])
     scene = cugs.synth(1003, 64, 48, seed=21)

@@ -453,6 +453,44 @@ def test_loss_vs_reference_autograd(ref, torch, shape):
     assert ok, msg
 
 
+@pytest.mark.parametrize("window", [3, 5, 7, 9, 13, 21])
+def test_ssim_any_odd_window_vs_reference(ref, torch, window):
+    """loss.hpp:33-44 lets the caller choose window_size (any odd size >= 3, loss.cpp:91-92): map and mean
+    against the reference's conv2d formulation, gradient against torch autograd of the same formulation."""
+    rng = np.random.default_rng(60 + window)
+    H, W = 57, 83
+    x = torch.from_numpy(rng.uniform(size=(H, W, 3)).astype(np.float32)).cuda()
+    y = torch.from_numpy(rng.uniform(size=(H, W, 3)).astype(np.float32)).cuda()
+    ref_map = ref.ssim(x, y, window)
+    mine = cugs.ssim(x, y, window)
+    assert mine.shape == ref_map.shape and float((mine - ref_map).abs().max()) <= 1e-4
+    assert abs(float(cugs.ssim_loss(x, y, window)) - (1.0 - float(ref_map.mean()))) <= 1e-5
+
+    def torch_ssim_loss(xr):  # loss.cpp:44-124 restated with torch ops (fp32 reference of the same op)
+        half = window // 2
+        k1 = torch.exp(-(torch.arange(window, dtype=torch.float32) - half) ** 2 / (2 * 1.5 * 1.5))
+        k1 = k1 / k1.sum()
+        k2 = k1[:, None] * k1[None, :]
+        k2 = (k2 / k2.sum()).cuda()[None, None].expand(3, 1, window, window).contiguous()
+        conv = lambda t: torch.nn.functional.conv2d(t, k2, padding=half, groups=3)
+        a, b = xr.permute(2, 0, 1)[None], y.permute(2, 0, 1)[None]
+        mx, my = conv(a), conv(b)
+        sx, sy, sxy = conv(a * a) - mx * mx, conv(b * b) - my * my, conv(a * b) - mx * my
+        m = ((2 * mx * my + 1e-4) * (2 * sxy + 9e-4)) / ((mx * mx + my * my + 1e-4) * (sx + sy + 9e-4))
+        return 0.8 * (xr - y).abs().mean() + 0.2 * (1.0 - m.mean())
+
+    xr = x.clone().requires_grad_(True)
+    loss = torch_ssim_loss(xr)
+    loss.backward()
+    sc, g = cugs.combined_loss_with_grad(x, y, 0.2, window_size=window)
+    assert abs(float(sc[0]) - float(loss)) <= 1e-5
+    ok, msg = grad_close(np_(g), np_(xr.grad))
+    assert ok, msg
+    for bad in (4, 1, 35):
+        with pytest.raises(RuntimeError):
+            cugs.ssim(x, y, bad)
+
+
 def test_loss_vs_cpu_oracle_and_known_answers(oracle, torch):  # test_loss.cpp:39-137
     rng = np.random.default_rng(2)
     x = rng.uniform(size=(50, 70, 3)).astype(np.float32)
@@ -702,6 +740,23 @@ def test_accumulate_stats_vs_reference_controller(ref, torch):
     ra, rc, rm = ref.accumulate_gradients(g, r, 3)   # optimizer/densification.cpp:59-88, unmodified
     assert torch.equal(st.grad_count, rc) and torch.equal(st.max_radii_2d, rm)
     assert float((st.grad_accum - ra).abs().max()) <= 1e-6 * float(ra.abs().max())
+
+
+def test_controller_lazy_init_then_resize_vs_reference_controller(ref, torch):
+    """The reference's lazy-init pattern (densification.cpp:66-68): construct the controller without N,
+    then accumulate; and again after the model size changed."""
+    rng = np.random.default_rng(17)
+    cfg = cugs.DensificationConfig(grad_threshold=0.5)
+    ctrl = cugs.DensificationController(cfg, 3.0, 0, "cuda")
+    for n in (7001, 1234):
+        g = torch.from_numpy(rng.normal(size=(n, 2)).astype(np.float32)).cuda()
+        r = torch.from_numpy(rng.integers(0, 5, size=n).astype(np.int32)).cuda()
+        for _ in range(2):
+            ctrl.accumulate_gradients(g, r)
+        ra, rc, rm = ref.accumulate_gradients(g, r, 2)
+        assert ctrl.grad_accum.shape == (n,) and ctrl.config is cfg and ctrl.scene_extent == 3.0
+        assert torch.equal(ctrl.grad_count, rc) and torch.equal(ctrl.max_radii_2d, rm)
+        assert float((ctrl.grad_accum - ra).abs().max()) <= 1e-6 * float(ra.abs().max())
 
 
 def test_mcmc_regulariser_fused_in_adam_vs_reference(ref, torch):

@@ -98,22 +98,33 @@ int tiles_of(int w, int h) { return ((w + kTileSize - 1) / kTileSize) * ((h + kT
 // ---- per-frame workspace cache: RenderOutput has no slot for the packed blend records, so the
 // workspace of the most recent frames is remembered by the address of their means_2d tensor ----
 struct Frame {
-    torch::Tensor workspace;
-    torch::Tensor means_2d;  // keeps the key address alive
+    torch::Tensor workspace;  // the N-sized frame arena (packed blend records, 2-D gradient accumulator)
+    torch::Tensor means_2d;   // keeps the key address alive
+    uint64_t stamp;           // last use, for LRU eviction
 };
 std::mutex g_frames_mu;
 std::unordered_map<const void*, Frame> g_frames;
-constexpr size_t kMaxFrames = 4;
+uint64_t g_frame_clock = 0;
+constexpr size_t kMaxFrames = 8;  // frames a caller may hold between render() and render_backward()
 
+// Bounded LRU: only the least recently used frame is dropped when the cache is full (a caller holding more
+// than kMaxFrames RenderOutputs falls back to the stage path for the oldest ones, never for the newest).
 void remember_frame(const torch::Tensor& means_2d, const torch::Tensor& ws) {
     std::lock_guard<std::mutex> lock(g_frames_mu);
-    if (g_frames.size() >= kMaxFrames) g_frames.clear();
-    g_frames[means_2d.data_ptr()] = Frame{ws, means_2d};
+    if (g_frames.size() >= kMaxFrames && g_frames.find(means_2d.data_ptr()) == g_frames.end()) {
+        auto oldest = g_frames.begin();
+        for (auto it = g_frames.begin(); it != g_frames.end(); ++it)
+            if (it->second.stamp < oldest->second.stamp) oldest = it;
+        g_frames.erase(oldest);
+    }
+    g_frames[means_2d.data_ptr()] = Frame{ws, means_2d, ++g_frame_clock};
 }
 torch::Tensor recall_frame(const torch::Tensor& means_2d) {
     std::lock_guard<std::mutex> lock(g_frames_mu);
     auto it = g_frames.find(means_2d.data_ptr());
-    return it == g_frames.end() ? torch::Tensor() : it->second.workspace;
+    if (it == g_frames.end()) return torch::Tensor();
+    it->second.stamp = ++g_frame_clock;
+    return it->second.workspace;
 }
 
 }  // namespace
@@ -159,17 +170,14 @@ RenderOutput render(const GaussianModel& model, const CameraInfo& camera, const 
     out.rgb = torch::empty({n, 3}, f32);
     out.opacities_act = torch::empty({n}, f32);
     const auto u8 = f32.dtype(torch::kUInt8);
-    const size_t head_bytes = cugs_b200_render_workspace_bytes(n, 0);
-    auto ws = torch::empty({(int64_t)head_bytes}, u8);
+    // the N-sized frame arena lives until render_backward; the P-sized pair scratch is a separate block that
+    // goes back to the caching allocator right after render_finish (stream-ordered reuse: no copy, no cudaMalloc)
+    auto ws = torch::empty({(int64_t)cugs_b200_render_workspace_bytes(n, 0)}, u8);
     int64_t P = 0;
     CUGS_CALL(h, cugs_b200_render_plan(h, stream, n, &v, fp(pos), fp(rot), fp(scl), fp(opa), fp(sh), fp(out.means_2d),
                                        fp(out.depths), fp(out.cov_2d_inv), ip(out.radii), fp(out.rgb),
                                        fp(out.opacities_act), ws.data_ptr(), (size_t)ws.numel(), &P));
-    if (P > 0) {  // grow the workspace for the P-sized scratch, keeping the N-sized head
-        auto big = torch::empty({(int64_t)cugs_b200_render_workspace_bytes(n, P)}, u8);
-        big.narrow(0, 0, (int64_t)head_bytes).copy_(ws);
-        ws = big;
-    }
+    auto scratch = torch::empty({(int64_t)cugs_b200_render_pair_scratch_bytes(P)}, u8);
     out.gaussian_indices = torch::empty({P}, i32);
     out.tile_ranges = torch::empty({tiles_of(W, H), 2}, i32);
     out.color = torch::empty({H, W, 3}, f32);
@@ -178,7 +186,8 @@ RenderOutput render(const GaussianModel& model, const CameraInfo& camera, const 
     CUGS_CALL(h, cugs_b200_render_finish(h, stream, n, P, &v, fp(out.means_2d), fp(out.depths), fp(out.cov_2d_inv),
                                          ip(out.radii), fp(out.rgb), fp(out.opacities_act), ip(out.gaussian_indices),
                                          ip(out.tile_ranges), fp(out.color), fp(out.final_T), ip(out.n_contrib),
-                                         ws.data_ptr(), (size_t)ws.numel()));
+                                         ws.data_ptr(), (size_t)ws.numel(), scratch.data_ptr(),
+                                         (size_t)scratch.numel()));
     remember_frame(out.means_2d, ws);
     return out;
 }
@@ -453,7 +462,7 @@ void validate_pair(const torch::Tensor& rendered, const torch::Tensor& target) {
 
 // scalars3 = {loss, l1, mean ssim}; optional gradient and SSIM map
 torch::Tensor fused_loss(const torch::Tensor& rendered, const torch::Tensor& target, float lambda, torch::Tensor* grad,
-                         torch::Tensor* ssim_map) {
+                         torch::Tensor* ssim_map, int window_size = 11) {
     validate_pair(rendered, target);
     cugs_handle_t* h = handle_for(rendered);
     const int H = (int)rendered.size(0), W = (int)rendered.size(1);
@@ -463,7 +472,8 @@ torch::Tensor fused_loss(const torch::Tensor& rendered, const torch::Tensor& tar
     const auto x = rendered.contiguous(), y = target.contiguous();
     if (grad) *grad = torch::empty({H, W, 3}, f32);
     if (ssim_map) *ssim_map = torch::empty({H, W}, f32);
-    CUGS_CALL(h, cugs_b200_loss_l1_ssim(h, current_stream(rendered), W, H, lambda, fp(x), fp(y), grad ? fp(*grad) : nullptr,
+    CUGS_CALL(h, cugs_b200_loss_l1_ssim(h, current_stream(rendered), W, H, lambda, window_size, fp(x), fp(y),
+                                        grad ? fp(*grad) : nullptr,
                                         fp(scalars), ws.data_ptr(), (size_t)ws.numel(),
                                         ssim_map ? fp(*ssim_map) : nullptr));
     return scalars;
@@ -471,16 +481,17 @@ torch::Tensor fused_loss(const torch::Tensor& rendered, const torch::Tensor& tar
 
 struct FusedLossFn : public torch::autograd::Function<FusedLossFn> {
     static torch::Tensor forward(torch::autograd::AutogradContext* ctx, const torch::Tensor& rendered,
-                                 const torch::Tensor& target, double lambda, int64_t which) {
+                                 const torch::Tensor& target, double lambda, int64_t which, int64_t window_size) {
         torch::Tensor grad;
-        const auto scalars = fused_loss(rendered.detach(), target.detach(), (float)lambda, &grad, nullptr);
+        const auto scalars =
+            fused_loss(rendered.detach(), target.detach(), (float)lambda, &grad, nullptr, (int)window_size);
         ctx->save_for_backward({grad});
         return scalars[which].clone();
     }
     static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx,
                                                    torch::autograd::variable_list grad_out) {
         const auto saved = ctx->get_saved_variables();
-        return {saved[0] * grad_out[0], torch::Tensor(), torch::Tensor(), torch::Tensor()};
+        return {saved[0] * grad_out[0], torch::Tensor(), torch::Tensor(), torch::Tensor(), torch::Tensor()};
     }
 };
 
@@ -488,7 +499,7 @@ struct FusedLossFn : public torch::autograd::Function<FusedLossFn> {
 
 torch::Tensor l1_loss(const torch::Tensor& rendered, const torch::Tensor& target) {
     validate_pair(rendered, target);
-    if (rendered.requires_grad()) return FusedLossFn::apply(rendered, target, 0.0, 0);  // lambda 0: loss == l1
+    if (rendered.requires_grad()) return FusedLossFn::apply(rendered, target, 0.0, 0, 11);  // lambda 0: loss == l1
     return fused_loss(rendered, target, 0.0f, nullptr, nullptr)[1];
 }
 
@@ -496,21 +507,22 @@ torch::Tensor ssim(const torch::Tensor& rendered, const torch::Tensor& target, i
     validate_pair(rendered, target);
     TORCH_CHECK(window_size % 2 == 1, "window_size must be odd, got ", window_size);
     TORCH_CHECK(window_size >= 3, "window_size must be >= 3, got ", window_size);
-    TORCH_CHECK(window_size == 11, "the fused kernel implements the reference's default window_size = 11 only");
     torch::Tensor map;
-    fused_loss(rendered, target, 1.0f, nullptr, &map);
+    fused_loss(rendered, target, 1.0f, nullptr, &map, window_size);
     return map;  // [H, W], channel mean of the SSIM map (loss.cpp:123)
 }
 
 torch::Tensor ssim_loss(const torch::Tensor& rendered, const torch::Tensor& target, int window_size) {
-    TORCH_CHECK(window_size == 11, "the fused kernel implements the reference's default window_size = 11 only");
-    if (rendered.requires_grad()) return FusedLossFn::apply(rendered, target, 1.0, 0);  // lambda 1: loss == 1 - ssim
-    return 1.0f - fused_loss(rendered, target, 1.0f, nullptr, nullptr)[2];
+    TORCH_CHECK(window_size % 2 == 1, "window_size must be odd, got ", window_size);
+    TORCH_CHECK(window_size >= 3, "window_size must be >= 3, got ", window_size);
+    if (rendered.requires_grad())
+        return FusedLossFn::apply(rendered, target, 1.0, 0, window_size);  // lambda 1: loss == 1 - ssim
+    return 1.0f - fused_loss(rendered, target, 1.0f, nullptr, nullptr, window_size)[2];
 }
 
 torch::Tensor combined_loss(const torch::Tensor& rendered, const torch::Tensor& target, float lambda_) {
     validate_pair(rendered, target);
-    if (rendered.requires_grad()) return FusedLossFn::apply(rendered, target, (double)lambda_, 0);
+    if (rendered.requires_grad()) return FusedLossFn::apply(rendered, target, (double)lambda_, 0, 11);
     return fused_loss(rendered, target, lambda_, nullptr, nullptr)[0];
 }
 
