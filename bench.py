@@ -151,25 +151,47 @@ def sort_passes(P_bits_depth: int, num_tiles: int) -> int:
 
 
 def algorithmic_bytes(n: int, p: int, w: int, h: int, tile_passes: int, views: int = 1, touched=None) -> dict:
-    """ALGORITHMIC bytes per frame of each stage: each distinct input read once +
-    each output written once, for the kernels as designed (depth passes hoisted before the key
-    duplication: the sort moves 8-byte packed elements)."""
+    """ALGORITHMIC bytes per frame of each HBM-bound stage = SURVEY.md §8(d)'s per-unit figure x the units
+    of one frame (each distinct input read once + each output written once, for the REFERENCE formulation
+    of the stage). `design_bytes` (below) is what this design actually has to move; it is reported beside
+    it, never used for `achieved`."""
     tiles = ((w + 15) // 16) * ((h + 15) // 16)
     return {
-        "preprocess_fwd": (284 + 48 + 8) * n,        # reference outputs + packed blend record + depth-sort element
-        "scan": 16 * n,                              # sorted element (8) + gathered tile count (4) + offset (4)
-        "duplicate_with_keys": 28 * n + 8 * p,       # element, offset, radius, tiles, mean (8+4+4+4+8) + packed pair
+        "preprocess_fwd": 284 * n,                   # 236 in (12+16+12+4+192) + 48 out
+        "scan": 8 * n,                               # tiles_touched in, offsets out
+        "duplicate_with_keys": 20 * n + 12 * p,      # mean, radius, tiles, offset per Gaussian + 12-B pair out
+        "sort": (8 + 24 * (4 + tile_passes)) * p,    # 1 histogram read of the keys + passes x (read 12 + write 12)
+        "tile_ranges": 8 * p + 8 * tiles,
+        "preprocess_bwd": 336 * n,                   # 44 params + 4 radii + 36 incoming + 12 rgb in, 236 out
+        "loss": 36 * w * h,                          # rendered + target in, dL/dcolor out
+        "adam": 28 * 59 * n,                         # p, g, m, v in; p, m, v out
+    }
+
+
+def design_bytes(n: int, p: int, w: int, h: int, tile_passes: int, views: int = 1, touched=None) -> dict:
+    """Bytes the kernels of THIS design move per frame: the depth passes are hoisted in
+    front of duplicateWithKeys (8-byte packed elements), preprocess also writes the 48-byte blend record and
+    the 8-byte depth-sort element, preprocess_bwd skips the untouched gradient rows."""
+    tiles = ((w + 15) // 16) * ((h + 15) // 16)
+    return {
+        "preprocess_fwd": (284 + 48 + 8) * n,
+        "scan": 16 * n,
+        "duplicate_with_keys": 28 * n + 8 * p,
         "sort": (8 + 4 * 16) * n + (8 + 16 * (tile_passes - 1) + 12) * p + 12 * tiles,
-        "tile_ranges": 0,                            # part of the sort (tile histogram -> ranges)
-        "blend_fwd": 52 * p + 20 * w * h,            # index (4) + packed record (48) per pair, 20 B per pixel
-        "blend_bwd": 52 * p + 20 * w * h + 48 * n,   # + dL/dcolor, final_T, n_contrib per pixel, 48-B gradient record
-        # dense: 336 B/Gaussian, views after the first of a step also READ the 236-B gradient row they
-        # add to. Sparse rows (touched = fraction of Gaussians with a gradient): 120 B/Gaussian of inputs,
-        # mask and dL/dmeans_2d, plus the 236-B row written (first view) or read+written (later views)
-        # for the touched fraction only.
+        "tile_ranges": 0,
         "preprocess_bwd": int(((336 + 236 * (views - 1) / max(views, 1)) if touched is None else
                                (120 + 236 * touched * (2 * views - 1) / max(views, 1))) * n),
+        "loss": (36 + 72) * w * h,
+        "adam": 28 * 59 * n,
     }
+
+
+# SURVEY.md §8(d) work units of the two blend kernels: FLOP (FMA = 2) and MUFU operations per
+# (pixel, Gaussian) evaluation of the REFERENCE traversal (counted exactly by cugs_b200_count_evaluations)
+FWD_FLOP = {"rejected": 15, "contributing": 24}
+BWD_FLOP = {"rejected": 15, "contributing": 55}
+FWD_MUFU = {"rejected": 1, "contributing": 1}
+BWD_MUFU = {"rejected": 1, "contributing": 2}
 
 
 def reference_sort_bytes(p: int, w: int, h: int) -> int:
@@ -198,7 +220,17 @@ def bench_views(scene, count: int):
     return cams
 
 
+MIN_TIMED_MS = 1000.0  # the timed region lasts at least this long whatever --steps says (clock sampling, noise)
+
+
+def calibrated_steps(requested: int, est_ms_per_step: float) -> int:
+    import math
+    return max(int(requested), int(math.ceil(MIN_TIMED_MS * 1.05 / max(est_ms_per_step, 1e-3))))
+
+
 def run_b200(args) -> dict:
+    import ctypes as C
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -213,7 +245,10 @@ def run_b200(args) -> dict:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, W, H, seed, desc = WORKLOADS[args.workload]
-    V = args.views_per_gpu
+    strong = args.views_total > 0
+    if strong:
+        assert args.views_total % world == 0, "--views-total must be a multiple of the number of GPUs"
+    V = args.views_total // world if strong else args.views_per_gpu
     scene = cugs.synth(n, W, H, seed=seed)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     model = cugs.GaussianModel(t(scene.positions), t(scene.sh_coeffs), t(scene.opacities), t(scene.rotations),
@@ -227,43 +262,63 @@ def run_b200(args) -> dict:
     if args.mode == "train_step":
         return run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world, local, dev, desc)
 
-    # synthetic targets (host, pinned) and the resident dL/dcolor of each view
+    # synthetic targets (host, pinned) and the resident dL/dcolor of each view; the blocking renders also
+    # establish the pair capacity of every buffer used below
     rng = np.random.default_rng(4321 + rank)
     targets_host = [torch.from_numpy(rng.uniform(size=(H, W, 3)).astype(np.float32)).pin_memory() for _ in range(V)]
     target_dev = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
-    scal_host = torch.empty((3,), dtype=torch.float32).pin_memory()
     dLs, Ps = [], []
+    work = None
     for v in range(V):
         out = cugs.render(model, cams[v], settings, buf)
         Ps.append(int(out.gaussian_indices.numel()))
+        if v == 0 and rank == 0:
+            work = cugs.count_evaluations(out, cams[0])   # E_fwd / E_bwd of view 0 (measurement only)
         target_dev.copy_(targets_host[v], non_blocking=True)
         _, g = cugs.combined_loss_with_grad(out.color, target_dev, 0.2)
         dLs.append(g)
     torch.cuda.synchronize()
+    p_cap = int(max(Ps) * 1.25) + 4096
 
+    with_stats = world > 1   # north_star: "parameter gradients plus densification statistics" in the exchange
     exchange = {"mode": "single"}
+    exch_state = {}
 
     def allreduce():
         # the step's gradient exchange: sparse (MAX-reduce of the touch mask + ONE sum all-reduce of the
-        # touched rows) unless --dense-allreduce (ONE sum all-reduce of the whole 61N-float arena)
+        # touched rows and the additive statistics) unless --dense-allreduce (ONE sum all-reduce of the whole
+        # 61N-float arena + the MAX-reduce of max_radii)
         if world == 1:
             return
         if args.dense_allreduce:
-            cugs.allreduce_step(buf.grad_arena)
+            cugs.allreduce_step(buf.grad_arena, buf.step_max_radii if with_stats else None)
             exchange.update(mode="dense")
         else:
-            exchange.update(cugs.sparse_allreduce_step(buf, with_stats=False))
+            exchange.update(cugs.sparse_allreduce_step(buf, with_stats=with_stats, state=exch_state))
     # touch mask + sparse gradient rows (rows a view does not touch are neither read nor written) unless
     # the dense exchange is requested (it sums rows this rank's mask does not know about)
-    touch = None if args.dense_allreduce else buf.touch_mask
+    sparse = not args.dense_allreduce
+    touch = buf.touch_mask if sparse else None
 
-    # Two frames in flight inside one step: view v runs on stream v % 2 with its own frame buffers, so
-    # the preprocess / sort / forward blend of view v+1 overlap the (issue-bound) backward blend of view v.
-    # The gradient arena is shared: view v's backward waits for view v-1's (in-place accumulation), and a
-    # step starts only after the previous step has completely finished (no overlap across steps, where a
-    # real training loop has its optimizer update).
+    # ---- headline path: the C++ step driver's "views" phase (cugs_b200_trainer_step, phases = 1) with a given
+    # dL/dcolor per view = forward + backward only. No host round trip per view (device-side pair count),
+    # two frames in flight on two streams, the whole step replayed as ONE CUDA graph.
+    tcfg = cugs.TrainConfig(densify=with_stats)
+    nat = cugs.NativeTrainer(model, cams, [None] * V, tcfg, total_views_per_step=world * V, pair_capacity=p_cap,
+                             frames_in_flight=1 if args.no_overlap else 2, use_graph=not args.no_graph,
+                             sparse_rows=sparse, grad_buffers=buf, dL_dcolors=dLs)
+    step_no = [3000]
+
+    def step_resident():
+        nat.step_views(step_no[0])
+        step_no[0] += 1
+        allreduce()
+
+    # ---- end-to-end path: the public Python API, per view H2D target -> render -> loss -> backward -> D2H loss
     streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)] if V > 1 and not args.no_overlap else None
     bufs = [buf, cugs.FrameBuffers(n, W, H, 16, dev, share_grads_with=buf)] if streams else [buf, buf]
+    for b in bufs:
+        b.ensure_capacity(max(Ps))
 
     def run_views(per_view):
         if streams is None:
@@ -275,49 +330,38 @@ def run_b200(args) -> dict:
         start.record(cur)
         prev_bwd = None
         for v in range(V):
-            s = streams[v % 2]
-            s.wait_event(start)
-            with torch.cuda.stream(s):
+            s_ = streams[v % 2]
+            s_.wait_event(start)
+            with torch.cuda.stream(s_):
                 prev_bwd = per_view(v, bufs[v % 2], prev_bwd)
         cur.wait_event(prev_bwd)
 
-    def view_resident(v, b, prev_bwd):
-        out = cugs.render(model, cams[v], settings, b)
-        if prev_bwd is not None:
-            torch.cuda.current_stream(dev).wait_event(prev_bwd)
-        cugs.render_backward(dLs[v], out, model, cams[v], settings, b, accumulate=(v > 0), touch_mask=touch,
-                             sparse_rows=touch is not None)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
-        return ev
-
-    def step_resident():
-        run_views(view_resident)
-        allreduce()
-
     uploader = cugs.TargetUploader(H, W, dev)
     uploader.prefetch(targets_host[0])
-
     scal_hosts = [torch.empty((3,), dtype=torch.float32).pin_memory() for _ in range(V)]
+    stats_e2e = (buf.step_grad_accum, buf.step_grad_count, buf.step_max_radii) if with_stats else None
 
     def view_e2e(v, b, prev_bwd):
         # every view's target is copied host->device (pinned, side stream) INSIDE the step; the copy of
         # the next view overlaps the rendering of the current one
         tgt = uploader.get()
         uploader.prefetch(targets_host[(v + 1) % V])                          # H2D of the next view's target
-        out = cugs.render(model, cams[v], settings, b)
+        out = cugs.render(model, cams[v], settings, b, sync=False)            # no host round trip for P
         sc, g = cugs.combined_loss_with_grad(out.color, tgt, 0.2)
         uploader.release()
         if prev_bwd is not None:
             torch.cuda.current_stream(dev).wait_event(prev_bwd)
-        cugs.render_backward(g, out, model, cams[v], settings, b, accumulate=(v > 0), touch_mask=touch,
-                             sparse_rows=touch is not None)
+        cugs.render_backward(g, out, model, cams[v], settings, b, stats=stats_e2e, accumulate=(v > 0),
+                             touch_mask=touch, sparse_rows=sparse)
         scal_hosts[v].copy_(sc, non_blocking=True)                            # D2H of {loss, l1, ssim}
+        b.fetch_status()                                                      # D2H of {P, overflowed}
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
         return ev
 
     def step_e2e():
+        if with_stats:
+            buf.step_grad_accum.zero_(); buf.step_grad_count.zero_(); buf.step_max_radii.zero_()
         run_views(view_e2e)
         allreduce()
         torch.cuda.current_stream().synchronize()                             # the losses are on the host now
@@ -340,28 +384,37 @@ def run_b200(args) -> dict:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def agree_steps(k):  # every rank must run the same number of steps (collectives inside)
+        tk = torch.tensor([k], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        return int(tk.item())
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_resident()
+    steps = agree_steps(calibrated_steps(args.steps, timed(step_resident, 5) / 5))
     l0 = int(lib.cugs_b200_launch_count(h))
     sampler.mark_begin()
-    total_ms = timed(step_resident, args.steps)
+    total_ms = timed(step_resident, steps)
     sampler.mark_end()
     launches = int(lib.cugs_b200_launch_count(h)) - l0
+    _, ok, pmax, _ = nat.result()
+    assert ok, f"a frame overflowed the pair capacity ({pmax} > {p_cap}): the timed region is invalid"
 
-    # second pass: per-stage device timing (events recorded by the library on the launching stream)
-    import ctypes as C
+    # ---- per-stage device timing (events recorded by the library on the launching stream), one frame in flight
     stage_sum = [0.0] * len(STAGES)
     stage_cnt = 0
     lib.cugs_b200_set_stage_timing(h, 1)
     ms8 = (C.c_float * 8)()
-    for _ in range(args.steps):
-        for v in range(V):  # (one frame in flight here: the stage events are per handle)
-            out = cugs.render(model, cams[v], settings, buf)
+    for _ in range(min(steps, 30)):
+        for v in range(V):
+            out = cugs.render(model, cams[v], settings, buf, sync=False)
             cugs.render_backward(dLs[v], out, model, cams[v], settings, buf, accumulate=(v > 0), touch_mask=touch,
-                                 sparse_rows=touch is not None)
+                                 sparse_rows=sparse)
             lib.cugs_b200_get_stage_ms(h, ms8)
             for k in range(8):
                 stage_sum[k] += max(float(ms8[k]), 0.0)
@@ -369,14 +422,49 @@ def run_b200(args) -> dict:
     lib.cugs_b200_set_stage_timing(h, 0)
     stages_ms = {nm: stage_sum[k] / max(stage_cnt, 1) for k, nm in enumerate(STAGES)}
 
+    # ---- the per-step kernels either side of the rasterizer, timed alone with an L2
+    # flush between iterations (their inputs at 1080p fit in the 126 MB L2)
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+
+    def timed_alone(fn, iters=10):
+        ts = []
+        for _ in range(iters + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts[2:])
+
+    extra_ms = {}
+    if rank == 0:
+        out0 = cugs.render(model, cams[0], settings, buf)
+        target_dev.copy_(targets_host[0])
+        extra_ms["loss"] = timed_alone(lambda: cugs.combined_loss_with_grad(out0.color, target_dev, 0.2))
+        scratch = cugs.GaussianModel(*[x.clone() for x in (model.positions, model.sh_coeffs, model.opacities,
+                                                           model.rotations, model.scales)])
+        opt = cugs.FusedAdam(scratch)
+        opt.apply_gradients(cugs.BackwardOutput(buf.dL_dpositions, buf.dL_drotations, buf.dL_dscales, buf.dL_dopacities,
+                                                buf.dL_dsh_coeffs, buf.dL_dmeans_2d))
+        extra_ms["adam"] = timed_alone(opt.step)
+        del scratch, opt
+    exchange_ms = None
+    if world > 1:   # the exchange alone, on the gradients of a finished step (every rank, max over ranks)
+        step_resident()
+        exchange_ms = timed(allreduce, 10) / 10
+    del flush
+
     for _ in range(3):
         step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
+    e2e_steps = agree_steps(calibrated_steps(args.steps, timed(step_e2e, 5) / 5))
+    e2e_ms = timed(step_e2e, e2e_steps)
+    e2e_overflow = any(b.last_pairs()[1] for b in set(bufs))
+    assert not e2e_overflow, "an end-to-end frame overflowed its pair capacity"
     clocks = sampler.stop() if rank == 0 else {}
 
-    views = world * V * args.steps
+    views = world * V * steps
     value = views / (total_ms * 1e-3)
-    e2e_value = views / (e2e_ms * 1e-3)
+    e2e_value = world * V * e2e_steps / (e2e_ms * 1e-3)
 
     res = None
     if rank == 0:
@@ -384,61 +472,101 @@ def run_b200(args) -> dict:
         c_passes, c_bits = C.c_int(0), C.c_int(0)
         lib.cugs_b200_last_sort_plan(h, C.byref(c_passes), C.byref(c_bits))
         passes, key_bits = int(c_passes.value), int(c_bits.value)
-        touched_frac = float(buf.touch_mask.float().mean()) if touch is not None else None
-        alg = algorithmic_bytes(n, P, W, H, max(passes - 4, 1), V, touched_frac)
+        touched_frac = float((buf.touch_mask != 0).float().mean()) if touch is not None else None
+        tile_passes = max(passes - 4, 1)
+        alg = algorithmic_bytes(n, P, W, H, tile_passes, V, touched_frac)
+        des = design_bytes(n, P, W, H, tile_passes, V, touched_frac)
         peak, peak_src = measured_peaks()
-        hbm_stages = ["preprocess_fwd", "scan", "duplicate_with_keys", "sort", "preprocess_bwd"]
+        sms, khz, l2 = C.c_int(0), C.c_int(0), C.c_int(0)
+        lib.cugs_b200_device_info(h, C.byref(sms), C.byref(khz), C.byref(l2))
+        clock_ghz = khz.value / 1e6
+        fp32_peak = sms.value * 128 * 2 * clock_ghz / 1e3      # TFLOP/s: SMs x 128 lanes x 2 (FMA) x clock
+        mufu_peak = sms.value * 16 * clock_ghz / 1e3           # T op/s: SMs x 16 SFU lanes x clock
+        all_ms = dict(stages_ms)
+        all_ms.update(extra_ms)
         rl_all = {}
-        for nm in STAGES:
-            ms = stages_ms[nm]
+        for nm in ["preprocess_fwd", "scan", "duplicate_with_keys", "sort", "tile_ranges", "preprocess_bwd", "loss", "adam"]:
+            ms = all_ms.get(nm, 0.0)
             gbs = alg[nm] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-            rl_all[nm] = {"ms": round(ms, 4), "algorithmic_bytes": alg[nm], "achieved_gbs": round(gbs, 1),
-                          "frac_of_hbm_peak": round(gbs / peak, 4),
-                          "bound": "hbm" if nm in hbm_stages else "fp32-issue/L2-atomics (not HBM)"}
-        # `roofline`: the largest HBM-bound stage that is ONE kernel launch (the sort stage is a dozen
-        # launches); the two blend kernels dominate the step but are instruction-issue bound, their
-        # HBM fraction is not a quality measure — see roofline_all / issue_bound and DESIGN.md §4
-        single = ["preprocess_fwd", "preprocess_bwd", "duplicate_with_keys", "scan"]
-        dom = max(single, key=lambda k: stages_ms[k])
-        kname = {"preprocess_fwd": "k_preprocess_fwd", "preprocess_bwd": "k_preprocess_bwd",
-                 "duplicate_with_keys": "k_duplicate_sorted", "scan": "k_scan_exclusive"}[dom]
-        roofline = {"kernel": kname, "bound": "hbm", "achieved": rl_all[dom]["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": rl_all[dom]["frac_of_hbm_peak"], "traffic": TRAFFIC.get(kname),
-                    "peak_source": peak_src, "ms": rl_all[dom]["ms"],
-                    "algorithmic_bytes_per_launch": alg[dom]}
+            rl_all[nm] = {"ms": round(ms, 4), "bound": "hbm", "algorithmic_bytes": alg[nm], "design_bytes": des[nm],
+                          "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4),
+                          "design_gbs": round(des[nm] / (ms * 1e-3) / 1e9, 1) if ms > 0 else 0.0}
+        rl_all["tile_ranges"]["note"] = "no separate pass: the ranges come from the tile histogram inside the sort stage"
+        rl_all["sort"]["note"] = ("algorithmic bytes = the reference formulation (12-B pairs, 6 passes): the design sorts the "
+                                  "depth bits on the N Gaussians and only the tile bits on the pairs, so achieved_gbs can "
+                                  "exceed the HBM peak; design_gbs is the traffic this design really has")
+        rl_all["loss"]["note"] = "k_ssim_moments + k_ssim_gradient + k_loss_finalize, timed alone with an L2 flush in between"
+        rl_all["adam"]["note"] = "k_adam_multi over 59 N floats, timed alone with an L2 flush in between"
+        for nm, fl, mu, e_r, e_c in (("blend_fwd", FWD_FLOP, FWD_MUFU, "fwd_rejected", "fwd_contributing"),
+                                     ("blend_bwd", BWD_FLOP, BWD_MUFU, "bwd_rejected", "bwd_contributing")):
+            ms = stages_ms[nm]
+            flop = fl["rejected"] * work[e_r] + fl["contributing"] * work[e_c]
+            mufu = mu["rejected"] * work[e_r] + mu["contributing"] * work[e_c]
+            tf = flop / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            tm = mufu / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            rl_all[nm] = {"ms": round(ms, 4), "bound": "fp32-issue", "evaluations_rejected": work[e_r],
+                          "evaluations_contributing": work[e_c], "algorithmic_flop": flop, "algorithmic_mufu": mufu,
+                          "achieved_tflops": round(tf, 3), "frac_of_fp32_peak": round(tf / fp32_peak, 4),
+                          "achieved_tmufu": round(tm, 4), "frac_of_mufu_peak": round(tm / mufu_peak, 4),
+                          "hbm_bytes": (40 * P + 20 * W * H) + (36 * P if nm == "blend_bwd" else 0)}
+        if exchange_ms is not None:
+            ex_floats = exchange.get("floats") or buf.grad_arena.numel()
+            rl_all["exchange"] = {"ms": round(exchange_ms, 4), "bound": "nvlink", "bytes_summed": 4 * int(ex_floats),
+                                  "bytes_max_reduced": 8 * n, "mode": exchange.get("mode"),
+                                  "note": "whole exchange of one step, timed alone after a finished step (max over ranks)"}
+        # `roofline`: the DOMINANT kernel of the step, k_blend_bwd, against the FP32-issue roofline of SURVEY 8(d)
+        bwd = rl_all["blend_bwd"]
+        roofline = {"kernel": "k_blend_bwd", "bound": "fp32-issue", "achieved": bwd["achieved_tflops"],
+                    "peak": round(fp32_peak, 2), "unit": "TFLOP/s", "frac": bwd["frac_of_fp32_peak"],
+                    "traffic": TRAFFIC.get("k_blend_bwd"), "ms": bwd["ms"], "share_of_step": round(bwd["ms"] / max(sum(stages_ms.values()), 1e-9), 3),
+                    "work": "E_bwd of view 0 by the reference traversal (backward.cu:117-145): 15 FLOP + 1 EX2 per "
+                            "alpha-rejected, 55 FLOP + 1 EX2 + 1 RCP per contributing evaluation (SURVEY 8d)",
+                    "mufu": {"achieved": bwd["achieved_tmufu"], "peak": round(mufu_peak, 3), "unit": "T op/s",
+                             "frac": bwd["frac_of_mufu_peak"]},
+                    "peak_source": f"{sms.value} SMs x 128 FP32 lanes x 2 x {clock_ghz:.3f} GHz (cudaDeviceGetAttribute)",
+                    "hbm_peak_gbs": peak, "hbm_peak_source": peak_src}
         ref_sort_gbs = reference_sort_bytes(P, W, H) / (stages_ms["sort"] * 1e-3) / 1e9 if stages_ms["sort"] > 0 else 0.0
         res = {
-            "metric": METRIC, "value": round(value, 3), "unit": "views/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4),
-            "ms_per_view": round(total_ms / args.steps / V, 4), "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": round(value, 3), "unit": "views/s", "n_gpus": world, "steps": steps,
+            "steps_requested": args.steps, "warmup": warm, "ms_per_step": round(total_ms / steps, 4),
+            "ms_per_view": round(total_ms / steps / V, 4), "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "views_per_gpu_per_step": V, "frames_in_flight": 2 if streams else 1,
-                       "P_pairs_view0": P, "sort_passes": passes,
-                       "sort_key_bits": key_bits,
+            "config": {"workload": desc, "views_per_gpu_per_step": V, "views_per_step": world * V,
+                       "frames_in_flight": 1 if args.no_overlap else 2,
+                       "driver": "cugs_b200_trainer_step(phases = views): C++ step driver, device-side pair count, "
+                                 + ("one CUDA graph per step" if not args.no_graph else "eager launches"),
+                       "P_pairs_view0": P, "pair_capacity": p_cap, "sort_passes": passes, "sort_key_bits": key_bits,
+                       "densification_stats_fused": with_stats,
                        "collective": "none" if world == 1 else (
-                           "one NCCL all-reduce(sum) of the 61N-float arena per step" if args.dense_allreduce else
-                           "per step: int32 MAX all-reduce of the touch mask (8 B/Gaussian) + ONE all-reduce(sum) of the "
-                           "touched gradient rows"),
+                           "one NCCL all-reduce(sum) of the 61N-float arena per step (+ MAX of max_radii)" if args.dense_allreduce else
+                           "per step: int32 MAX all-reduce of [touch mask | max_radii] (8 B/Gaussian) + ONE all-reduce(sum) of the "
+                           "touched gradient rows and the additive statistics"),
                        "gradient_exchange": exchange, "touched_fraction": touched_frac,
+                       "min_timed_ms": MIN_TIMED_MS,
                        "l2": "no flush needed: per-step inputs (708 MB of Gaussian parameters at 3M) exceed the 126 MB L2"},
             "clocks": clocks,
-            "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "ms_per_view": round(e2e_ms / args.steps / V, 4),
-                    "h2d_bytes_per_step": V * H * W * 3 * 4, "d2h_bytes_per_step": V * 12,
-                    "what": "per view: H2D target (pinned, side stream, overlapped with the previous view) -> render -> "
-                            "fused L1+SSIM loss+grad -> render_backward -> D2H loss"},
+            "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "ms_per_view": round(e2e_ms / e2e_steps / V, 4),
+                    "steps": e2e_steps,
+                    "h2d_bytes_per_step": V * H * W * 3 * 4, "d2h_bytes_per_step": V * (12 + 16),
+                    "what": "public Python API, per view: H2D target (pinned, side stream, overlapped with the previous view) -> "
+                            "render(sync=False) -> fused L1+SSIM loss+grad -> render_backward -> D2H {loss, l1, ssim} + {P, overflow}"},
             "gpu_launches": launches,
             "roofline": roofline,
+            "work_view0": work,
             "stages_ms": {k: round(v_, 4) for k, v_ in stages_ms.items()},
             "stages_sum_ms": round(sum(stages_ms.values()), 4),
             "roofline_all": rl_all,
             "sort_gbs": round(ref_sort_gbs, 1),
             "sort_gbs_note": "bytes of the reference formulation (12-B pairs, 6 onesweep passes at 1080p = 152 B/pair) "
-                             "divided by the time of this library's whole sort stage (depth sort of N + tile sort of P); "
-                             "roofline_all.sort uses the bytes this design actually has to move",
+                             "divided by the time of this library's whole sort stage (depth sort of N + tile sort of P): a "
+                             "cross-implementation throughput, NOT a bandwidth; the traffic this design has is "
+                             "roofline_all.sort.design_gbs; CUB on the same pairs: profiles/r02/sort_bench*.jsonl",
             "sort_mpairs_per_s": round(P / (stages_ms["sort"] * 1e-3) / 1e6, 1) if stages_ms["sort"] > 0 else None,
         }
         if world == 1 and not args.no_cpu_baseline:
             res["cpu_baseline"] = cpu_baseline(scene, args.workload)
+    nat.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -446,21 +574,31 @@ def run_b200(args) -> dict:
 
 
 def run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world, local, dev, desc):
-    """BASELINE.json configs[2]: the full training step (render fwd + fused L1/SSIM loss + render bwd
-    with fused densification statistics + one all-reduce + ONE fused Adam launch) through
-    SyntheticTrainer (the Trainer::train_step skeleton, training/trainer.cpp:178-316)."""
+    """BASELINE.json configs[2] / [3]: the full training step (render fwd + fused L1/SSIM loss + render bwd
+    with fused densification statistics + gradient exchange + ONE fused Adam launch) through the C++ step
+    driver (cugs_b200_trainer_step; Trainer::train_step, training/trainer.cpp:178-316), replayed as CUDA graphs."""
     import numpy as np
     from cuda_gaussian_splatting_b200 import _lib
     n, W, H = scene.n, scene.camera.width, scene.camera.height
-    V = args.views_per_gpu
+    V = len(cams)
     rng = np.random.default_rng(4321 + rank)
     targets = [torch.from_numpy(rng.uniform(size=(H, W, 3)).astype(np.float32)).to(dev) for _ in range(V)]
-    trainer = cugs.SyntheticTrainer(model, cams, targets, cugs.TrainConfig(), total_views_per_step=world * V)
+    trainer = cugs.NativeTrainer(model, cams, targets, cugs.TrainConfig(), total_views_per_step=world * V,
+                                 frames_in_flight=1 if args.no_overlap else 2, use_graph=not args.no_graph)
     lib, h = _lib.load_library(), _lib.handle(local)
     step_no = [3000]  # SH degree 3 active (lr_schedule.hpp:70-72)
+    exch_state = {}
 
     def step():
-        trainer.train_step(step_no[0])
+        if world == 1:
+            trainer.train_step(step_no[0])
+        else:
+            trainer.step_views(step_no[0])
+            cugs.sparse_allreduce_step(trainer.buffers, with_stats=True, state=exch_state)
+            b = trainer.buffers
+            cugs.fold_step_stats(b.step_grad_accum, b.step_grad_count, b.step_max_radii, trainer.stats.grad_accum,
+                                 trainer.stats.grad_count, trainer.stats.max_radii_2d)
+            trainer.step_update(step_no[0])
         step_no[0] += 1
 
     def barrier():
@@ -468,42 +606,56 @@ def run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = torch.tensor([calibrated_steps(args.steps, timed(5) / 5)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(k, op=dist.ReduceOp.MAX)
+    steps = int(k.item())
     l0 = int(lib.cugs_b200_launch_count(h))
-    barrier()
     sampler.mark_begin()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
+    total_ms = timed(steps)
     sampler.mark_end()
     launches = int(lib.cugs_b200_launch_count(h)) - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
     clocks = sampler.stop() if rank == 0 else {}
-    loss = float(trainer.last_scalars[0])
+    scalars, ok, pmax, _ = trainer.result()
+    assert ok, f"a frame overflowed the pair capacity ({pmax} > {trainer.pair_capacity})"
+    trainer.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return None
-    views = world * V * args.steps
+    views = world * V * steps
     return {"metric": "training views/s (render fwd+bwd + L1/SSIM loss + densification stats + fused Adam)",
-            "value": round(views / (total_ms * 1e-3), 3), "unit": "views/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 4),
-            "ms_per_view": round(total_ms / args.steps / V, 4), "higher_is_better": True, "scaling": "weak",
+            "value": round(views / (total_ms * 1e-3), 3), "unit": "views/s", "n_gpus": world, "steps": steps,
+            "steps_requested": args.steps, "warmup": warm, "ms_per_step": round(total_ms / steps, 4),
+            "ms_per_view": round(total_ms / steps / V, 4), "higher_is_better": True,
+            "scaling": "strong" if args.views_total > 0 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc.replace("fwd+bwd", "full training step"), "views_per_gpu_per_step": V,
-                       "adam_elements": 59 * n, "l2": "inputs exceed L2"},
-            "clocks": clocks, "gpu_launches": launches, "final_loss": loss}
+                       "views_per_step": world * V, "adam_elements": 59 * n, "l2": "inputs exceed L2",
+                       "driver": "cugs_b200_trainer_step: C++ step driver, no host synchronisation, "
+                                 + ("CUDA graph replay" if not args.no_graph else "eager launches"),
+                       "pair_capacity": trainer.pair_capacity, "largest_pair_count": pmax},
+            "clocks": clocks, "gpu_launches": launches, "final_loss": scalars[0]}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
@@ -634,6 +786,9 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--views-per-gpu", type=int, default=2,
                     help="views rendered fwd+bwd per GPU per step (2 = BASELINE config[3]: 16 views/step on 8 GPUs)")
+    ap.add_argument("--views-total", type=int, default=0,
+                    help="STRONG scaling: a fixed number of views per step split over the GPUs (16 = BASELINE config[3])")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense-allreduce", action="store_true",
                     help="N > 1: all-reduce the whole gradient arena instead of only the touched rows")

@@ -22,6 +22,7 @@ from .density import (  # noqa: F401
     DensificationConfig, DensificationController, DensificationResult, MCMCStats, mcmc_relocate,
     mcmc_should_relocate,
 )
+from .native_trainer import NativeTrainer  # noqa: F401
 from .parallel import (  # noqa: F401
     allreduce_step, arena_layout, fold_step_stats, grad_scale_for, shard_views, sparse_allreduce_step,
 )

@@ -43,6 +43,29 @@ class CugsDensifyConfig(C.Structure):  # cugs_densify_config_t
     ]
 
 
+class CugsTrainConfig(C.Structure):  # cugs_train_config_t
+    _fields_ = [
+        ("lambda_ssim", C.c_float), ("max_sh_degree", C.c_int32), ("background", C.c_float * 3),
+        ("lr_position_init", C.c_float), ("lr_position_final", C.c_float), ("lr_position_max_steps", C.c_int32),
+        ("lr_sh_coeffs", C.c_float), ("lr_opacities", C.c_float), ("lr_scales", C.c_float), ("lr_rotations", C.c_float),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("accumulate_stats", C.c_int32), ("mcmc", C.c_int32),
+        ("lambda_opacity", C.c_float), ("lambda_scale", C.c_float),
+        ("noise_lr_init", C.c_float), ("noise_lr_final", C.c_float), ("noise_lr_max_steps", C.c_int32),
+        ("noise_gate_k", C.c_float), ("noise_gate_t", C.c_float), ("noise_seed", C.c_uint64),
+        ("frames_in_flight", C.c_int32), ("use_graph", C.c_int32),
+    ]
+
+
+class CugsTrainTensors(C.Structure):  # cugs_train_tensors_t
+    _fields_ = [
+        ("params", C.c_void_p * 5), ("adam_m", C.c_void_p * 5), ("adam_v", C.c_void_p * 5), ("grads", C.c_void_p * 5),
+        ("dL_dmeans_2d", C.c_void_p), ("grad_accum", C.c_void_p), ("grad_count", C.c_void_p), ("max_radii", C.c_void_p),
+        ("touch_mask", C.c_void_p),
+    ]
+
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _SZ = C.c_size_t
@@ -58,6 +81,7 @@ SIGNATURES = {
     "cugs_b200_abi_version": (_INT, []),
     "cugs_b200_sm_count": (_INT, [_P]),
     "cugs_b200_launch_count": (C.c_uint64, [_P]),
+    "cugs_b200_device_info": (_INT, [_P, C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_INT)]),
     "cugs_b200_preprocess_fwd": (_INT, [_P, _P, _I64, _VP] + [_P] * 14),
     "cugs_b200_sh_forward": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P]),
     "cugs_b200_sh_backward": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P, _P]),
@@ -81,8 +105,8 @@ SIGNATURES = {
     "cugs_b200_render_finish": (_INT, [_P, _P, _I64, _I64, _VP] + [_P] * 11 + [_P, _SZ, _P, _SZ]),
     "cugs_b200_render_backward": (_INT, [_P, _P, _I64, _VP] + [_P] * 25 + [_INT, _P, _SZ]),
     "cugs_b200_compact_grad_floats": (_I64, [_I64, _INT]),
-    "cugs_b200_gather_grad_rows": (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, C.POINTER(_P), _P, _P]),
-    "cugs_b200_scatter_grad_rows": (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, _P, C.POINTER(_P), _P]),
+    "cugs_b200_gather_grad_rows": (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, C.POINTER(_P), _P, _P, _P, _P]),
+    "cugs_b200_scatter_grad_rows": (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, _P, C.POINTER(_P), _P, _P]),
     "cugs_b200_last_sort_plan": (_INT, [_P, C.POINTER(_INT), C.POINTER(_INT)]),
     "cugs_b200_set_stage_timing": (_INT, [_P, _INT]),
     "cugs_b200_get_stage_ms": (_INT, [_P, C.POINTER(_F)]),
@@ -93,6 +117,15 @@ SIGNATURES = {
     "cugs_b200_adam_step_mcmc": (_INT, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
                                          C.POINTER(_I64), C.POINTER(_F), _F, _F, _F, _F, _F, _F, _F, _F]),
     "cugs_b200_mcmc_inject_noise": (_INT, [_P, _P, _I64, _P, _P, _P, _F, _F, _F, C.c_uint64, C.c_uint32, _P]),
+    "cugs_b200_trainer_workspace_bytes": (_SZ, [_I64, _INT, _INT, _INT, _I64, _INT]),
+    "cugs_b200_trainer_create": (_INT, [_P, _I64, _INT, _INT, _INT, _I64, C.POINTER(CugsTrainConfig),
+                                         C.POINTER(CugsTrainTensors), _P, _SZ, C.POINTER(_P)]),
+    "cugs_b200_trainer_destroy": (None, [_P]),
+    "cugs_b200_trainer_set_views": (_INT, [_P, _INT, _VP, C.POINTER(_P), C.POINTER(_P), _INT]),
+    "cugs_b200_trainer_step": (_INT, [_P, _P, _INT, _INT]),
+    "cugs_b200_trainer_result": (_INT, [_P, _P, C.POINTER(_F), C.POINTER(_I64)]),
+    "cugs_b200_trainer_set_adam_steps": (_INT, [_P, _I64]),
+    "cugs_b200_trainer_adam_steps": (_I64, [_P]),
     "cugs_b200_accumulate_stats": (_INT, [_P, _P, _I64, _P, _P, _P, _P, _P]),
     "cugs_b200_densify_temp_bytes": (_SZ, [_I64]),
     "cugs_b200_densify_classify": (_INT, [_P, _P, _I64, _P, _P, _P, _P, _P, C.POINTER(CugsDensifyConfig), _P,

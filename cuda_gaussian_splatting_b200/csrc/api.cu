@@ -25,7 +25,12 @@ size_t cugs_packed_sort_temp_bytes(int64_t n, int passes, int num_tiles);
 int cugs_packed_passes(int key_bits);
 int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, uint64_t* a, uint64_t* b,
                      int* out32_last, int num_tiles, int* tile_ranges, void* temp, size_t temp_bytes,
-                     const int64_t* n_dev);
+                     const int64_t* n_dev, bool hist_done, const int* payload_src, int* payload_dst);
+int cugs_duplicate_sorted_hist(cugs_handle_t* h, cudaStream_t s, int64_t n, int width, int height,
+                               const uint64_t* sorted_elts, const float* means_2d, const int32_t* radii,
+                               const int32_t* tiles_touched, const int32_t* offsets_sorted, int64_t p, uint64_t* pairs,
+                               const int64_t* p_dev, int key_bits, int num_tiles, void* sort_temp,
+                               size_t sort_temp_bytes);
 int cugs_duplicate_sorted(cugs_handle_t* h, cudaStream_t s, int64_t n, int width, int height,
                           const uint64_t* sorted_elts, const float* means_2d, const int32_t* radii,
                           const int32_t* tiles_touched, const int32_t* offsets_sorted, int64_t p, uint64_t* pairs,
@@ -43,7 +48,8 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
                                float* dL_drotations, float* dL_dscales, float* dL_dopacities,
                                float* dL_dsh_coeffs, float* grad_accum, float* grad_count,
                                float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out,
-                               bool accumulate, int32_t* touch_mask, bool sparse_rows);
+                               bool accumulate, int32_t* touch_mask, bool sparse_rows, int32_t* list,
+                               int32_t* list_count);
 extern "C" int cugs_b200_sort_num_passes(int depth_bits, int tile_bits);
 extern "C" int cugs_b200_sort_pairs_pingpong(cugs_handle_t* h, void* stream, int64_t p, int depth_bits,
                                              int tile_bits, uint64_t* keys_a, int32_t* vals_a,
@@ -148,6 +154,23 @@ extern "C" const char* cugs_b200_last_error(const cugs_handle_t* h) { return h ?
 extern "C" int cugs_b200_sm_count(const cugs_handle_t* h) { return h ? h->sm_count : 0; }
 extern "C" uint64_t cugs_b200_launch_count(const cugs_handle_t* h) { return h ? h->launches : 0; }
 
+// what the FP32 / MUFU rooflines of the blend kernels are computed from ("read both from
+// cudaGetDeviceProperties, do not assume"): SM count, maximum SM clock in kHz, L2 size in bytes
+extern "C" int cugs_b200_device_info(const cugs_handle_t* h, int* sm_count, int* clock_khz, int* l2_bytes) {
+    if (!h) return CUGS_ERR_INVALID_ARG;
+    int v = 0;
+    if (sm_count) *sm_count = h->sm_count;
+    if (clock_khz) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, h->device) != cudaSuccess) return CUGS_ERR_INVALID_ARG;
+        *clock_khz = v;
+    }
+    if (l2_bytes) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, h->device) != cudaSuccess) return CUGS_ERR_INVALID_ARG;
+        *l2_bytes = v;
+    }
+    return CUGS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // workspace layout of one frame
 // ------------------------------------------------------------------------------------------------
@@ -156,6 +179,7 @@ namespace {
 struct FrameWorkspace {
     float* packed;          // [N,12]  blend records
     int32_t* tiles_touched; // [N]
+    int32_t* tiles_sorted;  // [N]     tiles_touched in depth order (written by the depth sort's last pass)
     int32_t* offsets;       // [N]     pair offsets in DEPTH order
     void* scan_temp;
     int64_t* total_dev;
@@ -164,6 +188,7 @@ struct FrameWorkspace {
     void* gsort_temp;
     size_t gsort_temp_bytes;
     float* grad_acc;        // [N,12]
+    int32_t* bwd_list;      // [N]     compact list of the Gaussians with a non-zero 2-D gradient (sparse backward)
     uint64_t* pairs_a;      // [Pcap]  tile << 32 | index
     uint64_t* pairs_b;      // [Pcap]
     void* psort_temp;
@@ -202,6 +227,7 @@ FrameWorkspace carve(void* base, int64_t n, int64_t pcap) {
     // and render_backward of one frame agree on them whatever P turns out to be.
     w.packed = static_cast<float*>(take(nn * 48));
     w.tiles_touched = static_cast<int32_t*>(take(nn * 4));
+    w.tiles_sorted = static_cast<int32_t*>(take(nn * 4));
     w.offsets = static_cast<int32_t*>(take(nn * 4));
     w.scan_temp = take(cugs_b200_scan_temp_bytes(n));
     w.total_dev = static_cast<int64_t*>(take(64));
@@ -210,6 +236,7 @@ FrameWorkspace carve(void* base, int64_t n, int64_t pcap) {
     w.gsort_temp_bytes = cugs_packed_sort_temp_bytes(n, 4, 0);
     w.gsort_temp = take(w.gsort_temp_bytes);
     w.grad_acc = static_cast<float*>(take(nn * 48));
+    w.bwd_list = static_cast<int32_t*>(take(nn * 4));
     w.head_bytes = off;
     // P-sized scratch, live only inside render_finish: the tail of the same block, or a separate one
     carve_pairs(w, base ? static_cast<char*>(base) + off : nullptr, pcap);
@@ -254,12 +281,13 @@ static int forward_front(cugs_handle_t* h, cudaStream_t s, int64_t n, const cugs
     mark(h, 1, s);
     // depth sort of the N Gaussians (the depth-bit passes of the reference's 64-bit sort, hoisted
     // in front of duplicateWithKeys), then the scan of tiles_touched in depth order
+    // (the last pass also delivers tiles_touched in depth order: the scan and duplicateWithKeys read it contiguously)
     if (int e = cugs_packed_sort(h, s, n, 32, w.gsort_a, w.gsort_b, nullptr, 0, nullptr, w.gsort_temp,
-                                 w.gsort_temp_bytes, nullptr))
+                                 w.gsort_temp_bytes, nullptr, false, w.tiles_touched, w.tiles_sorted))
         return e;
     mark(h, 11, s);
-    if (int e = cugs_scan_launch(h, s, n, w.tiles_touched, w.offsets, w.total_dev, total_pinned, w.scan_temp,
-                                 nullptr, w.gsort_a))
+    if (int e = cugs_scan_launch(h, s, n, w.tiles_sorted, w.offsets, w.total_dev, total_pinned, w.scan_temp,
+                                 nullptr, nullptr))
         return e;
     mark(h, 2, s);
     return CUGS_OK;
@@ -278,17 +306,28 @@ static int forward_back(cugs_handle_t* h, cudaStream_t s, int64_t n, int64_t p_c
         return set_error(h, CUGS_ERR_UNSUPPORTED, "%d tiles > %d is not supported by the fused path", num_tiles,
                          kMaxTilesForWorkspace);
     if (n > 0 && p_cap > 0) {
-        if (int e = cugs_duplicate_sorted(h, s, n, v->width, v->height, w.gsort_a, means_2d, radii, w.tiles_touched,
+        const int tile_bits = ceil_log2(num_tiles);
+#ifndef CUGS_NO_FUSED_PAIR_HIST
+        // duplicateWithKeys also takes the pair sort's histograms (no separate read of the P pairs)
+        if (int e = cugs_duplicate_sorted_hist(h, s, n, v->width, v->height, w.gsort_a, means_2d, radii,
+                                               w.tiles_sorted, w.offsets, p_cap, w.pairs_a, w.total_dev, tile_bits,
+                                               num_tiles, w.psort_temp, w.psort_temp_bytes))
+            return e;
+        const bool hist_done = true;
+#else
+        if (int e = cugs_duplicate_sorted(h, s, n, v->width, v->height, w.gsort_a, means_2d, radii, w.tiles_sorted,
                                           w.offsets, p_cap, w.pairs_a, w.total_dev))
             return e;
+        const bool hist_done = false;
+#endif
         mark(h, 4, s);
-        const int tile_bits = ceil_log2(num_tiles);
         h->last_sort_passes = 4 + cugs_packed_passes(tile_bits);
         h->last_sort_key_bits = 32 + tile_bits;
         // tile histogram -> tile ranges, and the stable sort of the pairs by tile id; the last pass
         // writes the Gaussian indices straight into the caller's buffer
         if (int e = cugs_packed_sort(h, s, p_cap, tile_bits, w.pairs_a, w.pairs_b, gaussian_idx, num_tiles,
-                                     tile_ranges, w.psort_temp, w.psort_temp_bytes, w.total_dev))
+                                     tile_ranges, w.psort_temp, w.psort_temp_bytes, w.total_dev, hist_done, nullptr,
+                                     nullptr))
             return e;
         mark(h, 5, s);
     } else {
@@ -455,12 +494,14 @@ extern "C" int cugs_b200_render_backward(
         return e;
     mark(h, 9, s);
     // stage 2 (rasterizer.cpp:163-176): 2-D gradients -> parameter gradients (+ SH backward, + stats)
+    const bool sparse = (flags & CUGS_BWD_SPARSE_ROWS) != 0 && touch_mask != nullptr;
     if (int e = cugs_preprocess_bwd_launch(h, s, n, v, positions, rotations, scales, opacities, sh_coeffs,
                                            radii, rgb, nullptr, nullptr, nullptr, nullptr, dL_dpositions,
                                            dL_drotations, dL_dscales, dL_dopacities, dL_dsh_coeffs, grad_accum,
                                            grad_count, max_radii, w.grad_acc, dL_dmeans_2d,
-                                           (flags & CUGS_BWD_ACCUMULATE) != 0, touch_mask,
-                                           (flags & CUGS_BWD_SPARSE_ROWS) != 0))
+                                           (flags & CUGS_BWD_ACCUMULATE) != 0, touch_mask, sparse,
+                                           sparse ? w.bwd_list : nullptr,
+                                           sparse ? reinterpret_cast<int32_t*>(w.total_dev + 1) : nullptr))
         return e;
     mark(h, 10, s);
     return CUGS_OK;

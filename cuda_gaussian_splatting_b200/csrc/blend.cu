@@ -72,6 +72,36 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// ---- experiment (-DCUGS_BLEND_TMA): stage each 48-byte record with ONE 1-D TMA bulk copy
+// (cp.async.bulk.shared::cluster.global, completion counted in bytes on an mbarrier) instead of three 16-byte
+// LDGSTS. Measured on B200 (profiles/r02/NOTES.md): no gain -- the staging is one batch ahead of its use and
+// costs ~1 % of the kernels' instructions either way -- so the default build keeps LDGSTS.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t"
+        "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy48(void* smem, const void* gmem, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 48, [%2];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
 // Stage one Gaussian of the batch into shared memory.
 template <bool kPacked>
 __device__ __forceinline__ void stage_gaussian(StagedGaussian* dst, int g, const float4* __restrict__ packed,
@@ -195,6 +225,37 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             float* __restrict__ out_T, int* __restrict__ out_n) {
     __shared__ StagedGaussian s_g[2][kBatch];
     __shared__ unsigned char s_list[2][kBatch];
+#ifdef CUGS_BLEND_TMA
+    __shared__ __align__(8) uint64_t s_bar[2];
+    if (kPacked) {
+        if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
+#define CUGS_STAGE(dstp, gi, slot)                                                              \
+    do {                                                                                        \
+        if (kPacked) bulk_copy48((dstp), packed + (int64_t)(gi) * 3, &s_bar[(slot)]);           \
+        else stage_gaussian<kPacked>((dstp), (gi), packed, means_2d, conic, rgb, opa);          \
+    } while (0)
+#define CUGS_EXPECT(slot, cnt)                                                                  \
+    do {                                                                                        \
+        if (kPacked && threadIdx.x == 0) mbar_expect_tx(&s_bar[(slot)], (unsigned)(cnt) * 48u); \
+    } while (0)
+#define CUGS_WAIT_BATCH(slot, parity, pending)                                                  \
+    do {                                                                                        \
+        if (kPacked) mbar_wait(&s_bar[(slot)], (parity));                                       \
+        else if (pending) cp_async_wait<1>();                                                   \
+        else cp_async_wait<0>();                                                                \
+    } while (0)
+#else
+#define CUGS_STAGE(dstp, gi, slot) stage_gaussian<kPacked>((dstp), (gi), packed, means_2d, conic, rgb, opa)
+#define CUGS_EXPECT(slot, cnt) do {} while (0)
+#define CUGS_WAIT_BATCH(slot, parity, pending)                                                  \
+    do {                                                                                        \
+        if (pending) cp_async_wait<1>();                                                        \
+        else cp_async_wait<0>();                                                                \
+    } while (0)
+#endif
 
     const int tile = blockIdx.x;
     const int tile_x = tile % ntx, tile_y = tile / ntx;
@@ -227,12 +288,11 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
     // prologue: gather batch 0, prefetch the indices of batch 1
     int next_idx[2] = {-1, -1};
     if (nb > 0) {
+        CUGS_EXPECT(0, min(kBatch, count));
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int li = range.x + threadIdx.x + u * kBlendThreads;
-            if (li < range.y)
-                stage_gaussian<kPacked>(&s_g[0][threadIdx.x + u * kBlendThreads], gaussian_idx[li], packed,
-                                        means_2d, conic, rgb, opa);
+            if (li < range.y) CUGS_STAGE(&s_g[0][threadIdx.x + u * kBlendThreads], gaussian_idx[li], 0);
             const int li1 = li + kBatch;
             if (li1 < range.y) next_idx[u] = gaussian_idx[li1];
         }
@@ -243,19 +303,16 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
         // issue the gather of batch b+1 into the other buffer (its previous reader, batch b-1,
         // finished before the __syncthreads_and at the end of the previous iteration)
         if (b + 1 < nb) {
+            CUGS_EXPECT((b + 1) & 1, min(kBatch, count - (b + 1) * kBatch));
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                if (next_idx[u] >= 0)
-                    stage_gaussian<kPacked>(&s_g[(b + 1) & 1][threadIdx.x + u * kBlendThreads], next_idx[u],
-                                            packed, means_2d, conic, rgb, opa);
+                if (next_idx[u] >= 0) CUGS_STAGE(&s_g[(b + 1) & 1][threadIdx.x + u * kBlendThreads], next_idx[u], (b + 1) & 1);
                 const int li2 = range.x + (b + 2) * kBatch + threadIdx.x + u * kBlendThreads;
                 next_idx[u] = (li2 < range.y) ? gaussian_idx[li2] : -1;
             }
             cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
         }
+        CUGS_WAIT_BATCH(b & 1, (b >> 1) & 1, b + 1 < nb);
         __syncthreads();
 
         const StagedGaussian* sg = s_g[b & 1];
@@ -374,6 +431,14 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
     __shared__ StagedGaussian s_g[2][kBatch];
     __shared__ int s_idx[2][kBatch];
     __shared__ unsigned char s_list[2][kBatch];
+#ifdef CUGS_BLEND_TMA
+    __shared__ __align__(8) uint64_t s_bar[2];
+    if (kPacked) {
+        if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
+#endif
 
     const int tile = blockIdx.x;
     const int tile_x = tile % ntx, tile_y = tile / ntx;
@@ -415,6 +480,7 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
     // batches are visited last to first; batch b covers [range.x + b*kBatch, ...)
     int next_idx[2] = {-1, -1};
     if (nb > 0) {
+        CUGS_EXPECT((nb - 1) & 1, count - (nb - 1) * kBatch);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int t = threadIdx.x + u * kBlendThreads;
@@ -422,7 +488,7 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             if (li < range.y) {
                 const int g = gaussian_idx[li];
                 s_idx[(nb - 1) & 1][t] = g;
-                stage_gaussian<kPacked>(&s_g[(nb - 1) & 1][t], g, packed, means_2d, conic, rgb, opa);
+                CUGS_STAGE(&s_g[(nb - 1) & 1][t], g, (nb - 1) & 1);
             }
             if (nb > 1) next_idx[u] = gaussian_idx[li - kBatch];  // batch nb-2 is always full
         }
@@ -431,18 +497,17 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
 
     for (int b = nb - 1; b >= 0; --b) {
         if (b > 0) {
+            CUGS_EXPECT((b - 1) & 1, kBatch);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int t = threadIdx.x + u * kBlendThreads;
                 s_idx[(b - 1) & 1][t] = next_idx[u];
-                stage_gaussian<kPacked>(&s_g[(b - 1) & 1][t], next_idx[u], packed, means_2d, conic, rgb, opa);
+                CUGS_STAGE(&s_g[(b - 1) & 1][t], next_idx[u], (b - 1) & 1);
                 if (b > 1) next_idx[u] = gaussian_idx[range.x + (b - 2) * kBatch + t];
             }
             cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
         }
+        CUGS_WAIT_BATCH(b & 1, ((nb - 1 - b) >> 1) & 1, b > 0);
         __syncthreads();
 
         const StagedGaussian* sg = s_g[b & 1];
@@ -628,6 +693,10 @@ k_count_evaluations(int ntx, int width, int height, const int* __restrict__ tile
     __syncthreads();
     if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
 }
+
+#undef CUGS_STAGE
+#undef CUGS_EXPECT
+#undef CUGS_WAIT_BATCH
 
 // grad_acc [N,12] -> the four public arrays of RasterizeBackwardOutput (backward.hpp:13-18)
 __global__ void __launch_bounds__(256)

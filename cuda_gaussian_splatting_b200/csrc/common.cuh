@@ -240,6 +240,20 @@ inline ViewParams make_view_params(const cugs_view_t* v) {
     return p;
 }
 
+// Per-step scalars of the training step that change every iteration (learning rates, Adam bias
+// corrections, noise scale, step number), kept in DEVICE memory so that a captured CUDA graph of the
+// step can be replayed unchanged: the host refreshes this struct with one small H2D copy before each
+// launch. ok = 0 (a frame of the step overflowed its pair capacity) turns the update kernels into no-ops:
+// the step is transactional, the host re-runs it with larger buffers.
+struct StepDyn {
+    float lr[5];
+    float bc1, bc2;
+    float noise_lr;
+    unsigned step;
+    int ok;
+    int pad[2];
+};
+
 // ---- counter-based random numbers (MCMC noise, split / relocation jitter) ----------------------
 // Philox-4x32-10; the caller chooses key = seed and a counter that names the draw (Gaussian index,
 // step, purpose), so results do not depend on the launch shape and every rank of a view-parallel

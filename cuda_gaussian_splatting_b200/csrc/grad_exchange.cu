@@ -32,11 +32,16 @@ k_build_touch_index(int64_t n, const int* __restrict__ touch, const int* __restr
 // blockIdx.y = parameter group.
 __host__ __device__ __forceinline__ int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
 
+// m_dev != NULL: `m` is the row CAPACITY the compact layout was sized for (known to the host from an earlier
+// step) and the real row count is read on the device; a gather zero-fills the rows between the two so that
+// the all-reduce sums defined values, and rows beyond the capacity are dropped (status[1] flags it).
 template <bool kGather>
 __global__ void __launch_bounds__(256)
-k_move_grad_rows(int C, const int* __restrict__ idx, int64_t m, GradGroups dense, float* __restrict__ compact) {
+k_move_grad_rows(int C, const int* __restrict__ idx, int64_t m, const int64_t* __restrict__ m_dev, GradGroups dense,
+                 float* __restrict__ compact) {
     const int grp = blockIdx.y;
     const int shw = 3 * C;
+    const int64_t m_real = m_dev ? min(*m_dev, m) : m;
     // group bases, each rounded up to 4 floats so that the SH block can be moved as float4
     const int64_t b_sh = align4(3 * m), b_op = b_sh + align4((int64_t)shw * m), b_sc = b_op + align4(m),
                   b_ro = b_sc + align4(3 * m);
@@ -48,6 +53,10 @@ k_move_grad_rows(int C, const int* __restrict__ idx, int64_t m, GradGroups dense
         float4* __restrict__ c4 = reinterpret_cast<float4*>(compact + b_sh);
         for (int64_t e = t0; e < m * w4; e += stride) {
             const int64_t j = e / w4;
+            if (j >= m_real) {
+                if (kGather) c4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
             const int64_t src = (int64_t)idx[j] * w4 + (e - j * w4);
             if (kGather) c4[e] = d4[src];
             else d4w[src] = c4[e];
@@ -59,10 +68,26 @@ k_move_grad_rows(int C, const int* __restrict__ idx, int64_t m, GradGroups dense
     float* __restrict__ d = dense.g[grp];
     for (int64_t e = t0; e < m * w; e += stride) {
         const int64_t j = e / w;
+        if (j >= m_real) {
+            if (kGather) compact[base + e] = 0.f;
+            continue;
+        }
         const int64_t src = (int64_t)idx[j] * w + (e - j * w);
         if (kGather) compact[base + e] = d[src];
         else d[src] = compact[base + e];
     }
+}
+
+// idx[offsets[i]] = i for touched rows below the capacity; status = {M, M > capacity}
+__global__ void __launch_bounds__(256)
+k_build_touch_index_cap(int64_t n, const int* __restrict__ touch, const int* __restrict__ offsets, int64_t cap,
+                        const int64_t* __restrict__ m_dev, int* __restrict__ idx, int64_t* __restrict__ status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && status != nullptr) {
+        status[0] = *m_dev;
+        status[1] = *m_dev > cap ? 1 : 0;
+    }
+    if (i < n && touch[i] != 0 && offsets[i] < cap) idx[offsets[i]] = (int)i;
 }
 
 }  // namespace cugs
@@ -73,7 +98,7 @@ using namespace cugs;
 // index list is rebuilt on every call into `idx`.
 static int move_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs, const int32_t* touch,
                      const int32_t* offsets, int64_t m, float* const grads[5], float* compact, int32_t* idx,
-                     bool gather) {
+                     bool gather, const int64_t* m_dev, int64_t* status_dev) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, n >= 0 && m >= 0 && m <= n, "bad n / m");
     CUGS_REQUIRE(h, num_coeffs >= 1 && num_coeffs <= 64, "bad num_coeffs");
@@ -85,14 +110,17 @@ static int move_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs, 
         G.g[k] = grads[k];
     }
     cudaStream_t s = (cudaStream_t)stream;
-    k_build_touch_index<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, touch, offsets, idx);
+    if (m_dev)
+        k_build_touch_index_cap<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, touch, offsets, m, m_dev, idx, status_dev);
+    else
+        k_build_touch_index<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, touch, offsets, idx);
     CUGS_LAUNCH_CHECK(h, "k_build_touch_index");
     int64_t bx = (m * 3 * num_coeffs + 255) / 256;
     const int64_t cap = (int64_t)h->sm_count * 16;
     if (bx > cap) bx = cap;
     const dim3 grid((unsigned)bx, 5);
-    if (gather) k_move_grad_rows<true><<<grid, 256, 0, s>>>(num_coeffs, idx, m, G, compact);
-    else k_move_grad_rows<false><<<grid, 256, 0, s>>>(num_coeffs, idx, m, G, compact);
+    if (gather) k_move_grad_rows<true><<<grid, 256, 0, s>>>(num_coeffs, idx, m, m_dev, G, compact);
+    else k_move_grad_rows<false><<<grid, 256, 0, s>>>(num_coeffs, idx, m, m_dev, G, compact);
     CUGS_LAUNCH_CHECK(h, "k_move_grad_rows");
     return CUGS_OK;
 }
@@ -103,14 +131,16 @@ extern "C" int64_t cugs_b200_compact_grad_floats(int64_t m, int num_coeffs) {
 
 extern "C" int cugs_b200_gather_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs,
                                           const int32_t* touch, const int32_t* offsets, int64_t m,
-                                          const float* const grads[5], float* compact, int32_t* idx_scratch) {
+                                          const float* const grads[5], float* compact, int32_t* idx_scratch,
+                                          const int64_t* m_dev, int64_t* status_dev) {
     return move_rows(h, stream, n, num_coeffs, touch, offsets, m, const_cast<float* const*>(grads), compact,
-                     idx_scratch, true);
+                     idx_scratch, true, m_dev, status_dev);
 }
 
 extern "C" int cugs_b200_scatter_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs,
                                            const int32_t* touch, const int32_t* offsets, int64_t m,
-                                           const float* compact, float* const grads[5], int32_t* idx_scratch) {
+                                           const float* compact, float* const grads[5], int32_t* idx_scratch,
+                                           const int64_t* m_dev) {
     return move_rows(h, stream, n, num_coeffs, touch, offsets, m, grads, const_cast<float*>(compact), idx_scratch,
-                     false);
+                     false, m_dev, nullptr);
 }

@@ -329,15 +329,20 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                  float* __restrict__ dL_dmeans_2d_out /* written when gacc != null */,
                  bool accumulate /* add to the five parameter-gradient outputs instead of overwriting */,
                  int* __restrict__ touch_mask /* optional: 1 where the incoming 2-D gradient is non-zero */,
-                 bool sparse_rows /* with touch_mask: only move gradient rows that can be non-zero */) {
+                 bool sparse_rows /* with touch_mask: only move gradient rows that can be non-zero */,
+                 const int* __restrict__ list /* optional: compacted indices of the Gaussians to process */,
+                 const int* __restrict__ list_count /* device count of `list` */) {
     __shared__ __align__(16) float sY[kPreWarps][32 * kYStride];
     __shared__ float sG[kPreWarps][96];  // gated dL/drgb per (Gaussian, channel)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t g0 = ((int64_t)blockIdx.x * kPreWarps + warp) * 32;
-    if (g0 >= n) return;
-    const int64_t i = g0 + lane;
-    const bool valid = i < n;
+    // list mode (second phase of the sparse backward, see k_bwd_classify): the warp owns 32 consecutive
+    // entries of the list of touched Gaussians instead of 32 consecutive Gaussians
+    const int64_t limit = list ? (int64_t)*list_count : n;
+    if (g0 >= limit) return;
+    const bool valid = g0 + lane < limit;
+    const int64_t i = list ? (valid ? (int64_t)list[g0 + lane] : 0) : g0 + lane;
 
     float px = 0.f, py = 0.f, pz = 0.f;
     int radius = 0;
@@ -349,6 +354,9 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
     // read-modified-written only if it is touched now (accumulate mode): ~80 % of the rows of a
     // view are skipped entirely.
     bool write_row = valid;
+    // sparse_rows: a Gaussian whose nine incoming 2-D gradients are all exactly zero has all-zero parameter
+    // gradients; the whole chain rule (a full re-projection) is skipped for it (~80 % of a view's Gaussians)
+    bool skip_chain = false;
     if (valid) {
         px = positions[i * 3 + 0]; py = positions[i * 3 + 1]; pz = positions[i * 3 + 2];
         radius = radii[i];
@@ -357,13 +365,16 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
             const float4 a = gacc[i * 3], b = gacc[i * 3 + 1], c = gacc[i * 3 + 2];
             dr[0] = a.x; dr[1] = a.y; dr[2] = a.z; in_dop = a.w;
             in_m0 = b.x; in_m1 = b.y; in_da = b.z; in_db = b.w; in_dc = c.x;
-            reinterpret_cast<float2*>(dL_dmeans_2d_out)[i] = make_float2(in_m0, in_m1);
+            if (dL_dmeans_2d_out != nullptr) reinterpret_cast<float2*>(dL_dmeans_2d_out)[i] = make_float2(in_m0, in_m1);
             if (touch_mask != nullptr) {
                 const bool t = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) |
                                (b.z != 0.f) | (b.w != 0.f) | (c.x != 0.f);
                 const int old = (accumulate || sparse_rows) ? touch_mask[i] : 0;
                 touch_mask[i] = accumulate ? (old | (int)t) : (int)t;
-                if (sparse_rows) write_row = accumulate ? t : (t || old != 0);
+                if (sparse_rows) {
+                    write_row = accumulate ? t : (t || old != 0);
+                    skip_chain = !t;
+                }
             }
         } else {
             dr[0] = dL_drgb[i * 3]; dr[1] = dL_drgb[i * 3 + 1]; dr[2] = dL_drgb[i * 3 + 2];
@@ -398,7 +409,7 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
     float g_pos[3] = {0.f, 0.f, 0.f}, g_rot[4] = {0.f, 0.f, 0.f, 0.f}, g_scl[3] = {0.f, 0.f, 0.f};
     float g_opa = 0.f;
     const float m0 = in_m0, m1 = in_m1;
-    if (valid && radius > 0) {  // projection_backward.cu:48
+    if (valid && radius > 0 && !skip_chain) {  // projection_backward.cu:48
         ProjFwd f;
         cam_transform(vp, px, py, pz, f.t);
         const float lsm = logf(add_rn(vp.scale_mod, 1e-8f));
@@ -531,17 +542,19 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
     }
 
     // ---- phase B: dL/dSH = gate * dL/drgb * Y_k, explicit zeros for inactive coefficients ----
-    const unsigned row_mask = __ballot_sync(kFull, write_row);  // bit g: Gaussian g0 + g moves its rows
+    const unsigned row_mask = __ballot_sync(kFull, write_row);  // bit g: the warp's Gaussian g moves its rows
     if (kVecSH) {
         __syncwarp();
-        float4* out4 = reinterpret_cast<float4*>(dL_dsh) + g0 * 12;
-        const int64_t lim = (n - g0) * 12;
+        float4* const sh_out4 = reinterpret_cast<float4*>(dL_dsh);
 #pragma unroll
         for (int it = 0; it < 12; ++it) {
             const int q = lane + 32 * it;
-            if (q >= lim) break;
             const int g = q / 12;
-            if (!((row_mask >> g) & 1u)) continue;
+            // row of Gaussian i_g = 12 float4; q - 12 g = float4 inside the row (contiguous mode: i_g = g0 + g,
+            // so the warp still writes its 6 KB block as 12 fully coalesced 512-byte rows)
+            const int64_t ig = __shfl_sync(kFull, i, g);
+            if (!((row_mask >> g) & 1u)) continue;  // also drops rows beyond the end (write_row = false there)
+            float4* out4 = sh_out4 + ig * 12 - (int64_t)g * 12;
             const int k0 = (q & 3) * 4;
             const float gd = sG[warp][q >> 2];
             const float4 y4 = *reinterpret_cast<const float4*>(&sY[warp][g * kYStride + k0]);
@@ -567,6 +580,59 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                 for (int k = na; k < vp.C; ++k) o[k] = 0.0f;
             }
         }
+    }
+}
+
+// ================================================================================================
+// Sparse backward, phase 1 (cugs_b200_render_backward with CUGS_BWD_SPARSE_ROWS): one pass over the N
+// packed 2-D gradient records that does everything that is per-Gaussian bookkeeping -- the touch mask,
+// dL/dmeans_2d, the fused densification statistics (optimizer/densification.cpp:59-88), zeroing of rows
+// that held a value from an earlier step but are not touched now -- and appends the touched Gaussians
+// (some gradient non-zero: ~20 % of a view) to a compact list. Phase 2 is k_preprocess_bwd in list mode:
+// the chain rule (a full re-projection, projection_backward.cu:26-247) and the 236-byte gradient row only
+// for the listed Gaussians, with full warps, instead of 32-lane warps in which ~6 lanes have work.
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+k_bwd_classify(int64_t n, int num_coeffs, const float4* __restrict__ gacc, const int* __restrict__ radii,
+               int* __restrict__ touch_mask, bool accumulate, float* __restrict__ dL_dmeans_2d_out,
+               float* __restrict__ grad_accum, float* __restrict__ grad_count, float* __restrict__ max_radii,
+               float* __restrict__ dL_dpos, float* __restrict__ dL_drot, float* __restrict__ dL_dscl,
+               float* __restrict__ dL_dopa, float* __restrict__ dL_dsh, int* __restrict__ list,
+               int* __restrict__ list_count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool t = false;
+    if (i < n) {
+        const float4 a = gacc[i * 3], b = gacc[i * 3 + 1], c = gacc[i * 3 + 2];
+        t = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) | (b.z != 0.f) |
+            (b.w != 0.f) | (c.x != 0.f);
+        reinterpret_cast<float2*>(dL_dmeans_2d_out)[i] = make_float2(b.x, b.y);
+        const int old = touch_mask[i];
+        touch_mask[i] = accumulate ? (old | (int)t) : (int)t;
+        if (grad_accum != nullptr) {
+            const int radius = radii[i];
+            if (radius > 0) {
+                grad_accum[i] += sqrtf(b.x * b.x + b.y * b.y);
+                grad_count[i] += 1.0f;
+            }
+            max_radii[i] = fmaxf(max_radii[i], (float)radius);
+        }
+        if (!accumulate && !t && old != 0) {  // stale row of an earlier step: back to zero
+            dL_dpos[i * 3 + 0] = 0.f; dL_dpos[i * 3 + 1] = 0.f; dL_dpos[i * 3 + 2] = 0.f;
+            reinterpret_cast<float4*>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dL_dscl[i * 3 + 0] = 0.f; dL_dscl[i * 3 + 1] = 0.f; dL_dscl[i * 3 + 2] = 0.f;
+            dL_dopa[i] = 0.f;
+            float* o = dL_dsh + i * 3 * num_coeffs;
+            for (int k = 0; k < 3 * num_coeffs; ++k) o[k] = 0.f;
+        }
+    }
+    // warp-aggregated append (order inside the list is irrelevant: every Gaussian is independent)
+    const unsigned m = __ballot_sync(kFull, t);
+    if (m != 0u) {
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(list_count, __popc(m));
+        base = __shfl_sync(kFull, base, __ffs(m) - 1);
+        if (t) list[base + __popc(m & ((1u << lane) - 1))] = (int)i;
     }
 }
 
@@ -689,30 +755,43 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
                                float* dL_drotations, float* dL_dscales, float* dL_dopacities,
                                float* dL_dsh_coeffs, float* grad_accum, float* grad_count,
                                float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out,
-                               bool accumulate, int32_t* touch_mask, bool sparse_rows) {
+                               bool accumulate, int32_t* touch_mask, bool sparse_rows, int32_t* list,
+                               int32_t* list_count) {
     const ViewParams vp = make_view_params(v);
     const unsigned grid = (unsigned)((n + kPreBlock - 1) / kPreBlock);
+    if (list != nullptr) {
+        // two-phase sparse backward: classify all N, then the chain rule on the compact list only (the second
+        // launch is sized for N; its warps beyond the device-side count leave at once)
+        CUGS_CUDA_TRY(h, cudaMemsetAsync(list_count, 0, sizeof(int32_t), s));
+        k_bwd_classify<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+            n, v->num_coeffs, reinterpret_cast<const float4*>(grad_acc), radii, touch_mask, accumulate,
+            dL_dmeans_2d_out, grad_accum, grad_count, max_radii, dL_dpositions, dL_drotations, dL_dscales,
+            dL_dopacities, dL_dsh_coeffs, list, list_count);
+        CUGS_LAUNCH_CHECK(h, "k_bwd_classify");
+        touch_mask = nullptr; grad_accum = grad_count = max_radii = nullptr; dL_dmeans_2d_out = nullptr;
+        sparse_rows = false;
+    }
     if (v->num_coeffs == 16 && v->active_sh_degree == 3)
         k_preprocess_bwd<true, true><<<grid, kPreBlock, 0, s>>>(
             n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
             dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
             dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
             reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate, touch_mask,
-            sparse_rows && touch_mask != nullptr);
+            sparse_rows && touch_mask != nullptr, list, list_count);
     else if (v->num_coeffs == 16)
         k_preprocess_bwd<true, false><<<grid, kPreBlock, 0, s>>>(
             n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
             dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
             dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
             reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate, touch_mask,
-            sparse_rows && touch_mask != nullptr);
+            sparse_rows && touch_mask != nullptr, list, list_count);
     else
         k_preprocess_bwd<false, false><<<grid, kPreBlock, 0, s>>>(
             n, vp, positions, rotations, scales, opacities, sh_coeffs, radii, rgb, dL_dmeans_2d,
             dL_dcov_2d_inv, dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
             dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
             reinterpret_cast<const float4*>(grad_acc), dL_dmeans_2d_out, accumulate, touch_mask,
-            sparse_rows && touch_mask != nullptr);
+            sparse_rows && touch_mask != nullptr, list, list_count);
     CUGS_LAUNCH_CHECK(h, "k_preprocess_bwd");
     return CUGS_OK;
 }
@@ -744,7 +823,7 @@ extern "C" int cugs_b200_preprocess_bwd(cugs_handle_t* h, void* stream, int64_t 
                                       opacities, sh_coeffs, radii, rgb, dL_dmeans_2d, dL_dcov_2d_inv,
                                       dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
                                       dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
-                                      nullptr, nullptr, false, nullptr, false);
+                                      nullptr, nullptr, false, nullptr, false, nullptr, nullptr);
 }
 
 extern "C" int cugs_b200_sh_forward(cugs_handle_t* h, void* stream, int64_t n, int degree,

@@ -28,7 +28,15 @@ constexpr int kPkRadixBits = 8;
 constexpr int kPkRadix = 256;
 constexpr int kPkThreads = 512;
 constexpr int kPkItems = 8;
-constexpr int kPkTile = kPkThreads * kPkItems;  // 4096 elements per block
+// (kPkThreads * kPkItems = 4096 elements per block)
+// Short inputs (the depth sort of the N Gaussians: 3 M elements = 733 tiles of 4096 on 444 block slots) are
+// latency bound by the length of a block's load -> rank -> look-back -> scatter chain, not by bandwidth: they
+// run with 4 items per thread (2048-element tiles, twice as many, shorter blocks).
+constexpr int kPkItemsSmall = 4;
+#ifndef CUGS_PK_SMALL_LIMIT
+#define CUGS_PK_SMALL_LIMIT (8ll << 20)  // elements; 0 disables the small-tile variant
+#endif
+inline int pk_items_for(int64_t n) { return (n > 0 && n <= (int64_t)CUGS_PK_SMALL_LIMIT) ? kPkItemsSmall : kPkItems; }
 constexpr int kPkWarps = kPkThreads / 32;
 constexpr int kPkMaxPasses = 4;
 
@@ -179,25 +187,29 @@ k_tile_hist_to_ranges(int num_tiles, const unsigned* __restrict__ tile_hist, int
 // one onesweep pass over packed 64-bit elements (digit taken from the high word). kLast: write
 // only the low word (the Gaussian index) of each element to out32.
 // ------------------------------------------------------------------------------------------------
-constexpr size_t kPkSmemBytes = (size_t)kPkTile * 8 + (size_t)kPkRadix * 8 + (size_t)kPkWarps * kPkRadix * 4 +
-                                (size_t)kPkRadix * 4 + 64;
+constexpr size_t pk_smem_bytes(int items) {
+    return (size_t)kPkThreads * items * 8 + (size_t)kPkRadix * 8 + (size_t)kPkWarps * kPkRadix * 4 +
+           (size_t)kPkRadix * 4 + 64;
+}
 
 #ifndef CUGS_OS_MINBLOCKS
 #define CUGS_OS_MINBLOCKS 3  // 40 registers (12 B of spills): 3 x 512 threads per SM, sort stage 0.531 -> 0.510 ms (4 blocks: 0.544)
 #endif
-// kBits = digit width of the pass (6, 7, 8), 0 = run-time width
-template <bool kLast, int kBits>
+// kBits = digit width of the pass (6, 7, 8), 0 = run-time width; kItems = elements per thread (8 or 4)
+template <bool kLast, int kBits, int kItems>
 __global__ void __launch_bounds__(kPkThreads, CUGS_OS_MINBLOCKS)
 k_onesweep_packed(int64_t n_cap, const int64_t* __restrict__ n_dev, const uint64_t* __restrict__ in,
                   uint64_t* __restrict__ out, int* __restrict__ out32, const unsigned* __restrict__ bin_base,
-                  volatile unsigned* __restrict__ lookback, unsigned* __restrict__ ticket, int shift, int bits) {
-    // capacity-sized launch: exactly ceil(n / kPkTile) blocks pass this test and take tickets
+                  volatile unsigned* __restrict__ lookback, unsigned* __restrict__ ticket, int shift, int bits,
+                  const int* __restrict__ payload_src, int* __restrict__ payload_dst) {
+    // capacity-sized launch: exactly ceil(n / kTileElts) blocks pass this test and take tickets
     // 0 .. tiles-1, so the look-back chain is the same as with a grid sized on the host
+    constexpr int kTileElts = kPkThreads * kItems;
     const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
-    if ((int64_t)blockIdx.x * kPkTile >= n) return;
+    if ((int64_t)blockIdx.x * kTileElts >= n) return;
     extern __shared__ __align__(16) unsigned char s_raw[];
-    uint64_t* s_elts = reinterpret_cast<uint64_t*>(s_raw);                   // [kPkTile]
-    int64_t* s_bin_global = reinterpret_cast<int64_t*>(s_elts + kPkTile);     // global index = [d] + slot
+    uint64_t* s_elts = reinterpret_cast<uint64_t*>(s_raw);                   // [kTileElts]
+    int64_t* s_bin_global = reinterpret_cast<int64_t*>(s_elts + kTileElts);     // global index = [d] + slot
     unsigned(*s_warp_hist)[kPkRadix] = reinterpret_cast<unsigned(*)[kPkRadix]>(s_bin_global + kPkRadix);
     unsigned* s_bin_start = &s_warp_hist[kPkWarps][0];
     unsigned* s_scan = s_bin_start + kPkRadix;
@@ -208,19 +220,19 @@ k_onesweep_packed(int64_t n_cap, const int64_t* __restrict__ n_dev, const uint64
     for (int b = lane; b < kPkRadix; b += 32) s_warp_hist[warp][b] = 0;
     __syncthreads();
     const unsigned tile = s_tile;
-    const int64_t tile_base = (int64_t)tile * kPkTile;
-    const int valid = (int)min((int64_t)kPkTile, n - tile_base);
-    const int64_t seg = tile_base + (int64_t)warp * (32 * kPkItems);
+    const int64_t tile_base = (int64_t)tile * kTileElts;
+    const int valid = (int)min((int64_t)kTileElts, n - tile_base);
+    const int64_t seg = tile_base + (int64_t)warp * (32 * kItems);
     const unsigned mask = (1u << bits) - 1;
     const unsigned lt_mask = (1u << lane) - 1;
 
-    uint64_t e[kPkItems];
-    if (tile_base + kPkTile <= n) {  // full tile: no bounds checks
+    uint64_t e[kItems];
+    if (tile_base + kTileElts <= n) {  // full tile: no bounds checks
 #pragma unroll
-        for (int i = 0; i < kPkItems; ++i) e[i] = __ldcs(in + seg + i * 32 + lane);
+        for (int i = 0; i < kItems; ++i) e[i] = __ldcs(in + seg + i * 32 + lane);
     } else {
 #pragma unroll
-        for (int i = 0; i < kPkItems; ++i) {
+        for (int i = 0; i < kItems; ++i) {
             const int64_t idx = seg + i * 32 + lane;
             e[i] = (idx < n) ? __ldcs(in + idx) : ~0ull;
         }
@@ -230,9 +242,9 @@ k_onesweep_packed(int64_t n_cap, const int64_t* __restrict__ n_dev, const uint64
     // the group's leader bumps the warp's counter with ONE shared-memory atomic whose return value is
     // the number of equal digits in the warp's earlier items (shared atomics of one warp retire in
     // program order), so the eight items are independent instruction streams for the scheduler.
-    unsigned short rank[kPkItems];
+    unsigned short rank[kItems];
 #pragma unroll
-    for (int i = 0; i < kPkItems; ++i) {
+    for (int i = 0; i < kItems; ++i) {
         const unsigned d = pk_digit(e[i], shift, mask);
         const unsigned peers = kBits > 0 ? match_digit_fixed<(kBits > 0 ? kBits : 1)>(d) : match_digit(d, bits);
         const int leader = __ffs(peers) - 1;
@@ -276,7 +288,7 @@ k_onesweep_packed(int64_t n_cap, const int64_t* __restrict__ n_dev, const uint64
 
     // scatter into the local sorted slot (needs only the local starts) ...
 #pragma unroll
-    for (int i = 0; i < kPkItems; ++i) {
+    for (int i = 0; i < kItems; ++i) {
         const unsigned d = pk_digit(e[i], shift, mask);
         s_elts[s_bin_start[d] + s_warp_hist[warp][d] + rank[i]] = e[i];
     }
@@ -321,24 +333,29 @@ k_onesweep_packed(int64_t n_cap, const int64_t* __restrict__ n_dev, const uint64
     __syncthreads();
 
     // write runs of equal digits contiguously
-    if (valid == kPkTile) {
+    if (valid == kTileElts) {
 #pragma unroll
-        for (int i = 0; i < kPkItems; ++i) {
+        for (int i = 0; i < kItems; ++i) {
             const int slot = tid + i * kPkThreads;
             const uint64_t x = s_elts[slot];
             const int64_t g = s_bin_global[pk_digit(x, shift, mask)] + slot;
             if (kLast) out32[g] = (int)(unsigned)x;
             else out[g] = x;
+            // optional: a per-element payload (indexed by the low word) gathered into sorted order by the
+            // pass that knows the final position -- the depth sort's last pass delivers tiles_touched in depth
+            // order, so the scan that follows reads contiguous memory
+            if (payload_dst != nullptr) payload_dst[g] = payload_src[(unsigned)x];
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < kPkItems; ++i) {
+        for (int i = 0; i < kItems; ++i) {
             const int slot = tid + i * kPkThreads;
             if (slot < valid) {
                 const uint64_t x = s_elts[slot];
                 const int64_t g = s_bin_global[pk_digit(x, shift, mask)] + slot;
                 if (kLast) out32[g] = (int)(unsigned)x;
                 else out[g] = x;
+                if (payload_dst != nullptr) payload_dst[g] = payload_src[(unsigned)x];
             }
         }
     }
@@ -354,18 +371,16 @@ k_onesweep_packed(int64_t n_cap, const int64_t* __restrict__ n_dev, const uint64
 // ------------------------------------------------------------------------------------------------
 constexpr int kDupBlock = 256;
 
-__global__ void __launch_bounds__(kDupBlock)
-k_duplicate_sorted(int64_t n, int width, int height, int ntx, int nty,
-                   const uint64_t* __restrict__ sorted_elts, const float* __restrict__ means_2d,
-                   const int* __restrict__ radii, const int* __restrict__ tiles_touched,
-                   const int* __restrict__ offsets /* in sorted order */, int64_t p_cap,
-                   const int64_t* __restrict__ p_dev, uint64_t* __restrict__ pairs) {
-    // pairs beyond the capacity of the caller's buffers are dropped (the frame is then flagged as
-    // overflowed by the scan's P > capacity, see cugs_b200_render_forward)
-    const int64_t p = p_dev ? min(*p_dev, p_cap) : p_cap;
+// one warp: 32 consecutive positions of the depth-sorted Gaussian list starting at s0. s_tile (optional):
+// the block's shared tile histogram, one shared atomic per emitted pair (fused pair histogram).
+template <bool kHist>
+__device__ __forceinline__ void dup_warp(int64_t s0, int64_t n, int width, int height, int ntx, int nty,
+                                         const uint64_t* __restrict__ sorted_elts, const float* __restrict__ means_2d,
+                                         const int* __restrict__ radii,
+                                         const int* __restrict__ tiles_sorted /* tiles_touched in depth order */,
+                                         const int* __restrict__ offsets, int64_t p, uint64_t* __restrict__ pairs,
+                                         unsigned* __restrict__ s_tile) {
     const int lane = threadIdx.x & 31;
-    const int64_t s0 = ((int64_t)blockIdx.x * (kDupBlock / 32) + (threadIdx.x >> 5)) * 32;
-    if (s0 >= n) return;
     const int64_t si = s0 + lane;
 
     int reserved = 0, emit = 0, tx0 = 0, ty0 = 0, w = 1;
@@ -373,7 +388,7 @@ k_duplicate_sorted(int64_t n, int width, int height, int ntx, int nty,
     int64_t off = 0;
     if (si < n) {
         g = (unsigned)sorted_elts[si];
-        reserved = tiles_touched[g];
+        reserved = tiles_sorted[si];
         off = offsets[si];
         const int radius = radii[g];
         if (radius > 0 && reserved > 0) {  // sorting.cu:44-45
@@ -415,13 +430,74 @@ k_duplicate_sorted(int64_t n, int width, int height, int ntx, int nty,
         const unsigned o_g = __shfl_sync(kFull, g, owner);
         if (k < total && base + k < p) {
             uint64_t pair = 0;
+            unsigned tile = 0;  // filler slots of quirk A.2: (tile 0, Gaussian 0)
             if (j < o_emit) {
                 const int q = (o_w > 1) ? (int)__umulhi((unsigned)j, o_magic) : j;   // j / o_w
                 const int ty = o_ty0 + q, tx = o_tx0 + (j - q * o_w);  // ty outer, tx inner (:63-64)
-                pair = ((uint64_t)(unsigned)(ty * ntx + tx) << 32) | (uint64_t)o_g;
+                tile = (unsigned)(ty * ntx + tx);
+                pair = ((uint64_t)tile << 32) | (uint64_t)o_g;
             }
             __stcs(pairs + base + k, pair);
+            if (kHist) atomicAdd(&s_tile[tile], 1u);
         }
+    }
+}
+
+__global__ void __launch_bounds__(kDupBlock)
+k_duplicate_sorted(int64_t n, int width, int height, int ntx, int nty,
+                   const uint64_t* __restrict__ sorted_elts, const float* __restrict__ means_2d,
+                   const int* __restrict__ radii, const int* __restrict__ tiles_touched,
+                   const int* __restrict__ offsets /* in sorted order */, int64_t p_cap,
+                   const int64_t* __restrict__ p_dev, uint64_t* __restrict__ pairs) {
+    // pairs beyond the capacity of the caller's buffers are dropped (the frame is then flagged as
+    // overflowed by the scan's P > capacity, see cugs_b200_render_forward)
+    const int64_t p = p_dev ? min(*p_dev, p_cap) : p_cap;
+    const int64_t s0 = ((int64_t)blockIdx.x * (kDupBlock / 32) + (threadIdx.x >> 5)) * 32;
+    if (s0 >= n) return;
+    dup_warp<false>(s0, n, width, height, ntx, nty, sorted_elts, means_2d, radii, tiles_touched, offsets, p, pairs,
+                    nullptr);
+}
+
+// duplicateWithKeys + the pair sort's histograms in ONE pass: a persistent grid of fat blocks (one or two per
+// SM) walks the depth-sorted list; every emitted pair also bumps the block's shared tile histogram, which
+// is folded into the digit histograms of the pair sort's passes and flushed once per block. This removes the
+// separate read of all P pairs that k_packed_histogram<true> needs (149 MB at 3 M Gaussians / 1080p).
+constexpr int kDupHistThreads = 1024;
+
+__global__ void __launch_bounds__(kDupHistThreads)
+k_duplicate_sorted_hist(int64_t n, int width, int height, int ntx, int nty,
+                        const uint64_t* __restrict__ sorted_elts, const float* __restrict__ means_2d,
+                        const int* __restrict__ radii, const int* __restrict__ tiles_touched,
+                        const int* __restrict__ offsets, int64_t p_cap, const int64_t* __restrict__ p_dev,
+                        uint64_t* __restrict__ pairs, PackedPlan plan, unsigned* __restrict__ digit_hist,
+                        int num_tiles, unsigned* __restrict__ tile_hist) {
+    extern __shared__ unsigned s_hist[];  // [passes*256] + [num_tiles]
+    unsigned* s_tile = s_hist + plan.passes * kPkRadix;
+    const int total_bins = plan.passes * kPkRadix + num_tiles;
+    for (int b = threadIdx.x; b < total_bins; b += kDupHistThreads) s_hist[b] = 0;
+    __syncthreads();
+    const int64_t p = p_dev ? min(*p_dev, p_cap) : p_cap;
+    const int64_t chunk = kDupHistThreads;  // Gaussians per block iteration (32 per warp)
+    for (int64_t c0 = (int64_t)blockIdx.x * chunk; c0 < n; c0 += (int64_t)gridDim.x * chunk) {
+        const int64_t s0 = c0 + (int64_t)(threadIdx.x >> 5) * 32;
+        if (s0 < n)
+            dup_warp<true>(s0, n, width, height, ntx, nty, sorted_elts, means_2d, radii, tiles_touched, offsets, p,
+                           pairs, s_tile);
+    }
+    __syncthreads();
+    // every digit of a pair's key is a function of its tile id: fold the digit histograms out of the tile histogram
+    for (int b = threadIdx.x; b < num_tiles; b += kDupHistThreads) {
+        const unsigned c = s_tile[b];
+        if (c) {
+            for (int ps = 0; ps < plan.passes; ++ps)
+                atomicAdd(&s_hist[ps * kPkRadix + (((unsigned)b >> plan.shift[ps]) & ((1u << plan.bits[ps]) - 1))], c);
+            atomicAdd(&tile_hist[b], c);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < plan.passes * kPkRadix; b += kDupHistThreads) {
+        const unsigned c = s_hist[b];
+        if (c) atomicAdd(&digit_hist[b], c);
     }
 }
 
@@ -433,7 +509,8 @@ using namespace cugs;
 // host-side launchers (internal; used by api.cu)
 // ------------------------------------------------------------------------------------------------
 size_t cugs_packed_sort_temp_bytes(int64_t n, int passes, int num_tiles) {
-    const int64_t tiles = (n + kPkTile - 1) / kPkTile;
+    const int64_t tile_elts = (int64_t)kPkThreads * pk_items_for(n);
+    const int64_t tiles = (n + tile_elts - 1) / tile_elts;
     return (size_t)kPkMaxPasses * kPkRadix * 4 + 64 + align_up((size_t)(num_tiles > 0 ? num_tiles : 1) * 4, 256) +
            (size_t)passes * (size_t)(tiles > 0 ? tiles : 1) * kPkRadix * 4;
 }
@@ -448,9 +525,12 @@ int cugs_packed_passes(int key_bits) { return make_packed_plan(key_bits).passes;
 //                    as the digit histograms and turned into [start,end) ranges
 //   n_dev          : if non-null, n is only the CAPACITY of a / b / out32_last and the element count is
 //                    min(*n_dev, n), read on the device (no host round trip: launches are sized on n)
+//   hist_done      : the digit / tile histograms in `temp` were already filled (k_duplicate_sorted_hist after
+//                    cugs_packed_sort_prepare): no memset, no histogram pass
+//   payload_src/dst: if non-null the LAST pass also writes payload_dst[final position] = payload_src[low word]
 int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, uint64_t* a, uint64_t* b,
                      int* out32_last, int num_tiles, int* tile_ranges, void* temp, size_t temp_bytes,
-                     const int64_t* n_dev) {
+                     const int64_t* n_dev, bool hist_done, const int* payload_src, int* payload_dst) {
     const PackedPlan plan = make_packed_plan(key_bits);
     if (n >= (1ll << 30))
         return set_error(h, CUGS_ERR_UNSUPPORTED, "n = %lld >= 2^30 elements is not supported", (long long)n);
@@ -462,19 +542,23 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
         return CUGS_OK;
     }
     if (n == 0) return CUGS_OK;
-    const int64_t tiles = (n + kPkTile - 1) / kPkTile;
+    const int items = pk_items_for(n);
+    const int64_t tile_elts = (int64_t)kPkThreads * items;
+    const int64_t tiles = (n + tile_elts - 1) / tile_elts;
     unsigned* digit_hist = reinterpret_cast<unsigned*>(temp);
     unsigned* tickets = digit_hist + kPkMaxPasses * kPkRadix;
     unsigned* tile_hist = tickets + 16;
     unsigned* lookback = tile_hist + align_up((size_t)(num_tiles > 0 ? num_tiles : 1) * 4, 256) / 4;
-    CUGS_CUDA_TRY(h, cudaMemsetAsync(temp, 0, need, s));
+    if (!hist_done) CUGS_CUDA_TRY(h, cudaMemsetAsync(temp, 0, need, s));
 
     int hist_blocks = h->sm_count;  // 148 x 8160 global atomics in the flush instead of 444 x 8160
     const int64_t hist_tile = (int64_t)kPkHistThreads * kPkHistItems;
     if ((int64_t)hist_blocks * hist_tile > n) hist_blocks = (int)((n + hist_tile - 1) / hist_tile);
     const bool want_ranges = tile_ranges != nullptr && num_tiles > 0;
     const size_t hist_smem = (size_t)plan.passes * kPkRadix * 4 + (want_ranges ? (size_t)num_tiles * 4 : 0);
-    if (want_ranges) {
+    if (hist_done) {
+        // nothing: filled by k_duplicate_sorted_hist
+    } else if (want_ranges) {
         if (hist_smem > 200 * 1024)
             return set_error(h, CUGS_ERR_UNSUPPORTED, "%d tiles exceed the shared-memory tile histogram", num_tiles);
         CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_packed_histogram<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -485,7 +569,7 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
         k_packed_histogram<false><<<hist_blocks, kPkHistThreads, hist_smem, s>>>(n, n_dev, a, plan, digit_hist, 0,
                                                                                  nullptr);
     }
-    CUGS_LAUNCH_CHECK(h, "k_packed_histogram");
+    if (!hist_done) CUGS_LAUNCH_CHECK(h, "k_packed_histogram");
     k_packed_scan_bins<<<plan.passes, kPkRadix, 0, s>>>(digit_hist);
     CUGS_LAUNCH_CHECK(h, "k_packed_scan_bins");
     if (want_ranges) {
@@ -495,15 +579,22 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
     uint64_t* src = a;
     uint64_t* dst = b;
     for (int ps = 0; ps < plan.passes; ++ps) {
-        const bool last = (ps == plan.passes - 1) && out32_last != nullptr;
+        const bool final_pass = ps == plan.passes - 1;
+        const bool last = final_pass && out32_last != nullptr;
         unsigned* lb = lookback + (size_t)ps * tiles * kPkRadix;
-#define CUGS_OS_LAUNCH(LAST, BITS)                                                                              \
+#define CUGS_OS_LAUNCH_I(LAST, BITS, ITEMS)                                                                     \
     do {                                                                                                        \
-        CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_onesweep_packed<LAST, BITS>,                                    \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPkSmemBytes)); \
-        k_onesweep_packed<LAST, BITS><<<(unsigned)tiles, kPkThreads, kPkSmemBytes, s>>>(                        \
+        CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_onesweep_packed<LAST, BITS, ITEMS>,                             \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
+                                              (int)pk_smem_bytes(ITEMS)));                                      \
+        k_onesweep_packed<LAST, BITS, ITEMS><<<(unsigned)tiles, kPkThreads, pk_smem_bytes(ITEMS), s>>>(         \
             n, n_dev, src, dst, LAST ? out32_last : nullptr, digit_hist + ps * kPkRadix, lb, tickets + ps,      \
-            plan.shift[ps], plan.bits[ps]);                                                                     \
+            plan.shift[ps], plan.bits[ps], final_pass ? payload_src : nullptr, final_pass ? payload_dst : nullptr); \
+    } while (0)
+#define CUGS_OS_LAUNCH(LAST, BITS)                                                  \
+    do {                                                                            \
+        if (items == kPkItemsSmall) CUGS_OS_LAUNCH_I(LAST, BITS, kPkItemsSmall);    \
+        else CUGS_OS_LAUNCH_I(LAST, BITS, kPkItems);                                \
     } while (0)
 #define CUGS_OS_DISPATCH(LAST)                          \
     switch (plan.bits[ps]) {                            \
@@ -515,9 +606,40 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
         if (last) { CUGS_OS_DISPATCH(true) } else { CUGS_OS_DISPATCH(false) }
 #undef CUGS_OS_DISPATCH
 #undef CUGS_OS_LAUNCH
+#undef CUGS_OS_LAUNCH_I
         CUGS_LAUNCH_CHECK(h, "k_onesweep_packed");
         uint64_t* t = src; src = dst; dst = t;
     }
+    return CUGS_OK;
+}
+
+// duplicateWithKeys fused with the pair sort's histograms: clears `sort_temp` (the temp of the pair sort that
+// follows, which must then be called with hist_done = true), then one persistent pass
+int cugs_duplicate_sorted_hist(cugs_handle_t* h, cudaStream_t s, int64_t n, int width, int height,
+                               const uint64_t* sorted_elts, const float* means_2d, const int32_t* radii,
+                               const int32_t* tiles_touched, const int32_t* offsets_sorted, int64_t p, uint64_t* pairs,
+                               const int64_t* p_dev, int key_bits, int num_tiles, void* sort_temp,
+                               size_t sort_temp_bytes) {
+    const PackedPlan plan = make_packed_plan(key_bits);
+    const size_t need = cugs_packed_sort_temp_bytes(p, plan.passes, num_tiles);
+    if (sort_temp_bytes < need)
+        return set_error(h, CUGS_ERR_WORKSPACE, "packed sort temp too small: %zu < %zu", sort_temp_bytes, need);
+    CUGS_CUDA_TRY(h, cudaMemsetAsync(sort_temp, 0, need, s));
+    if (n == 0 || p == 0) return CUGS_OK;
+    unsigned* digit_hist = reinterpret_cast<unsigned*>(sort_temp);
+    unsigned* tile_hist = digit_hist + kPkMaxPasses * kPkRadix + 16;
+    const size_t smem = (size_t)plan.passes * kPkRadix * 4 + (size_t)num_tiles * 4;
+    if (smem > 200 * 1024)
+        return set_error(h, CUGS_ERR_UNSUPPORTED, "%d tiles exceed the shared-memory tile histogram", num_tiles);
+    CUGS_CUDA_TRY(h, cudaFuncSetAttribute(k_duplicate_sorted_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntx = (width + kTile - 1) / kTile, nty = (height + kTile - 1) / kTile;
+    int blocks = h->sm_count * (smem <= 100 * 1024 ? 2 : 1);
+    const int64_t chunks = (n + kDupHistThreads - 1) / kDupHistThreads;
+    if ((int64_t)blocks > chunks) blocks = (int)chunks;
+    k_duplicate_sorted_hist<<<blocks, kDupHistThreads, smem, s>>>(n, width, height, ntx, nty, sorted_elts, means_2d,
+                                                                  radii, tiles_touched, offsets_sorted, p, p_dev, pairs,
+                                                                  plan, digit_hist, num_tiles, tile_hist);
+    CUGS_LAUNCH_CHECK(h, "k_duplicate_sorted_hist");
     return CUGS_OK;
 }
 
@@ -554,5 +676,5 @@ extern "C" int cugs_b200_sort_packed(cugs_handle_t* h, void* stream, int64_t n, 
                  "num_tiles exceeds 2^key_bits");
     CUGS_REQUIRE(h, n == 0 || (elts_a && elts_b && temp), "null pointer");
     return cugs_packed_sort(h, (cudaStream_t)stream, n, key_bits, elts_a, elts_b, out32_last, num_tiles, tile_ranges,
-                            temp, temp_bytes, n_dev);
+                            temp, temp_bytes, n_dev, false, nullptr, nullptr);
 }

@@ -477,7 +477,13 @@ __device__ __forceinline__ float mcmc_reg_grad(int grp, float p, float reg_opa, 
 
 __global__ void __launch_bounds__(256)
 k_adam_multi(AdamGroups G, int64_t total_chunks, float b1, float b2, float eps, float bc1, float bc2,
-             float grad_scale, float reg_opa /* lambda_o / N */, float reg_scl /* lambda_s / (3N) */) {
+             float grad_scale, float reg_opa /* lambda_o / N */, float reg_scl /* lambda_s / (3N) */,
+             const StepDyn* __restrict__ dyn /* optional: per-step scalars in device memory (graph replay) */) {
+    if (dyn != nullptr) {
+        if (!dyn->ok) return;  // a frame of this step overflowed: the host re-runs the step
+        bc1 = dyn->bc1;
+        bc2 = dyn->bc2;
+    }
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total_chunks;
          c += (int64_t)gridDim.x * blockDim.x) {
         int grp = 0;
@@ -490,7 +496,7 @@ k_adam_multi(AdamGroups G, int64_t total_chunks, float b1, float b2, float eps, 
         const float* g = G.g[grp];
         float* m = G.m[grp];
         float* v = G.v[grp];
-        const float lr = G.lr[grp];
+        const float lr = dyn ? dyn->lr[grp] : G.lr[grp];
         const bool reg = (reg_opa != 0.0f && grp == 2) || (reg_scl != 0.0f && grp == 3);
         if (e0 + 4 <= G.count[grp]) {
             float4 pv = *reinterpret_cast<float4*>(p + e0);
@@ -541,9 +547,15 @@ k_adam_multi(AdamGroups G, int64_t total_chunks, float b1, float b2, float eps, 
 __global__ void __launch_bounds__(256)
 k_mcmc_noise(int64_t n, float* __restrict__ positions, const float* __restrict__ scales,
              const float* __restrict__ opacities, float noise_lr, float gate_k, float gate_t, unsigned seed_lo,
-             unsigned seed_hi, unsigned step, float* __restrict__ normals_out /* optional [N,3] */) {
+             unsigned seed_hi, unsigned step, float* __restrict__ normals_out /* optional [N,3] */,
+             const StepDyn* __restrict__ dyn) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (dyn != nullptr) {
+        if (!dyn->ok) return;
+        noise_lr = dyn->noise_lr;
+        step = dyn->step;
+    }
     float z0, z1, z2;
     philox_normal3((unsigned)i, (unsigned)((uint64_t)i >> 32), step, 0x3c6ef372u, seed_lo, seed_hi, z0, z1, z2);
     const float sg = 1.0f / (1.0f + expf(-opacities[i]));
@@ -578,6 +590,14 @@ k_accumulate_stats(int64_t n, const float* __restrict__ dL_dmeans_2d, const int*
 }  // namespace cugs
 
 using namespace cugs;
+
+int cugs_adam_launch(cugs_handle_t* h, void* stream, float* const params[5], const float* const grads[5],
+                     float* const m[5], float* const v[5], const int64_t counts[5], const float lr[5], float beta1,
+                     float beta2, float eps, float bc1, float bc2, float grad_scale, float lambda_opacity,
+                     float lambda_scale, const StepDyn* dyn);
+int cugs_noise_launch(cugs_handle_t* h, void* stream, int64_t n, float* positions, const float* scales,
+                      const float* opacities, float noise_lr, float gate_k, float gate_t, uint64_t seed,
+                      uint32_t step, float* normals_out, const StepDyn* dyn);
 
 extern "C" size_t cugs_b200_loss_workspace_bytes(int width, int height) {
     if (width <= 0 || height <= 0) return 64;
@@ -649,6 +669,15 @@ extern "C" int cugs_b200_adam_step_mcmc(cugs_handle_t* h, void* stream, float* c
                                         const int64_t counts[5], const float lr[5], float beta1, float beta2,
                                         float eps, float bc1, float bc2, float grad_scale, float lambda_opacity,
                                         float lambda_scale) {
+    return cugs_adam_launch(h, stream, params, grads, m, v, counts, lr, beta1, beta2, eps, bc1, bc2, grad_scale,
+                            lambda_opacity, lambda_scale, nullptr);
+}
+
+// dyn != NULL: learning rates and bias corrections are read from device memory (trainer.cu)
+int cugs_adam_launch(cugs_handle_t* h, void* stream, float* const params[5], const float* const grads[5],
+                     float* const m[5], float* const v[5], const int64_t counts[5], const float lr[5], float beta1,
+                     float beta2, float eps, float bc1, float bc2, float grad_scale, float lambda_opacity,
+                     float lambda_scale, const StepDyn* dyn) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, params && grads && m && v && counts && lr, "null pointer");
     AdamGroups G;
@@ -670,7 +699,7 @@ extern "C" int cugs_b200_adam_step_mcmc(cugs_handle_t* h, void* stream, float* c
     const float reg_opa = (lambda_opacity != 0.0f && counts[2] > 0) ? lambda_opacity / (float)counts[2] : 0.0f;
     const float reg_scl = (lambda_scale != 0.0f && counts[3] > 0) ? lambda_scale / (float)counts[3] : 0.0f;
     k_adam_multi<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(G, chunks, beta1, beta2, eps, bc1, bc2,
-                                                                    grad_scale, reg_opa, reg_scl);
+                                                                    grad_scale, reg_opa, reg_scl, dyn);
     CUGS_LAUNCH_CHECK(h, "k_adam_multi");
     return CUGS_OK;
 }
@@ -679,13 +708,20 @@ extern "C" int cugs_b200_mcmc_inject_noise(cugs_handle_t* h, void* stream, int64
                                            const float* scales, const float* opacities, float noise_lr,
                                            float gate_k, float gate_t, uint64_t seed, uint32_t step,
                                            float* normals_out) {
+    return cugs_noise_launch(h, stream, n, positions, scales, opacities, noise_lr, gate_k, gate_t, seed, step,
+                             normals_out, nullptr);
+}
+
+int cugs_noise_launch(cugs_handle_t* h, void* stream, int64_t n, float* positions, const float* scales,
+                      const float* opacities, float noise_lr, float gate_k, float gate_t, uint64_t seed,
+                      uint32_t step, float* normals_out, const StepDyn* dyn) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, n >= 0, "n must be >= 0");
     if (n == 0) return CUGS_OK;
     CUGS_REQUIRE(h, positions && scales && opacities, "null pointer");
     k_mcmc_noise<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         n, positions, scales, opacities, noise_lr, gate_k, gate_t, (unsigned)(seed & 0xffffffffu),
-        (unsigned)(seed >> 32), step, normals_out);
+        (unsigned)(seed >> 32), step, normals_out, dyn);
     CUGS_LAUNCH_CHECK(h, "k_mcmc_noise");
     return CUGS_OK;
 }

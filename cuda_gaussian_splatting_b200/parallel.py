@@ -50,13 +50,21 @@ def allreduce_step(arena: torch.Tensor, max_radii: Optional[torch.Tensor] = None
 
 
 def sparse_allreduce_step(buffers, with_stats: bool = True, dense_threshold: float = 0.6,
-                          group: Optional[dist.ProcessGroup] = None, ops=None) -> dict:
+                          group: Optional[dist.ProcessGroup] = None, ops=None, state: Optional[dict] = None) -> dict:
     """The step's gradient exchange, exploiting that a view leaves most Gaussians' gradients exactly
     zero: (1) ONE int32 MAX all-reduce of [touch mask | max_radii bits] (8 B/Gaussian), (2) exclusive
-    scan of the union mask -> M touched Gaussians (one 8-byte read on the host), (3) the M gradient
-    rows are gathered into a dense buffer, followed by the two additive statistics, (4) ONE
-    all-reduce(sum) of (59 M + 2 N) floats instead of 61 N, (5) scatter back. Falls back to the dense
-    all-reduce when M > dense_threshold * N. Numerically a plain sum either way.
+    scan of the union mask -> M touched Gaussians, (3) the M gradient rows are gathered into a dense
+    buffer, followed by the two additive statistics, (4) ONE all-reduce(sum) of (59 M + 2 N) floats
+    instead of 61 N, (5) scatter back. Falls back to the dense all-reduce when M > dense_threshold * N.
+    Numerically a plain sum either way.
+
+    ``state`` (a dict the caller keeps between steps) removes the host round trip for M: the collective is
+    sized on a row CAPACITY derived from the previous steps' M (identical on every rank, because M is the
+    size of the all-reduced union), the real count is read on the device, and {M, M > capacity} reaches the
+    host asynchronously; it is looked at one step later (``state["overflow"]`` is then set and the caller must
+    repeat that step -- the capacity is ``state["headroom"]`` (default 1.15) x the M that set it and grows as
+    soon as M comes within 5 % of it, which makes an overflow a non-event for a view set that changes
+    gradually). Without ``state`` the call blocks once on M, as in round 1.
 
     ``buffers``: FrameBuffers (grad_arena, max_buf, touch_mask, dL_d* views). ``ops``: object with
     scan(mask)->(offsets, M), gather(...), scatter(...); defaults to the CUDA library (tests inject
@@ -67,25 +75,78 @@ def sparse_allreduce_step(buffers, with_stats: bool = True, dense_threshold: flo
         return {"mode": "single", "touched": None}
     dist.all_reduce(b.max_buf, op=dist.ReduceOp.MAX, group=group)
     ops = ops or _CudaRowOps()
+    num_coeffs = int(b.dL_dsh_coeffs.shape[2])
+
+    def finish(m_layout, offsets, m_for_ops, m_dev):
+        rows = ops.compact_floats(m_layout, num_coeffs)  # the gradient rows, group-major
+        need = rows + (2 * n if with_stats else 0)
+        if b.grad_compact is None or b.grad_compact.numel() < need:
+            # zeros: the <= 3 pad floats between the group blocks are never written by the gather
+            b.grad_compact = torch.zeros((int(need * 1.25) + 1024,), dtype=torch.float32, device=b.grad_arena.device)
+        compact = b.grad_compact[:need]
+        ops.gather(b, offsets, m_for_ops, compact, m_dev)
+        if with_stats:
+            compact[rows:rows + n].copy_(b.step_grad_accum)
+            compact[rows + n:].copy_(b.step_grad_count)
+        dist.all_reduce(compact, op=dist.ReduceOp.SUM, group=group)
+        ops.scatter(b, offsets, m_for_ops, compact, m_dev)
+        if with_stats:
+            b.step_grad_accum.copy_(compact[rows:rows + n])
+            b.step_grad_count.copy_(compact[rows + n:])
+        return need
+
+    if state is not None and state.get("m_cap") and hasattr(ops, "scan_dev"):
+        # look at the status of the PREVIOUS exchange (its copy was queued a whole step ago)
+        prev = state.get("pending")
+        if prev is not None:
+            prev["event"].synchronize()
+            m_prev, over = int(prev["host"][0]), bool(int(prev["host"][1]))
+            state["m_seen"] = max(state.get("m_seen", 0), m_prev)
+            if over:
+                state["overflow"] = True
+            if m_prev > dense_threshold * n:
+                state["m_cap"] = None          # go back to the blocking path, which switches to dense
+            elif m_prev * 1.05 > state["m_cap"]:
+                state["m_cap"] = min(n, int(m_prev * state.get("headroom", 1.15)) + 1024)
+            state["pending"] = None
+    if state is not None and state.get("m_cap") and hasattr(ops, "scan_dev"):
+        m_cap = int(state["m_cap"])
+        offsets, m_dev = ops.scan_dev(b)
+        if "status_dev" not in state:
+            dev = b.grad_arena.device
+            state["status_dev"] = torch.zeros((2,), dtype=torch.int64, device=dev)
+            pin = (lambda t: t.pin_memory()) if dev.type == "cuda" else (lambda t: t)
+            state["status_host"] = [pin(torch.zeros((2,), dtype=torch.int64)) for _ in range(2)]
+            state["flip"] = 0
+        ops.status_dev = state["status_dev"]
+        need = finish(m_cap, offsets, m_cap, m_dev)
+        host = state["status_host"][state["flip"]]
+        state["flip"] ^= 1
+        host.copy_(state["status_dev"], non_blocking=True)
+        ev = _DoneEvent()
+        if b.grad_arena.device.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record()
+        state["pending"] = {"host": host, "event": ev}
+        return {"mode": "sparse", "touched": state.get("m_seen"), "row_capacity": m_cap, "floats": need,
+                "host_sync": False}
+
     offsets, m = ops.scan(b)
     if m > dense_threshold * n:
         dist.all_reduce(b.grad_arena, op=dist.ReduceOp.SUM, group=group)
         return {"mode": "dense", "touched": m}
-    rows = ops.compact_floats(m, int(b.dL_dsh_coeffs.shape[2]))  # the M gradient rows, group-major
-    need = rows + (2 * n if with_stats else 0)
-    if b.grad_compact is None or b.grad_compact.numel() < need:
-        b.grad_compact = torch.empty((int(need * 1.25) + 1024,), dtype=torch.float32, device=b.grad_arena.device)
-    compact = b.grad_compact[:need]
-    ops.gather(b, offsets, m, compact)
-    if with_stats:
-        compact[rows:rows + n].copy_(b.step_grad_accum)
-        compact[rows + n:].copy_(b.step_grad_count)
-    dist.all_reduce(compact, op=dist.ReduceOp.SUM, group=group)
-    ops.scatter(b, offsets, m, compact)
-    if with_stats:
-        b.step_grad_accum.copy_(compact[rows:rows + n])
-        b.step_grad_count.copy_(compact[rows + n:])
-    return {"mode": "sparse", "touched": m, "floats": need}
+    need = finish(m, offsets, m, None)
+    if state is not None:
+        state["m_cap"] = min(n, int(m * state.get("headroom", 1.15)) + 1024)
+        state["m_seen"] = max(state.get("m_seen", 0), m)
+    return {"mode": "sparse", "touched": m, "floats": need, "host_sync": True}
+
+
+class _DoneEvent:
+    """Stand-in for torch.cuda.Event on the CPU (gloo) test path: copies there are synchronous."""
+
+    def synchronize(self):
+        return None
 
 
 class _CudaRowOps:
@@ -119,24 +180,47 @@ class _CudaRowOps:
         _lib.check(h, st, "cugs_b200_scan")
         return b.touch_offsets, int(total.value)
 
-    def gather(self, b, offsets, m, compact):
+    status_dev = None  # set by sparse_allreduce_step in the no-host-sync mode: receives {M, M > capacity}
+
+    def scan_dev(self, b):
+        """Scan of the union mask with the total left on the device (no host round trip)."""
+        from . import _lib
+        from .rasterizer import _lib_and_handle, _stream
+        dev = b.grad_arena.device
+        lib, h = _lib_and_handle(dev)
+        n = int(b.n)
+        if b.touch_offsets is None:
+            b.touch_offsets = torch.empty((n,), dtype=torch.int32, device=dev)
+            b._scan_tmp = torch.empty((lib.cugs_b200_scan_temp_bytes(n),), dtype=torch.uint8, device=dev)
+            b._touch_idx = torch.empty((n,), dtype=torch.int32, device=dev)
+        if getattr(b, "_touch_total", None) is None:
+            b._touch_total = torch.zeros((1,), dtype=torch.int64, device=dev)
+        st = lib.cugs_b200_scan(h, _stream(dev), n, b.touch_mask.data_ptr(), b.touch_offsets.data_ptr(),
+                                b._touch_total.data_ptr(), None, b._scan_tmp.data_ptr(), b._scan_tmp.numel())
+        _lib.check(h, st, "cugs_b200_scan")
+        return b.touch_offsets, b._touch_total
+
+    def gather(self, b, offsets, m, compact, m_dev=None):
         from . import _lib
         from .rasterizer import _lib_and_handle, _stream
         dev = b.grad_arena.device
         lib, h = _lib_and_handle(dev)
         st = lib.cugs_b200_gather_grad_rows(h, _stream(dev), int(b.n), int(b.dL_dsh_coeffs.shape[2]),
                                             b.touch_mask.data_ptr(), offsets.data_ptr(), int(m), self._groups(b),
-                                            compact.data_ptr(), b._touch_idx.data_ptr())
+                                            compact.data_ptr(), b._touch_idx.data_ptr(),
+                                            None if m_dev is None else m_dev.data_ptr(),
+                                            None if (m_dev is None or self.status_dev is None) else self.status_dev.data_ptr())
         _lib.check(h, st, "cugs_b200_gather_grad_rows")
 
-    def scatter(self, b, offsets, m, compact):
+    def scatter(self, b, offsets, m, compact, m_dev=None):
         from . import _lib
         from .rasterizer import _lib_and_handle, _stream
         dev = b.grad_arena.device
         lib, h = _lib_and_handle(dev)
         st = lib.cugs_b200_scatter_grad_rows(h, _stream(dev), int(b.n), int(b.dL_dsh_coeffs.shape[2]),
                                              b.touch_mask.data_ptr(), offsets.data_ptr(), int(m), compact.data_ptr(),
-                                             self._groups(b), b._touch_idx.data_ptr())
+                                             self._groups(b), b._touch_idx.data_ptr(),
+                                             None if m_dev is None else m_dev.data_ptr())
         _lib.check(h, st, "cugs_b200_scatter_grad_rows")
 
 

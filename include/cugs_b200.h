@@ -74,7 +74,11 @@ void cugs_b200_destroy(cugs_handle_t* h);
 const char* cugs_b200_last_error(const cugs_handle_t* h);
 int cugs_b200_abi_version(void);
 int cugs_b200_sm_count(const cugs_handle_t* h);
-/* number of CUDA kernels this handle has launched so far (memsets / copies not counted) */
+/* SM count, maximum SM clock (kHz) and L2 size (bytes) of the handle's device, from the CUDA runtime: the
+ * denominators of the FP32 / MUFU rooflines the benchmark reports for the blend kernels. */
+int cugs_b200_device_info(const cugs_handle_t* h, int* sm_count, int* clock_khz, int* l2_bytes);
+/* number of CUDA kernels this handle has launched so far (memsets / copies not counted; a replayed CUDA
+ * graph of the trainer counts the kernel nodes it contains) */
 uint64_t cugs_b200_launch_count(const cugs_handle_t* h);
 
 /* ---- stage 1: preprocess forward ---------------------------------------------------------
@@ -375,20 +379,97 @@ int cugs_b200_mcmc_relocate(cugs_handle_t* h, void* stream, int64_t n, int num_c
                             uint32_t step, int32_t* source_out, float* normals_out, int64_t* counts_host,
                             void* temp, size_t temp_bytes);
 
+/* ---- the training step in C++ ---------------------------------------------------
+ * Trainer::train_step (training/trainer.cpp:178-316) without the Dataset, as host code of this library:
+ * update_lr (:180) -> active SH degree (:183, training/lr_schedule.hpp:70-72) -> per view: render (:211) ->
+ * fused L1+SSIM loss and gradient (:214-225) -> render_backward (:228) with the step's gradients summed in
+ * place and accumulate_gradients (:269) fused in -> FusedAdam::step (:240-242) [+ the MCMC regulariser
+ * :232-237 inside the Adam launch, + inject_noise :251]. No host synchronisation inside a step (the
+ * reference blocks 3-6 times per iteration): frames go through cugs_b200_render_forward, losses and the
+ * per-frame pair counts stay on the device and reach pinned memory at the end of the step. With use_graph the
+ * step is captured into a CUDA graph on its second call and replayed afterwards (re-captured when the view
+ * set or the active SH degree changes); per-step scalars (learning rates, bias corrections, noise scale,
+ * step number) are refreshed by one small H2D copy in front of each replay. If a frame's pair count exceeds
+ * p_capacity the update phase does nothing (status ok = 0): re-create the trainer with a larger capacity and
+ * repeat the step. All tensors are caller-owned device memory in the reference's layouts; params / adam_m /
+ * adam_v / grads are in the Adam group order positions, sh_coeffs, opacities, scales, rotations
+ * (optimizer/fused_adam.cu:94-97). */
+typedef struct cugs_train_config {
+    float lambda_ssim;             /* TrainConfig::lambda_ssim, weight of the SSIM term (loss.hpp:52) */
+    int32_t max_sh_degree;
+    float background[3];
+    float lr_position_init, lr_position_final; /* PositionLRConfig, training/lr_schedule.hpp:36-41 */
+    int32_t lr_position_max_steps;
+    float lr_sh_coeffs, lr_opacities, lr_scales, lr_rotations; /* AdamConfig, optimizer/adam.hpp:30-41 */
+    float beta1, beta2, eps;
+    int32_t accumulate_stats;      /* fuse DensificationController::accumulate_gradients (needs the stats pointers) */
+    int32_t mcmc;                  /* MCMC mode: regulariser gradient inside Adam + position noise after it */
+    float lambda_opacity, lambda_scale;
+    float noise_lr_init, noise_lr_final;
+    int32_t noise_lr_max_steps;
+    float noise_gate_k, noise_gate_t;
+    uint64_t noise_seed;
+    int32_t frames_in_flight;      /* 1 or 2 (two streams: the front end of view v+1 under the backward of view v) */
+    int32_t use_graph;             /* capture the step into a CUDA graph and replay it */
+} cugs_train_config_t;
+
+typedef struct cugs_train_tensors {
+    float* params[5];
+    float* adam_m[5];
+    float* adam_v[5];
+    float* grads[5];
+    float* dL_dmeans_2d;           /* [N,2], per view (densification.cpp:77) */
+    float* grad_accum;             /* optional, all three or none: the densification accumulators */
+    float* grad_count;
+    float* max_radii;
+    int32_t* touch_mask;           /* optional [N] i32: sparse gradient rows (see CUGS_BWD_SPARSE_ROWS) */
+} cugs_train_tensors_t;
+
+typedef struct cugs_trainer cugs_trainer_t;
+size_t cugs_b200_trainer_workspace_bytes(int64_t n, int num_coeffs, int width, int height,
+                                         int64_t p_capacity, int frames_in_flight);
+int cugs_b200_trainer_create(cugs_handle_t* h, int64_t n, int num_coeffs, int width, int height,
+                             int64_t p_capacity, const cugs_train_config_t* cfg,
+                             const cugs_train_tensors_t* tensors, void* workspace, size_t workspace_bytes,
+                             cugs_trainer_t** out);
+void cugs_b200_trainer_destroy(cugs_trainer_t* t);
+/* The views this rank renders every step (cameras + device target images [H,W,3]); total_views_per_step =
+ * views of ALL ranks (Adam's gradient scale is 1 / total). active_sh_degree, num_coeffs, bg and
+ * scale_modifier of the views are set by the trainer. dL_dcolor_dev (optional array, entries may be NULL):
+ * a view with a given dL/dcolor [H,W,3] skips the loss (forward + backward only; its loss scalars are 0). */
+int cugs_b200_trainer_set_views(cugs_trainer_t* t, int num_views, const cugs_view_t* views,
+                                const float* const* targets_dev, const float* const* dL_dcolor_dev,
+                                int total_views_per_step);
+/* phases: 1 = views (render -> loss -> backward), 2 = update (Adam [+ regulariser] [+ noise]), 3 = both.
+ * View-parallel training calls 1, exchanges the gradients, then 2. Nothing blocks. */
+int cugs_b200_trainer_step(cugs_trainer_t* t, void* stream, int step, int phases);
+/* Blocking read of the most recent step: scalars3 = {loss, l1, mean ssim} averaged over this rank's views,
+ * status3 = {ok, largest pair count of the step's frames, views folded in}. */
+int cugs_b200_trainer_result(cugs_trainer_t* t, void* stream, float scalars3[3], int64_t status3[3]);
+/* FusedAdam::step_count_ (bias corrections): carried over when a trainer is re-created */
+int cugs_b200_trainer_set_adam_steps(cugs_trainer_t* t, int64_t steps);
+int64_t cugs_b200_trainer_adam_steps(const cugs_trainer_t* t);
+
 /* ---- view-parallel gradient exchange (no reference counterpart: the reference is single-GPU) ----
  * Compaction of the gradient rows of the touched Gaussians around the all-reduce. touch: [N] i32
  * union mask (after a MAX all-reduce over the ranks); offsets: its exclusive scan (cugs_b200_scan);
  * m: number of touched Gaussians; grads: the five dense gradient arrays in Adam group order
  * (positions [N,3], sh_coeffs [N,3,C], opacities [N,1], scales [N,3], rotations [N,4]); compact:
  * cugs_b200_compact_grad_floats(m, C) floats, group-major, every group block starting at a multiple of
- * 4 floats; idx_scratch: m ints of device scratch (index list). */
+ * 4 floats; idx_scratch: m ints of device scratch (index list).
+ * m_dev (optional, device int64 = the total the scan wrote): no host round trip for M -- `m` is then only the
+ * row CAPACITY the compact layout is sized for (e.g. 1.25 x the previous step's M), the real count is read on
+ * the device, the gather zero-fills the rows in between and status_dev (optional, 2 x int64) receives
+ * {M, M > capacity}; rows beyond the capacity are dropped, so an overflowed exchange must be repeated. */
 int64_t cugs_b200_compact_grad_floats(int64_t m, int num_coeffs);
 int cugs_b200_gather_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs,
                                const int32_t* touch, const int32_t* offsets, int64_t m,
-                               const float* const grads[5], float* compact, int32_t* idx_scratch);
+                               const float* const grads[5], float* compact, int32_t* idx_scratch,
+                               const int64_t* m_dev, int64_t* status_dev);
 int cugs_b200_scatter_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs,
                                 const int32_t* touch, const int32_t* offsets, int64_t m,
-                                const float* compact, float* const grads[5], int32_t* idx_scratch);
+                                const float* compact, float* const grads[5], int32_t* idx_scratch,
+                                const int64_t* m_dev);
 
 #ifdef __cplusplus
 }

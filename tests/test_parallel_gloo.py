@@ -115,21 +115,37 @@ class TorchRowOps:
     def _groups(self, b):
         return [b.dL_dpositions, b.dL_dsh_coeffs.view(b.n, -1), b.dL_dopacities, b.dL_dscales, b.dL_drotations]
 
-    def gather(self, b, offsets, m, compact):
-        sel = b.touch_mask.bool()
+    status_dev = None
+
+    def scan_dev(self, b):  # the total stays "on the device": a tensor, never an int
+        offsets, m = self.scan(b)
+        return offsets, torch.tensor([m], dtype=torch.int64)
+
+    def _rows(self, b, m, m_dev):
+        """(selected rows, count): with m_dev, m is the row capacity (rows beyond it are dropped)."""
+        idx = b.touch_mask.bool().nonzero().reshape(-1)
+        if m_dev is not None:
+            real = int(m_dev[0])
+            if self.status_dev is not None:
+                self.status_dev[0], self.status_dev[1] = real, int(real > m)
+            idx = idx[:m]
+        return idx, idx.numel()
+
+    def gather(self, b, offsets, m, compact, m_dev=None):
+        idx, k = self._rows(b, m, m_dev)
         off = 0
         for g in self._groups(b):
             w = g.shape[1]
-            compact[off:off + m * w].copy_(g[sel].reshape(-1))
-            compact[off + m * w:off + _a4(m * w)] = 0
+            compact[off:off + k * w].copy_(g[idx].reshape(-1))
+            compact[off + k * w:off + _a4(m * w)] = 0
             off += _a4(m * w)
 
-    def scatter(self, b, offsets, m, compact):
-        sel = b.touch_mask.bool()
+    def scatter(self, b, offsets, m, compact, m_dev=None):
+        idx, k = self._rows(b, m, m_dev)
         off = 0
         for g in self._groups(b):
             w = g.shape[1]
-            g[sel] = compact[off:off + m * w].view(m, w)
+            g[idx] = compact[off:off + k * w].view(k, w)
             off += _a4(m * w)
 
 
@@ -190,3 +206,46 @@ def test_sparse_exchange_equals_dense_sum(tmp_path, threshold, mode):
     assert torch.equal(r0["arena"], a.grad_arena + b.grad_arena), "sparse exchange must equal the dense sum"
     assert torch.equal(r0["max_buf"][:N], torch.maximum(a.touch_mask, b.touch_mask))
     assert torch.equal(r0["max_buf"][N:].view(torch.float32), torch.maximum(a.step_max_radii, b.step_max_radii))
+
+
+def nosync_worker(rank, world, port, out_dir):
+    """Three consecutive exchanges with `state`: the first blocks on M and sets the row capacity, the next two
+    size the collective on that capacity and read M "on the device"; the last one is made to overflow."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cuda_gaussian_splatting_b200 import parallel
+    state, outs = {}, []
+    for step in range(3):
+        b = FakeBuffers(N, C)
+        fill_rank(b, rank + 10 * step)
+        info = parallel.sparse_allreduce_step(b, with_stats=True, ops=TorchRowOps(), state=state)
+        outs.append({"arena": b.grad_arena.clone(), "info": dict(info)})
+    # force an overflow: a capacity far below the union
+    state["m_cap"], state["pending"] = 8, None
+    b = FakeBuffers(N, C)
+    fill_rank(b, rank)
+    parallel.sparse_allreduce_step(b, with_stats=True, ops=TorchRowOps(), state=state)
+    b2 = FakeBuffers(N, C)
+    fill_rank(b2, rank)
+    parallel.sparse_allreduce_step(b2, with_stats=True, ops=TorchRowOps(), state=state)   # sees the previous status
+    torch.save({"outs": outs, "overflow": bool(state.get("overflow")), "m_cap": state["m_cap"]},
+               os.path.join(out_dir, f"n{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_without_host_round_trip_for_m(tmp_path):
+    world, port = 2, 33500 + (os.getpid() % 2000)
+    mp.spawn(nosync_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "n0.pt"), torch.load(tmp_path / "n1.pt")
+    assert r0["outs"][0]["info"]["host_sync"] is True
+    assert r0["outs"][1]["info"]["host_sync"] is False and r0["outs"][2]["info"]["host_sync"] is False
+    for step in range(3):
+        a, b = FakeBuffers(N, C), FakeBuffers(N, C)
+        fill_rank(a, 0 + 10 * step)
+        fill_rank(b, 1 + 10 * step)
+        assert torch.equal(r0["outs"][step]["arena"], r1["outs"][step]["arena"])
+        assert torch.equal(r0["outs"][step]["arena"], a.grad_arena + b.grad_arena), f"step {step}"
+    assert r0["overflow"] and r1["overflow"], "an exchange beyond its row capacity must be flagged one step later"
+    assert r0["m_cap"] == r1["m_cap"] > 8, "every rank grows the capacity to the same value"

@@ -56,11 +56,13 @@ def main():
     accumulate(mine, dense, sparse=False, with_stats=True)
     parallel.allreduce_step(dense.grad_arena, dense.step_max_radii)
     # (c) sparse exchange of the local shard (two steps in a row: the mask / zero-row invariant must survive)
+    # the first exchange blocks once on M and sets the row capacity; the next two read M on the device
     sp = cugs.FrameBuffers(n, W, H, 16, dev)
-    infos = []
-    for _ in range(2):
+    infos, state = [], {}
+    for _ in range(3):
         accumulate(mine, sp, sparse=True, with_stats=True)
-        infos.append(parallel.sparse_allreduce_step(sp, with_stats=True))
+        # (dense_threshold 0.99: this small scene is mostly visible; the sparse path is what is under test)
+        infos.append(parallel.sparse_allreduce_step(sp, with_stats=True, state=state, dense_threshold=0.99))
     torch.cuda.synchronize()
 
     def rel(a, b):
@@ -91,6 +93,10 @@ def main():
         errs.append("grad_count differs")
     if infos[0].get("mode") != "sparse":
         errs.append(f"expected the sparse mode, got {infos[0]}")
+    if infos[0].get("host_sync") is not True or infos[2].get("host_sync") is not False:
+        errs.append(f"expected a blocking first exchange and a non-blocking third one, got {infos}")
+    if state.get("overflow"):
+        errs.append("the row capacity overflowed")
 
     # (d) replicas stay identical: Adam (grad_scale = 1/V) + MCMC noise on the exchanged gradients
     opt = cugs.FusedAdam(model)
