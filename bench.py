@@ -284,7 +284,7 @@ def run_b200(args) -> dict:
     exchange = {"mode": "single"}
     exch_state = {}
 
-    def allreduce():
+    def allreduce(mask_reduced=False):
         # the step's gradient exchange: sparse (MAX-reduce of the touch mask + ONE sum all-reduce of the
         # touched rows and the additive statistics) unless --dense-allreduce (ONE sum all-reduce of the whole
         # 61N-float arena + the MAX-reduce of max_radii)
@@ -294,7 +294,8 @@ def run_b200(args) -> dict:
             cugs.allreduce_step(buf.grad_arena, buf.step_max_radii if with_stats else None)
             exchange.update(mode="dense")
         else:
-            exchange.update(cugs.sparse_allreduce_step(buf, with_stats=with_stats, state=exch_state))
+            exchange.update(cugs.sparse_allreduce_step(buf, with_stats=with_stats, state=exch_state,
+                                                       mask_reduced=mask_reduced))
     # touch mask + sparse gradient rows (rows a view does not touch are neither read nor written) unless
     # the dense exchange is requested (it sums rows this rank's mask does not know about)
     sparse = not args.dense_allreduce
@@ -308,11 +309,21 @@ def run_b200(args) -> dict:
                              frames_in_flight=1 if args.no_overlap else 2, use_graph=not args.no_graph,
                              sparse_rows=sparse, grad_buffers=buf, dL_dcolors=dLs)
     step_no = [3000]
+    # the MAX all-reduce of the touch mask (and the scan of the union) run on a side stream under the chain rule
+    # of the step's last backward
+    overlap = cugs.MaskOverlap(dev) if (world > 1 and sparse and not args.no_mask_overlap) else None
 
     def step_resident():
-        nat.step_views(step_no[0])
+        if overlap is not None:
+            nat.step_views_until_mask(step_no[0])
+            overlap.start(buf, exch_state)
+            nat.step_views_rest(step_no[0])
+            overlap.finish()
+            allreduce(mask_reduced=True)
+        else:
+            nat.step_views(step_no[0])
+            allreduce()
         step_no[0] += 1
-        allreduce()
 
     # ---- end-to-end path: the public Python API, per view H2D target -> render -> loss -> backward -> D2H loss
     streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)] if V > 1 and not args.no_overlap else None
@@ -543,6 +554,7 @@ def run_b200(args) -> dict:
                            "per step: int32 MAX all-reduce of [touch mask | max_radii] (8 B/Gaussian) + ONE all-reduce(sum) of the "
                            "touched gradient rows and the additive statistics"),
                        "gradient_exchange": exchange, "touched_fraction": touched_frac,
+                       "mask_allreduce_overlapped": overlap is not None,
                        "min_timed_ms": MIN_TIMED_MS,
                        "l2": "no flush needed: per-step inputs (708 MB of Gaussian parameters at 3M) exceed the 126 MB L2"},
             "clocks": clocks,
@@ -588,13 +600,21 @@ def run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world
     lib, h = _lib.load_library(), _lib.handle(local)
     step_no = [3000]  # SH degree 3 active (lr_schedule.hpp:70-72)
     exch_state = {}
+    overlap = cugs.MaskOverlap(dev) if (world > 1 and not args.no_mask_overlap) else None
 
     def step():
         if world == 1:
             trainer.train_step(step_no[0])
         else:
-            trainer.step_views(step_no[0])
-            cugs.sparse_allreduce_step(trainer.buffers, with_stats=True, state=exch_state)
+            if overlap is not None:
+                trainer.step_views_until_mask(step_no[0])
+                overlap.start(trainer.buffers, exch_state)
+                trainer.step_views_rest(step_no[0])
+                overlap.finish()
+            else:
+                trainer.step_views(step_no[0])
+            cugs.sparse_allreduce_step(trainer.buffers, with_stats=True, state=exch_state,
+                                       mask_reduced=overlap is not None)
             b = trainer.buffers
             cugs.fold_step_stats(b.step_grad_accum, b.step_grad_count, b.step_max_radii, trainer.stats.grad_accum,
                                  trainer.stats.grad_count, trainer.stats.max_radii_2d)
@@ -684,7 +704,11 @@ def cpu_baseline(scene, workload: str, views: int = 1) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
-def run_reference(args) -> dict:
+def run_reference(args, module: str = "cugs_ref") -> dict:
+    """module = "cugs_ref": the UNMODIFIED reference compiled for sm_100 (the reference arm);
+    module = "cugs_dropin" (--impl dropin): the SAME harness and the same calls -- cugs::render / render_backward /
+    combined_loss with the reference's own C++ signatures -- linked against wrapper/cugs_b200_dropin.cpp, i.e.
+    this library behind the reference's API exactly as the reference's C++ training loop would use it."""
     rank, world, local = dist_env()
     if rank != 0:
         return None
@@ -694,7 +718,8 @@ def run_reference(args) -> dict:
     import cuda_gaussian_splatting_b200 as cugs  # synth() only: the scene generator, no kernels
     n, W, H, seed, desc = WORKLOADS[args.workload]
     scene = cugs.synth(n, W, H, seed=seed)
-    base = {"impl": "reference", "metric": METRIC, "unit": "views/s", "n_gpus": world, "steps": args.steps,
+    impl = "reference" if module == "cugs_ref" else "dropin"
+    base = {"impl": impl, "metric": METRIC, "unit": "views/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "views_per_gpu_per_step": args.views_per_gpu}}
@@ -702,10 +727,14 @@ def run_reference(args) -> dict:
     why = ""
     try:
         sys.path.insert(0, str(ROOT / "oracle" / "_ref"))
-        import cugs_ref as ref  # the unmodified reference, compiled from /root/reference for sm_100
+        import importlib
+        ref = importlib.import_module(module)  # cugs_ref: the unmodified reference, compiled from /root/reference for sm_100
         assert torch.cuda.is_available()
     except Exception as e:  # noqa: BLE001
         ref, why = None, f"{type(e).__name__}: {e}"
+    if ref is None and impl == "dropin":
+        base["unavailable"] = f"oracle/_ref/cugs_dropin*.so not built ({why})"
+        return base
     if ref is None:
         cb = cpu_baseline(scene, args.workload, views=max(1, min(args.steps, 2)))
         cb["sample"] += f"; compiled reference unavailable ({why})"
@@ -754,22 +783,27 @@ def run_reference(args) -> dict:
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    steps = calibrated_steps(args.steps, timed(step_resident, 3) / 3)   # >= 1 s timed region
     sampler.mark_begin()
-    ms = timed(step_resident, args.steps)
+    ms = timed(step_resident, steps)
     sampler.mark_end()
     clocks = sampler.stop()
     for _ in range(2):
         step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
-    value = args.steps * V / (ms * 1e-3)
+    e2e_steps = calibrated_steps(args.steps, timed(step_e2e, 3) / 3)
+    e2e_ms = timed(step_e2e, e2e_steps)
+    value = steps * V / (ms * 1e-3)
+    base["steps"], base["steps_requested"] = steps, args.steps
     base.update({
-        "value": round(value, 3), "ms_per_step": round(ms / args.steps, 4), "ms_per_view": round(ms / args.steps / V, 4),
+        "value": round(value, 3), "ms_per_step": round(ms / steps, 4), "ms_per_view": round(ms / steps / V, 4),
         "clocks": clocks,
         "cpu_baseline": {"value": round(value, 3), "unit": "views/s", "cores": 0, "kind": "reference",
-                         "sample": "the unmodified reference's own CUDA render()+render_backward() (oracle/_ref, built "
-                                   "for sm_100), full workload, run on the GPU: the reference has no CPU rasterizer"},
-        "e2e": {"value": round(args.steps * V / (e2e_ms * 1e-3), 3), "unit": "views/s",
-                "ms_per_view": round(e2e_ms / args.steps / V, 4),
+                         "sample": ("the unmodified reference's own CUDA render()+render_backward() (oracle/_ref, built "
+                                    "for sm_100), full workload, run on the GPU: the reference has no CPU rasterizer")
+                         if impl == "reference" else
+                         "this library behind the reference's C++ API (wrapper/cugs_b200_dropin.cpp), same harness calls"},
+        "e2e": {"value": round(e2e_steps * V / (e2e_ms * 1e-3), 3), "unit": "views/s",
+                "ms_per_view": round(e2e_ms / e2e_steps / V, 4), "steps": e2e_steps,
                 "h2d_bytes_per_step": V * H * W * 3 * 4, "d2h_bytes_per_step": V * 4,
                 "what": "H2D target (pinned) -> ref render -> ref combined_loss + autograd -> ref render_backward -> loss.item()"},
         "P_pairs": int(out[9].numel()),
@@ -782,13 +816,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "dropin"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--views-per-gpu", type=int, default=2,
                     help="views rendered fwd+bwd per GPU per step (2 = BASELINE config[3]: 16 views/step on 8 GPUs)")
     ap.add_argument("--views-total", type=int, default=0,
                     help="STRONG scaling: a fixed number of views per step split over the GPUs (16 = BASELINE config[3])")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA graph replay")
+    ap.add_argument("--no-mask-overlap", action="store_true",
+                    help="N > 1: run the MAX all-reduce of the touch mask after the backward instead of under it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense-allreduce", action="store_true",
                     help="N > 1: all-reduce the whole gradient arena instead of only the touched rows")
@@ -796,7 +832,12 @@ def main():
     ap.add_argument("--mode", default="fwd_bwd", choices=["fwd_bwd", "train_step"],
                     help="fwd_bwd = the headline metric; train_step = BASELINE config[2] (full step incl. loss, Adam, stats)")
     args = ap.parse_args()
-    res = run_reference(args) if args.impl == "reference" else run_b200(args)
+    if args.impl == "reference":
+        res = run_reference(args)
+    elif args.impl == "dropin":
+        res = run_reference(args, module="cugs_dropin")
+    else:
+        res = run_b200(args)
     if res is not None:
         print(json.dumps(res), flush=True)
 

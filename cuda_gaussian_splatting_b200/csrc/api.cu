@@ -49,7 +49,7 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
                                float* dL_dsh_coeffs, float* grad_accum, float* grad_count,
                                float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out,
                                bool accumulate, int32_t* touch_mask, bool sparse_rows, int32_t* list,
-                               int32_t* list_count);
+                               int32_t* list_count, int phase);
 extern "C" int cugs_b200_sort_num_passes(int depth_bits, int tile_bits);
 extern "C" int cugs_b200_sort_pairs_pingpong(cugs_handle_t* h, void* stream, int64_t p, int depth_bits,
                                              int tile_bits, uint64_t* keys_a, int32_t* vals_a,
@@ -487,21 +487,26 @@ extern "C" int cugs_b200_render_backward(
                          workspace_bytes, cugs_b200_render_workspace_bytes(n, 0));
     cudaStream_t s = (cudaStream_t)stream;
     const FrameWorkspace w = carve(workspace, n, 0);
+    const bool sparse = (flags & CUGS_BWD_SPARSE_ROWS) != 0 && touch_mask != nullptr;
+    const bool stop = (flags & CUGS_BWD_STOP_AFTER_MASK) != 0, resume = (flags & CUGS_BWD_RESUME_AFTER_MASK) != 0;
+    CUGS_REQUIRE(h, !(stop || resume) || sparse, "CUGS_BWD_STOP/RESUME_AFTER_MASK need CUGS_BWD_SPARSE_ROWS");
+    CUGS_REQUIRE(h, !(stop && resume), "STOP_AFTER_MASK and RESUME_AFTER_MASK are exclusive");
     // stage 1 (rasterizer.cpp:146-158): pixel gradients -> packed per-Gaussian 2-D gradients
     mark(h, 8, s);
-    if (int e = cugs_blend_bwd_accumulate(h, s, n, v, tile_ranges, gaussian_idx, means_2d, cov_2d_inv, rgb,
-                                          opacities_act, w.packed, dL_dcolor, final_T, n_contrib, w.grad_acc))
-        return e;
+    if (!resume)
+        if (int e = cugs_blend_bwd_accumulate(h, s, n, v, tile_ranges, gaussian_idx, means_2d, cov_2d_inv, rgb,
+                                              opacities_act, w.packed, dL_dcolor, final_T, n_contrib, w.grad_acc))
+            return e;
     mark(h, 9, s);
     // stage 2 (rasterizer.cpp:163-176): 2-D gradients -> parameter gradients (+ SH backward, + stats)
-    const bool sparse = (flags & CUGS_BWD_SPARSE_ROWS) != 0 && touch_mask != nullptr;
     if (int e = cugs_preprocess_bwd_launch(h, s, n, v, positions, rotations, scales, opacities, sh_coeffs,
                                            radii, rgb, nullptr, nullptr, nullptr, nullptr, dL_dpositions,
                                            dL_drotations, dL_dscales, dL_dopacities, dL_dsh_coeffs, grad_accum,
                                            grad_count, max_radii, w.grad_acc, dL_dmeans_2d,
                                            (flags & CUGS_BWD_ACCUMULATE) != 0, touch_mask, sparse,
                                            sparse ? w.bwd_list : nullptr,
-                                           sparse ? reinterpret_cast<int32_t*>(w.total_dev + 1) : nullptr))
+                                           sparse ? reinterpret_cast<int32_t*>(w.total_dev + 1) : nullptr,
+                                           stop ? 1 : (resume ? 2 : 0)))
         return e;
     mark(h, 10, s);
     return CUGS_OK;

@@ -42,7 +42,29 @@ constexpr int kBlendThreads = 64;
 #define CUGS_BWD_MINBLOCKS 12
 #endif
 constexpr int kPix = 4;      // pixels per thread (one row segment)
+// Staging granularity. Default: the CTA's two warps share one ring of 128-Gaussian batches (one barrier per batch).
+// -DCUGS_BLEND_WP ("warp private"): every warp stages its OWN ring of 64-Gaussian batches and walks the tile's
+// list on its own -- no block barrier anywhere, a warp whose 16x8 patch is finished leaves without waiting for its
+// sibling -- at the price of staging every record twice (L2 -> shared, the 48-byte records are L2 resident).
+#ifdef CUGS_BLEND_WP
+constexpr int kBatch = 64;
+#define CUGS_ST_T (threadIdx.x & 31)          /* staging slot of the thread inside the batch */
+#define CUGS_ST_N 32                          /* threads that stage one batch */
+#define CUGS_SG(buf) s_g[threadIdx.x >> 5][buf]
+#define CUGS_SID(buf) s_idx[threadIdx.x >> 5][buf]
+#define CUGS_BATCH_SYNC() __syncwarp()
+#define CUGS_BATCH_DONE(pred) __all_sync(kFull, (pred))
+#define CUGS_RING_DIMS [2][2][kBatch]
+#else
 constexpr int kBatch = 128;  // Gaussians per staged batch (two per thread)
+#define CUGS_ST_T threadIdx.x
+#define CUGS_ST_N kBlendThreads
+#define CUGS_SG(buf) s_g[buf]
+#define CUGS_SID(buf) s_idx[buf]
+#define CUGS_BATCH_SYNC() __syncthreads()
+#define CUGS_BATCH_DONE(pred) __syncthreads_and(pred)
+#define CUGS_RING_DIMS [2][kBatch]
+#endif
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kTMin = 1.0f / 255.0f;  // forward.cuh:25-31 kTransmittanceThreshold
 
@@ -148,7 +170,7 @@ __device__ __forceinline__ int build_warp_list(const void* sg_void, int bc, floa
     const float x1 = x0 + 15.0f, y1 = y0 + 7.0f;  // pixel centres of the patch corners
     int cnt = 0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kBatch / 32; ++u) {
         const int jj = u * 32 + lane;
         bool keep = false;
         if (jj < bc) {
@@ -223,7 +245,7 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             const float* __restrict__ conic, const float* __restrict__ rgb,
             const float* __restrict__ opa, float* __restrict__ out_color,
             float* __restrict__ out_T, int* __restrict__ out_n) {
-    __shared__ StagedGaussian s_g[2][kBatch];
+    __shared__ StagedGaussian s_g CUGS_RING_DIMS;
     __shared__ unsigned char s_list[2][kBatch];
 #ifdef CUGS_BLEND_TMA
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -291,8 +313,8 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
         CUGS_EXPECT(0, min(kBatch, count));
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const int li = range.x + threadIdx.x + u * kBlendThreads;
-            if (li < range.y) CUGS_STAGE(&s_g[0][threadIdx.x + u * kBlendThreads], gaussian_idx[li], 0);
+            const int li = range.x + CUGS_ST_T + u * CUGS_ST_N;
+            if (li < range.y) CUGS_STAGE(&CUGS_SG(0)[CUGS_ST_T + u * CUGS_ST_N], gaussian_idx[li], 0);
             const int li1 = li + kBatch;
             if (li1 < range.y) next_idx[u] = gaussian_idx[li1];
         }
@@ -306,16 +328,16 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             CUGS_EXPECT((b + 1) & 1, min(kBatch, count - (b + 1) * kBatch));
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                if (next_idx[u] >= 0) CUGS_STAGE(&s_g[(b + 1) & 1][threadIdx.x + u * kBlendThreads], next_idx[u], (b + 1) & 1);
-                const int li2 = range.x + (b + 2) * kBatch + threadIdx.x + u * kBlendThreads;
+                if (next_idx[u] >= 0) CUGS_STAGE(&CUGS_SG((b + 1) & 1)[CUGS_ST_T + u * CUGS_ST_N], next_idx[u], (b + 1) & 1);
+                const int li2 = range.x + (b + 2) * kBatch + CUGS_ST_T + u * CUGS_ST_N;
                 next_idx[u] = (li2 < range.y) ? gaussian_idx[li2] : -1;
             }
             cp_async_commit();
         }
         CUGS_WAIT_BATCH(b & 1, (b >> 1) & 1, b + 1 < nb);
-        __syncthreads();
+        CUGS_BATCH_SYNC();
 
-        const StagedGaussian* sg = s_g[b & 1];
+        const StagedGaussian* sg = CUGS_SG(b & 1);
         const int bc = min(kBatch, count - b * kBatch);
         const unsigned char* list = s_list[warp];
         const int cnt = build_warp_list(sg, bc, patch_x0, patch_y0, s_list[warp]);
@@ -362,7 +384,7 @@ k_blend_fwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
                 }
             }
         }
-        if (__syncthreads_and(CUGS_ALL_DONE)) break;
+        if (CUGS_BATCH_DONE(CUGS_ALL_DONE)) break;
     }
     cp_async_wait<0>();
 #undef CUGS_ALL_DONE
@@ -428,8 +450,8 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             const float* __restrict__ opa, const float* __restrict__ dL_dcolor,
             const float* __restrict__ final_T, const int* __restrict__ n_contrib,
             float* __restrict__ grad_acc /* [N,12] */) {
-    __shared__ StagedGaussian s_g[2][kBatch];
-    __shared__ int s_idx[2][kBatch];
+    __shared__ StagedGaussian s_g CUGS_RING_DIMS;
+    __shared__ int s_idx CUGS_RING_DIMS;
     __shared__ unsigned char s_list[2][kBatch];
 #ifdef CUGS_BLEND_TMA
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -483,12 +505,12 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
         CUGS_EXPECT((nb - 1) & 1, count - (nb - 1) * kBatch);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const int t = threadIdx.x + u * kBlendThreads;
+            const int t = CUGS_ST_T + u * CUGS_ST_N;
             const int li = range.x + (nb - 1) * kBatch + t;
             if (li < range.y) {
                 const int g = gaussian_idx[li];
-                s_idx[(nb - 1) & 1][t] = g;
-                CUGS_STAGE(&s_g[(nb - 1) & 1][t], g, (nb - 1) & 1);
+                CUGS_SID((nb - 1) & 1)[t] = g;
+                CUGS_STAGE(&CUGS_SG((nb - 1) & 1)[t], g, (nb - 1) & 1);
             }
             if (nb > 1) next_idx[u] = gaussian_idx[li - kBatch];  // batch nb-2 is always full
         }
@@ -500,18 +522,18 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             CUGS_EXPECT((b - 1) & 1, kBatch);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const int t = threadIdx.x + u * kBlendThreads;
-                s_idx[(b - 1) & 1][t] = next_idx[u];
-                CUGS_STAGE(&s_g[(b - 1) & 1][t], next_idx[u], (b - 1) & 1);
+                const int t = CUGS_ST_T + u * CUGS_ST_N;
+                CUGS_SID((b - 1) & 1)[t] = next_idx[u];
+                CUGS_STAGE(&CUGS_SG((b - 1) & 1)[t], next_idx[u], (b - 1) & 1);
                 if (b > 1) next_idx[u] = gaussian_idx[range.x + (b - 2) * kBatch + t];
             }
             cp_async_commit();
         }
         CUGS_WAIT_BATCH(b & 1, ((nb - 1 - b) >> 1) & 1, b > 0);
-        __syncthreads();
+        CUGS_BATCH_SYNC();
 
-        const StagedGaussian* sg = s_g[b & 1];
-        const int* sid = s_idx[b & 1];
+        const StagedGaussian* sg = CUGS_SG(b & 1);
+        const int* sid = CUGS_SID(b & 1);
         const int bc = min(kBatch, count - b * kBatch);
         const unsigned char* list = s_list[warp];
         const int cnt = build_warp_list(sg, bc, patch_x0, patch_y0, s_list[warp]);
@@ -596,7 +618,7 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             warp_reduce9(v, lane, r, r8);
             if (red_slot >= 0) atomicAdd(grad_acc + (int64_t)sid[j] * 12 + red_slot, (red_slot == 8) ? r8 : r);
         }
-        if (__syncthreads_and(CUGS_ALL_DONE)) break;
+        if (CUGS_BATCH_DONE(CUGS_ALL_DONE)) break;
     }
     cp_async_wait<0>();
 #undef CUGS_ALL_DONE

@@ -218,7 +218,7 @@ k_densify_move(int64_t n, int64_t n_out, const uint8_t* __restrict__ flags, cons
                         const float zc = (c == 0) ? z[0] : (c == 1 ? z[1] : z[2]);
                         const float child_pos = add_rn(val, mul_rn(zc, e_new));
                         if (child == 0) v1 = child_pos; else v2 = child_pos;
-                        if (split_normals) split_normals[((d1 - K - Cn) + child * S) * 3 + c] = zc;
+                        if (split_normals && d2 < n_out) split_normals[((d1 - K - Cn) + child * S) * 3 + c] = zc;
                     }
                 }
                 if (d2 < n_out) {
@@ -490,6 +490,18 @@ extern "C" int cugs_b200_densify_apply(cugs_handle_t* h, void* stream, int64_t n
     k_densify_move<<<(unsigned)nb, kRowsPerBlock, 0, s>>>(n, n_out, flags, block_counts, nb, totals, a, log_split,
                                                           (unsigned)seed, (unsigned)(seed >> 32), split_normals_out);
     CUGS_LAUNCH_CHECK(h, "k_densify_move");
+    // n_out is the caller's claim (computed from counts it may have edited together with the flags): verify it
+    // against the totals the scan just derived from the flags themselves. Densification runs on a 100-step
+    // schedule and the classification before it blocks anyway, so one more stream synchronisation is free.
+    unsigned long long tot[3] = {0, 0, 0};
+    CUGS_CUDA_TRY(h, cudaMemcpyAsync(tot, totals, sizeof(tot), cudaMemcpyDeviceToHost, s));
+    CUGS_CUDA_TRY(h, cudaStreamSynchronize(s));
+    const long long expect = (long long)tot[0] + (long long)tot[1] + 2 * (long long)tot[2];
+    if (expect != (long long)n_out)
+        return set_error(h, CUGS_ERR_INVALID_ARG,
+                         "n_out = %lld does not match the flags: kept %llu + clones %llu + 2 x splits %llu = %lld "
+                         "(the destination was only written up to min(n_out, that))",
+                         (long long)n_out, tot[0], tot[1], tot[2], expect);
     return CUGS_OK;
 }
 

@@ -29,7 +29,10 @@ k_build_touch_index(int64_t n, const int* __restrict__ touch, const int* __restr
 
 // One thread per float of the compact buffer (fully coalesced on the compact side, w-float contiguous
 // runs on the dense side: 192-byte runs for the SH group, which is 81 % of the bytes).
-// blockIdx.y = parameter group.
+// blockIdx.y = parameter group. Two other work splits were measured in round 2 (2 x B200, 531 k rows = 125 MB
+// each way, profiles/r02/NOTES.md) and were SLOWER than this one (0.105 ms): one warp per row with the index
+// broadcast (0.17 ms: one dependent load chain per warp) and one thread per 16-byte chunk of a row with the
+// groups interleaved inside a warp (0.13 ms: mixed float4 / scalar accesses in one warp).
 __host__ __device__ __forceinline__ int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
 
 // m_dev != NULL: `m` is the row CAPACITY the compact layout was sized for (known to the host from an earlier
@@ -103,18 +106,23 @@ static int move_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs, 
     CUGS_REQUIRE(h, n >= 0 && m >= 0 && m <= n, "bad n / m");
     CUGS_REQUIRE(h, num_coeffs >= 1 && num_coeffs <= 64, "bad num_coeffs");
     if (n == 0 || m == 0) return CUGS_OK;
-    CUGS_REQUIRE(h, touch && offsets && grads && compact && idx, "null pointer");
+    CUGS_REQUIRE(h, grads && compact && idx, "null pointer");
+    CUGS_REQUIRE(h, (touch != nullptr) == (offsets != nullptr), "touch and offsets go together");
+    CUGS_REQUIRE(h, touch != nullptr || !gather, "gather needs the touch mask and its scan");
     GradGroups G;
     for (int k = 0; k < 5; ++k) {
         CUGS_REQUIRE(h, grads[k] != nullptr, "null gradient group");
         G.g[k] = grads[k];
     }
     cudaStream_t s = (cudaStream_t)stream;
-    if (m_dev)
-        k_build_touch_index_cap<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, touch, offsets, m, m_dev, idx, status_dev);
-    else
-        k_build_touch_index<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, touch, offsets, idx);
-    CUGS_LAUNCH_CHECK(h, "k_build_touch_index");
+    if (touch != nullptr) {  // (a scatter right after the gather of the same exchange passes touch = NULL: idx is still valid)
+        if (m_dev)
+            k_build_touch_index_cap<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, touch, offsets, m, m_dev, idx,
+                                                                                status_dev);
+        else
+            k_build_touch_index<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, touch, offsets, idx);
+        CUGS_LAUNCH_CHECK(h, "k_build_touch_index");
+    }
     int64_t bx = (m * 3 * num_coeffs + 255) / 256;
     const int64_t cap = (int64_t)h->sm_count * 16;
     if (bx > cap) bx = cap;

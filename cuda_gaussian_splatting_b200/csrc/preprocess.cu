@@ -592,47 +592,69 @@ k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
 // the chain rule (a full re-projection, projection_backward.cu:26-247) and the 236-byte gradient row only
 // for the listed Gaussians, with full warps, instead of 32-lane warps in which ~6 lanes have work.
 // ================================================================================================
-__global__ void __launch_bounds__(256)
+constexpr int kClassifyThreads = 512;
+constexpr int kClassifyChunk = 6144;  // Gaussians per block iteration = capacity of the block's shared index list
+
+// A persistent grid (a few blocks per SM). Every block walks chunks of kClassifyChunk consecutive Gaussians,
+// collects the touched ones in a SHARED list (warp-aggregated shared atomics) and reserves their place in the
+// global list with ONE global atomic per chunk -- one atomic per warp on a single address (94 k of them at 3 M
+// Gaussians) serialised in L2 and made the first version of this pass take 121 us instead of ~40.
+__global__ void __launch_bounds__(kClassifyThreads)
 k_bwd_classify(int64_t n, int num_coeffs, const float4* __restrict__ gacc, const int* __restrict__ radii,
                int* __restrict__ touch_mask, bool accumulate, float* __restrict__ dL_dmeans_2d_out,
                float* __restrict__ grad_accum, float* __restrict__ grad_count, float* __restrict__ max_radii,
                float* __restrict__ dL_dpos, float* __restrict__ dL_drot, float* __restrict__ dL_dscl,
                float* __restrict__ dL_dopa, float* __restrict__ dL_dsh, int* __restrict__ list,
                int* __restrict__ list_count) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_list[kClassifyChunk];
+    __shared__ int s_count, s_base;
     const int lane = threadIdx.x & 31;
-    bool t = false;
-    if (i < n) {
-        const float4 a = gacc[i * 3], b = gacc[i * 3 + 1], c = gacc[i * 3 + 2];
-        t = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) | (b.z != 0.f) |
-            (b.w != 0.f) | (c.x != 0.f);
-        reinterpret_cast<float2*>(dL_dmeans_2d_out)[i] = make_float2(b.x, b.y);
-        const int old = touch_mask[i];
-        touch_mask[i] = accumulate ? (old | (int)t) : (int)t;
-        if (grad_accum != nullptr) {
-            const int radius = radii[i];
-            if (radius > 0) {
-                grad_accum[i] += sqrtf(b.x * b.x + b.y * b.y);
-                grad_count[i] += 1.0f;
+    for (int64_t c0 = (int64_t)blockIdx.x * kClassifyChunk; c0 < n; c0 += (int64_t)gridDim.x * kClassifyChunk) {
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+        const int64_t c1 = min(n, c0 + kClassifyChunk);
+        for (int64_t i0 = c0; i0 < c1; i0 += kClassifyThreads) {  // block-uniform trip count
+            const int64_t i = i0 + threadIdx.x;
+            bool t = false;
+            if (i < c1) {
+                const float4 a = __ldcs(gacc + i * 3), b = __ldcs(gacc + i * 3 + 1), c = __ldcs(gacc + i * 3 + 2);
+                t = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) |
+                    (b.z != 0.f) | (b.w != 0.f) | (c.x != 0.f);
+                reinterpret_cast<float2*>(dL_dmeans_2d_out)[i] = make_float2(b.x, b.y);
+                const int old = touch_mask[i];
+                touch_mask[i] = accumulate ? (old | (int)t) : (int)t;
+                if (grad_accum != nullptr) {
+                    const int radius = radii[i];
+                    if (radius > 0) {
+                        grad_accum[i] += sqrtf(b.x * b.x + b.y * b.y);
+                        grad_count[i] += 1.0f;
+                    }
+                    max_radii[i] = fmaxf(max_radii[i], (float)radius);
+                }
+                if (!accumulate && !t && old != 0) {  // stale row of an earlier step: back to zero
+                    dL_dpos[i * 3 + 0] = 0.f; dL_dpos[i * 3 + 1] = 0.f; dL_dpos[i * 3 + 2] = 0.f;
+                    reinterpret_cast<float4*>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    dL_dscl[i * 3 + 0] = 0.f; dL_dscl[i * 3 + 1] = 0.f; dL_dscl[i * 3 + 2] = 0.f;
+                    dL_dopa[i] = 0.f;
+                    float* o = dL_dsh + i * 3 * num_coeffs;
+                    for (int k = 0; k < 3 * num_coeffs; ++k) o[k] = 0.f;
+                }
             }
-            max_radii[i] = fmaxf(max_radii[i], (float)radius);
+            const unsigned m = __ballot_sync(kFull, t);
+            if (m != 0u) {
+                int base = 0;
+                if (lane == __ffs(m) - 1) base = atomicAdd(&s_count, __popc(m));
+                base = __shfl_sync(kFull, base, __ffs(m) - 1);
+                if (t) s_list[base + __popc(m & ((1u << lane) - 1))] = (int)i;
+            }
         }
-        if (!accumulate && !t && old != 0) {  // stale row of an earlier step: back to zero
-            dL_dpos[i * 3 + 0] = 0.f; dL_dpos[i * 3 + 1] = 0.f; dL_dpos[i * 3 + 2] = 0.f;
-            reinterpret_cast<float4*>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            dL_dscl[i * 3 + 0] = 0.f; dL_dscl[i * 3 + 1] = 0.f; dL_dscl[i * 3 + 2] = 0.f;
-            dL_dopa[i] = 0.f;
-            float* o = dL_dsh + i * 3 * num_coeffs;
-            for (int k = 0; k < 3 * num_coeffs; ++k) o[k] = 0.f;
-        }
-    }
-    // warp-aggregated append (order inside the list is irrelevant: every Gaussian is independent)
-    const unsigned m = __ballot_sync(kFull, t);
-    if (m != 0u) {
-        int base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(list_count, __popc(m));
-        base = __shfl_sync(kFull, base, __ffs(m) - 1);
-        if (t) list[base + __popc(m & ((1u << lane) - 1))] = (int)i;
+        __syncthreads();
+        const int cnt = s_count;
+        if (threadIdx.x == 0) s_base = cnt ? atomicAdd(list_count, cnt) : 0;
+        __syncthreads();
+        const int base = s_base;
+        for (int k = threadIdx.x; k < cnt; k += kClassifyThreads) list[base + k] = s_list[k];
+        __syncthreads();  // s_list / s_count are reused by the next chunk
     }
 }
 
@@ -756,18 +778,23 @@ int cugs_preprocess_bwd_launch(cugs_handle_t* h, cudaStream_t s, int64_t n, cons
                                float* dL_dsh_coeffs, float* grad_accum, float* grad_count,
                                float* max_radii, const float* grad_acc, float* dL_dmeans_2d_out,
                                bool accumulate, int32_t* touch_mask, bool sparse_rows, int32_t* list,
-                               int32_t* list_count) {
+                               int32_t* list_count, int phase /* 0 = all, 1 = classify only, 2 = chain only (list mode) */) {
     const ViewParams vp = make_view_params(v);
     const unsigned grid = (unsigned)((n + kPreBlock - 1) / kPreBlock);
     if (list != nullptr) {
         // two-phase sparse backward: classify all N, then the chain rule on the compact list only (the second
         // launch is sized for N; its warps beyond the device-side count leave at once)
-        CUGS_CUDA_TRY(h, cudaMemsetAsync(list_count, 0, sizeof(int32_t), s));
-        k_bwd_classify<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
-            n, v->num_coeffs, reinterpret_cast<const float4*>(grad_acc), radii, touch_mask, accumulate,
-            dL_dmeans_2d_out, grad_accum, grad_count, max_radii, dL_dpositions, dL_drotations, dL_dscales,
-            dL_dopacities, dL_dsh_coeffs, list, list_count);
-        CUGS_LAUNCH_CHECK(h, "k_bwd_classify");
+        if (phase != 2) {
+            CUGS_CUDA_TRY(h, cudaMemsetAsync(list_count, 0, sizeof(int32_t), s));
+            int64_t cb = (n + kClassifyChunk - 1) / kClassifyChunk;
+            if (cb > (int64_t)h->sm_count * 4) cb = (int64_t)h->sm_count * 4;
+            k_bwd_classify<<<(unsigned)cb, kClassifyThreads, 0, s>>>(
+                n, v->num_coeffs, reinterpret_cast<const float4*>(grad_acc), radii, touch_mask, accumulate,
+                dL_dmeans_2d_out, grad_accum, grad_count, max_radii, dL_dpositions, dL_drotations, dL_dscales,
+                dL_dopacities, dL_dsh_coeffs, list, list_count);
+            CUGS_LAUNCH_CHECK(h, "k_bwd_classify");
+        }
+        if (phase == 1) return CUGS_OK;
         touch_mask = nullptr; grad_accum = grad_count = max_radii = nullptr; dL_dmeans_2d_out = nullptr;
         sparse_rows = false;
     }
@@ -823,7 +850,7 @@ extern "C" int cugs_b200_preprocess_bwd(cugs_handle_t* h, void* stream, int64_t 
                                       opacities, sh_coeffs, radii, rgb, dL_dmeans_2d, dL_dcov_2d_inv,
                                       dL_drgb, dL_dopacity_act, dL_dpositions, dL_drotations, dL_dscales,
                                       dL_dopacities, dL_dsh_coeffs, grad_accum, grad_count, max_radii,
-                                      nullptr, nullptr, false, nullptr, false, nullptr, nullptr);
+                                      nullptr, nullptr, false, nullptr, false, nullptr, nullptr, 0);
 }
 
 extern "C" int cugs_b200_sh_forward(cugs_handle_t* h, void* stream, int64_t n, int degree,

@@ -29,12 +29,14 @@ constexpr int kPkRadix = 256;
 constexpr int kPkThreads = 512;
 constexpr int kPkItems = 8;
 // (kPkThreads * kPkItems = 4096 elements per block)
-// Short inputs (the depth sort of the N Gaussians: 3 M elements = 733 tiles of 4096 on 444 block slots) are
-// latency bound by the length of a block's load -> rank -> look-back -> scatter chain, not by bandwidth: they
-// run with 4 items per thread (2048-element tiles, twice as many, shorter blocks).
+// Experiment (kept as a build option, off by default): short inputs -- the depth sort of the N Gaussians, 3 M
+// elements = 733 tiles of 4096 on 444 block slots -- are latency bound by a block's load -> rank -> look-back ->
+// scatter chain, so a 4-items-per-thread variant (2048-element tiles, twice as many, shorter blocks) was tried.
+// Measured on B200 (profiles/r02/NOTES.md): SLOWER, 35.1 us instead of 29 us per depth pass at 3 M (the look-back
+// chain doubles in length and the per-block fixed costs are paid twice); no difference at 100 k.
 constexpr int kPkItemsSmall = 4;
 #ifndef CUGS_PK_SMALL_LIMIT
-#define CUGS_PK_SMALL_LIMIT (8ll << 20)  // elements; 0 disables the small-tile variant
+#define CUGS_PK_SMALL_LIMIT 0  // elements up to which the small-tile variant is used; 0 = never
 #endif
 inline int pk_items_for(int64_t n) { return (n > 0 && n <= (int64_t)CUGS_PK_SMALL_LIMIT) ? kPkItemsSmall : kPkItems; }
 constexpr int kPkWarps = kPkThreads / 32;

@@ -90,12 +90,12 @@ struct cugs_trainer {
     std::vector<const float*> dLs;  // optional per view: a given dL/dcolor replaces the loss (forward+backward only)
     int total_views;
     // graph cache: one executable per phase mask (1, 2, 3), valid for (views generation, degree)
-    cudaGraphExec_t exec[4];
-    int exec_degree[4];
-    uint64_t exec_gen[4];
+    cudaGraphExec_t exec[16];
+    int exec_degree[16];
+    uint64_t exec_gen[16];
     uint64_t views_gen;
-    bool warmed[4];
-    unsigned long long graph_kernels[4];  // kernel nodes of each captured graph (for the handle's launch counter)
+    bool warmed[16];
+    unsigned long long graph_kernels[16];  // kernel nodes of each captured graph (for the handle's launch counter)
 };
 
 namespace {
@@ -186,9 +186,35 @@ int degree_for_step(int step, int max_degree) { return std::min(step / 1000, max
 
 #define CUGS_TRY_RT(h, expr) CUGS_CUDA_TRY(h, expr)
 
-int enqueue_views(cugs_trainer* t, cudaStream_t s, int degree) {
+// part 0 = all views; part 1 = everything up to and including the classification pass of the LAST view's backward
+// (touch mask, dL/dmeans_2d and statistics final); part 2 = the rest of the last view's backward. The caller
+// starts the MAX all-reduce of the mask between parts 1 and 2.
+int enqueue_views(cugs_trainer* t, cudaStream_t s, int degree, int part) {
     cugs_handle_t* h = t->h;
     const int V = (int)t->views.size();
+    if (part == 2) {
+        const bool two2 = t->frames == 2 && V > 1;
+        const int v = V - 1, slot = two2 ? (v & 1) : 0;
+        FrameBuf& f = t->f[slot];
+        cugs_view_t view = t->views[v];
+        view.active_sh_degree = degree;
+        view.num_coeffs = t->C;
+        for (int c = 0; c < 3; ++c) view.bg[c] = t->cfg.background[c];
+        view.scale_modifier = 1.0f;
+        const float* dL = t->dLs[v] ? t->dLs[v] : f.dL;
+        const bool stats = t->cfg.accumulate_stats && t->t.grad_accum;
+        const int flags = (v > 0 ? CUGS_BWD_ACCUMULATE : 0) | CUGS_BWD_SPARSE_ROWS | CUGS_BWD_RESUME_AFTER_MASK;
+        if (int e = cugs_b200_render_backward(
+                h, s, t->n, &view, t->t.params[0], t->t.params[4], t->t.params[3], t->t.params[2], t->t.params[1],
+                f.means_2d, f.cov, f.radii, f.rgb, f.opa, f.gidx, f.ranges, f.final_T, f.n_contrib, dL,
+                t->t.grads[0], t->t.grads[4], t->t.grads[3], t->t.grads[2], t->t.grads[1], t->t.dL_dmeans_2d,
+                stats ? t->t.grad_accum : nullptr, stats ? t->t.grad_count : nullptr,
+                stats ? t->t.max_radii : nullptr, t->t.touch_mask, flags, f.ws, f.ws_bytes))
+            return e;
+        k_end_views<<<1, 1, 0, s>>>(t->res_dev, t->dyn_dev);
+        CUGS_LAUNCH_CHECK(h, "k_end_views");
+        return CUGS_OK;
+    }
     k_begin_step<<<1, 1, 0, s>>>(t->res_dev);
     CUGS_LAUNCH_CHECK(h, "k_begin_step");
     const bool two = t->frames == 2 && V > 1;
@@ -221,7 +247,8 @@ int enqueue_views(cugs_trainer* t, cudaStream_t s, int degree) {
         // the gradient arena is shared: view v adds to what view v-1 wrote
         if (have_prev && two) CUGS_TRY_RT(h, cudaStreamWaitEvent(sv, t->ev_bwd[prev_slot], 0));
         const bool stats = t->cfg.accumulate_stats && t->t.grad_accum;
-        const int flags = (v > 0 ? CUGS_BWD_ACCUMULATE : 0) | (t->t.touch_mask ? CUGS_BWD_SPARSE_ROWS : 0);
+        const int flags = (v > 0 ? CUGS_BWD_ACCUMULATE : 0) | (t->t.touch_mask ? CUGS_BWD_SPARSE_ROWS : 0) |
+                          ((part == 1 && v == V - 1) ? CUGS_BWD_STOP_AFTER_MASK : 0);
         if (int e = cugs_b200_render_backward(
                 h, sv, t->n, &view, t->t.params[0], t->t.params[4], t->t.params[3], t->t.params[2], t->t.params[1],
                 f.means_2d, f.cov, f.radii, f.rgb, f.opa, f.gidx, f.ranges, f.final_T, f.n_contrib, dL,
@@ -238,8 +265,8 @@ int enqueue_views(cugs_trainer* t, cudaStream_t s, int degree) {
     if (two) {  // join: everything the auxiliary stream did is ordered before what follows on s
         CUGS_TRY_RT(h, cudaEventRecord(t->ev_join, t->aux));
         CUGS_TRY_RT(h, cudaStreamWaitEvent(s, t->ev_join, 0));
-        if (prev_slot == 1) {}  // (the last backward ran on aux: covered by ev_join)
     }
+    if (part == 1) return CUGS_OK;  // k_end_views closes part 2
     k_end_views<<<1, 1, 0, s>>>(t->res_dev, t->dyn_dev);
     CUGS_LAUNCH_CHECK(h, "k_end_views");
     return CUGS_OK;
@@ -268,7 +295,11 @@ int enqueue_update(cugs_trainer* t, cudaStream_t s) {
 
 int enqueue_phases(cugs_trainer* t, cudaStream_t s, int phases, int degree) {
     if (phases & 1)
-        if (int e = enqueue_views(t, s, degree)) return e;
+        if (int e = enqueue_views(t, s, degree, 0)) return e;
+    if (phases & 4)
+        if (int e = enqueue_views(t, s, degree, 1)) return e;
+    if (phases & 8)
+        if (int e = enqueue_views(t, s, degree, 2)) return e;
     if (phases & 2)
         if (int e = enqueue_update(t, s)) return e;
     // results to pinned memory; the caller reads them after any later synchronisation of `s`
@@ -324,7 +355,7 @@ extern "C" int cugs_b200_trainer_create(cugs_handle_t* h, int64_t n, int num_coe
     t->res_dev = reinterpret_cast<StepResult*>(base + off); off += a256(sizeof(StepResult));
     t->dyn_pinned = nullptr; t->res_pinned = nullptr; t->aux = nullptr; t->cap = nullptr;
     t->dyn_seq = 0; t->total_views = 0; t->views_gen = 0;
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 16; ++k) {
         t->exec[k] = nullptr; t->exec_degree[k] = -1; t->exec_gen[k] = 0; t->warmed[k] = false; t->graph_kernels[k] = 0;
     }
     for (int k = 0; k < kDynRing; ++k) { t->ring_ev[k] = nullptr; t->ring_ev_used[k] = false; }
@@ -358,7 +389,7 @@ extern "C" int cugs_b200_trainer_create(cugs_handle_t* h, int64_t n, int num_coe
 
 extern "C" void cugs_b200_trainer_destroy(cugs_trainer_t* t) {
     if (!t) return;
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 16; ++k)
         if (t->exec[k]) cudaGraphExecDestroy(t->exec[k]);
     if (t->dyn_pinned) cudaFreeHost(t->dyn_pinned);
     if (t->res_pinned) cudaFreeHost(t->res_pinned);
@@ -420,8 +451,10 @@ extern "C" int64_t cugs_b200_trainer_adam_steps(const cugs_trainer_t* t) {
 extern "C" int cugs_b200_trainer_step(cugs_trainer_t* t, void* stream, int step, int phases) {
     if (!t) return CUGS_ERR_INVALID_ARG;
     cugs_handle_t* h = t->h;
-    CUGS_REQUIRE(h, phases >= 1 && phases <= 3, "phases must be 1, 2 or 3");
-    CUGS_REQUIRE(h, !(phases & 1) || !t->views.empty(), "no views set");
+    CUGS_REQUIRE(h, phases == 1 || phases == 2 || phases == 3 || phases == 4 || phases == 8,
+                 "phases must be 1 (views), 2 (update), 3 (both), 4 (views up to the last mask) or 8 (rest of the views)");
+    CUGS_REQUIRE(h, !(phases & 13) || !t->views.empty(), "no views set");
+    CUGS_REQUIRE(h, !(phases & 12) || t->t.touch_mask != nullptr, "phases 4 / 8 need the touch mask (sparse rows)");
     cudaStream_t s = (cudaStream_t)stream;
     const int degree = degree_for_step(step, t->cfg.max_sh_degree);  // trainer.cpp:183
 
@@ -436,7 +469,9 @@ extern "C" int cugs_b200_trainer_step(cugs_trainer_t* t, void* stream, int step,
     d.step = (unsigned)step;
     d.ok = 1;  // phase 1 overwrites it on the device; an update-only call trusts the caller's exchange
     d.pad[0] = d.pad[1] = 0;
-    if (phases == 2) {
+    if (phases == 8) {
+        // nothing: the per-step scalars were uploaded by phase 4 of the same step
+    } else if (phases == 2) {
         // keep the ok flag the views phase left on the device: copy everything but `ok`
         CUGS_CUDA_TRY(h, cudaMemcpyAsync(t->dyn_dev, &d, offsetof(StepDyn, ok), cudaMemcpyHostToDevice, s));
     } else {

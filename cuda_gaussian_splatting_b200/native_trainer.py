@@ -26,7 +26,7 @@ class NativeTrainer:
     View-parallel training: construct with ``total_views_per_step`` = views of all ranks and call
     ``step_views(step)`` -> gradient exchange -> ``step_update(step)``."""
 
-    VIEWS, UPDATE, BOTH = 1, 2, 3
+    VIEWS, UPDATE, BOTH, VIEWS_UNTIL_MASK, VIEWS_REST = 1, 2, 3, 4, 8
 
     def __init__(self, model: GaussianModel, cameras: Sequence[CameraInfo], targets: Sequence[torch.Tensor],
                  config: Optional[TrainConfig] = None, total_views_per_step: Optional[int] = None,
@@ -163,6 +163,19 @@ class NativeTrainer:
             b = self.buffers
             b.step_grad_accum.zero_(); b.step_grad_count.zero_(); b.step_max_radii.zero_()
         self._step(step, self.VIEWS)
+
+    def step_views_until_mask(self, step: int) -> None:
+        """The views phase up to and including the classification pass of the last view's backward: after it the
+        touch mask, dL/dmeans_2d and the statistics are final (parallel.MaskOverlap starts the mask collective)."""
+        _check(self.sparse_rows, "step_views_until_mask needs sparse_rows=True")
+        if self.multi_rank and self.config.densify and self.config.mcmc is None:
+            b = self.buffers
+            b.step_grad_accum.zero_(); b.step_grad_count.zero_(); b.step_max_radii.zero_()
+        self._step(step, self.VIEWS_UNTIL_MASK)
+
+    def step_views_rest(self, step: int) -> None:
+        """The rest of the views phase: the chain rule of the last view (does not touch the mask / statistics)."""
+        self._step(step, self.VIEWS_REST)
 
     def step_update(self, step: int) -> None:
         self._step(step, self.UPDATE)

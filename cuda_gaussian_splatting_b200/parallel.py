@@ -49,14 +49,50 @@ def allreduce_step(arena: torch.Tensor, max_radii: Optional[torch.Tensor] = None
     return works if async_op else []
 
 
+class MaskOverlap:
+    """Hides the first collective of the sparse exchange -- the MAX all-reduce of [touch mask | max_radii] and
+    the scan of the union mask -- under the tail of the step's last backward: the mask is final after the
+    classification pass of the last view (NativeTrainer.step_views_until_mask), the chain rule of that view
+    (step_views_rest) does not touch it, so the collective runs on a side stream meanwhile.
+
+        trainer.step_views_until_mask(step); overlap.start(buffers, state)
+        trainer.step_views_rest(step);       overlap.finish()
+        sparse_allreduce_step(buffers, ..., state=state, mask_reduced=True)
+    """
+
+    def __init__(self, device, group: Optional[dist.ProcessGroup] = None):
+        self.device = torch.device(device)
+        self.group = group
+        self.stream = torch.cuda.Stream(self.device)
+        self.ready = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+
+    def start(self, buffers, state: Optional[dict] = None, ops=None) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        self.ready.record(cur)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.ready)
+            dist.all_reduce(buffers.max_buf, op=dist.ReduceOp.MAX, group=self.group)
+            if state is not None and state.get("m_cap"):
+                ops = ops or _CudaRowOps()
+                state["pre_scanned"] = ops.scan_dev(buffers)   # offsets + device-side M of the union mask
+            self.done.record(self.stream)
+
+    def finish(self) -> None:
+        torch.cuda.current_stream(self.device).wait_event(self.done)
+
+
 def sparse_allreduce_step(buffers, with_stats: bool = True, dense_threshold: float = 0.6,
-                          group: Optional[dist.ProcessGroup] = None, ops=None, state: Optional[dict] = None) -> dict:
+                          group: Optional[dist.ProcessGroup] = None, ops=None, state: Optional[dict] = None,
+                          mask_reduced: bool = False) -> dict:
     """The step's gradient exchange, exploiting that a view leaves most Gaussians' gradients exactly
     zero: (1) ONE int32 MAX all-reduce of [touch mask | max_radii bits] (8 B/Gaussian), (2) exclusive
     scan of the union mask -> M touched Gaussians, (3) the M gradient rows are gathered into a dense
     buffer, followed by the two additive statistics, (4) ONE all-reduce(sum) of (59 M + 2 N) floats
     instead of 61 N, (5) scatter back. Falls back to the dense all-reduce when M > dense_threshold * N.
     Numerically a plain sum either way.
+
+    ``mask_reduced``: the MAX all-reduce (and, with ``state``, the scan) was already done by :class:`MaskOverlap`.
 
     ``state`` (a dict the caller keeps between steps) removes the host round trip for M: the collective is
     sized on a row CAPACITY derived from the previous steps' M (identical on every rank, because M is the
@@ -73,7 +109,8 @@ def sparse_allreduce_step(buffers, with_stats: bool = True, dense_threshold: flo
     n = int(b.n)
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return {"mode": "single", "touched": None}
-    dist.all_reduce(b.max_buf, op=dist.ReduceOp.MAX, group=group)
+    if not mask_reduced:   # (MaskOverlap already reduced it under the last backward)
+        dist.all_reduce(b.max_buf, op=dist.ReduceOp.MAX, group=group)
     ops = ops or _CudaRowOps()
     num_coeffs = int(b.dL_dsh_coeffs.shape[2])
 
@@ -111,7 +148,8 @@ def sparse_allreduce_step(buffers, with_stats: bool = True, dense_threshold: flo
             state["pending"] = None
     if state is not None and state.get("m_cap") and hasattr(ops, "scan_dev"):
         m_cap = int(state["m_cap"])
-        offsets, m_dev = ops.scan_dev(b)
+        pre = state.pop("pre_scanned", None) if mask_reduced else None
+        offsets, m_dev = pre if pre is not None else ops.scan_dev(b)
         if "status_dev" not in state:
             dev = b.grad_arena.device
             state["status_dev"] = torch.zeros((2,), dtype=torch.int64, device=dev)
@@ -217,8 +255,9 @@ class _CudaRowOps:
         from .rasterizer import _lib_and_handle, _stream
         dev = b.grad_arena.device
         lib, h = _lib_and_handle(dev)
+        # touch = offsets = None: the index list built by this exchange's gather is still in b._touch_idx
         st = lib.cugs_b200_scatter_grad_rows(h, _stream(dev), int(b.n), int(b.dL_dsh_coeffs.shape[2]),
-                                             b.touch_mask.data_ptr(), offsets.data_ptr(), int(m), compact.data_ptr(),
+                                             None, None, int(m), compact.data_ptr(),
                                              self._groups(b), b._touch_idx.data_ptr(),
                                              None if m_dev is None else m_dev.data_ptr())
         _lib.check(h, st, "cugs_b200_scatter_grad_rows")

@@ -278,6 +278,12 @@ int cugs_b200_render_backward(cugs_handle_t* h, void* stream, int64_t n, const c
 int cugs_b200_last_sort_plan(const cugs_handle_t* h, int* passes, int* key_bits);
 #define CUGS_BWD_ACCUMULATE 1
 #define CUGS_BWD_SPARSE_ROWS 2
+/* With SPARSE_ROWS the call can be split in two: STOP_AFTER_MASK runs the backward blend and the classification
+ * pass -- after it touch_mask, dL_dmeans_2d and the three statistics are final -- and RESUME_AFTER_MASK (same
+ * arguments, same workspace) runs the rest (the chain rule on the touched Gaussians). View-parallel training
+ * starts the MAX all-reduce of the mask between the two, so it is hidden under the second part. */
+#define CUGS_BWD_STOP_AFTER_MASK 4
+#define CUGS_BWD_RESUME_AFTER_MASK 8
 #define CUGS_NUM_STAGES 8
 int cugs_b200_set_stage_timing(cugs_handle_t* h, int enable);
 int cugs_b200_get_stage_ms(cugs_handle_t* h, float* ms8);
@@ -342,6 +348,8 @@ int cugs_b200_accumulate_stats(cugs_handle_t* h, void* stream, int64_t n,
  *                     split_normals_out [2 * splits, 3]. src_m/src_v/dst_m/dst_v (each NULL or five
  *                     pointers): Adam moments carried over for kept rows and zeroed for new rows (the
  *                     reference rebuilds the optimizer, i.e. zeroes all of them: pass src_* = NULL for that).
+ * densify_apply blocks once at its end to compare n_out with the row counts it derived from the flags
+ * (CUGS_ERR_INVALID_ARG on a mismatch; no row beyond n_out is ever written).
  * temp: cugs_b200_densify_temp_bytes(n) bytes of device scratch, the same buffer for both calls. */
 #define CUGS_DENSIFY_KEEP 1
 #define CUGS_DENSIFY_CLONE 2
@@ -460,7 +468,8 @@ int64_t cugs_b200_trainer_adam_steps(const cugs_trainer_t* t);
  * m_dev (optional, device int64 = the total the scan wrote): no host round trip for M -- `m` is then only the
  * row CAPACITY the compact layout is sized for (e.g. 1.25 x the previous step's M), the real count is read on
  * the device, the gather zero-fills the rows in between and status_dev (optional, 2 x int64) receives
- * {M, M > capacity}; rows beyond the capacity are dropped, so an overflowed exchange must be repeated. */
+ * {M, M > capacity}; rows beyond the capacity are dropped, so an overflowed exchange must be repeated.
+ * scatter with touch = offsets = NULL reuses the index list the gather of the same exchange left in idx_scratch. */
 int64_t cugs_b200_compact_grad_floats(int64_t m, int num_coeffs);
 int cugs_b200_gather_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs,
                                const int32_t* touch, const int32_t* offsets, int64_t m,

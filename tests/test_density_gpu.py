@@ -425,3 +425,31 @@ def test_known_answers_mcmc_relocation(torch):
         st = cugs.mcmc_relocate(model, 500 + i * 100, cugs.MCMCConfig(relocate_cap=1.0), 10.0)
         assert model.num_gaussians() == 30 and model.is_valid()
         assert st.num_relocated == (10 if i == 0 else 0)  # relocated ones come back with opacity 0.01: alive
+
+
+def test_densify_apply_rejects_a_wrong_row_count(torch):
+    """cugs_b200_densify_apply checks the caller's n_out against the row counts it derives from the flags
+    (ADVICE r01): a mismatch is an error instead of a model with uninitialised or missing rows."""
+    import ctypes as C
+    from cuda_gaussian_splatting_b200 import _lib
+    lib, h = _lib.load_library(), _lib.handle(0)
+    n, Cn = 1000, 16
+    rng = np.random.default_rng(4)
+    flags = rng.choice([1, 1 | 2, 4, 0], size=n).astype(np.uint8)          # keep / keep+clone / split / prune
+    kept = int(((flags & 1) != 0).sum() - 0) - int((((flags & 4) != 0) & ((flags & 1) != 0)).sum())
+    clones, splits = int(((flags & 2) != 0).sum()), int(((flags & 4) != 0).sum())
+    want = kept + clones + 2 * splits
+    shapes = [(n, 3), (n, 3 * Cn), (n, 1), (n, 3), (n, 4)]
+    src = [torch.randn(s, device="cuda") for s in shapes]
+    fl = torch.from_numpy(flags).cuda()
+    temp = torch.empty((lib.cugs_b200_densify_temp_bytes(n),), dtype=torch.uint8, device="cuda")
+
+    def apply(n_out):
+        dst = [torch.empty((max(n_out, 1), s[1]), device="cuda") for s in shapes]
+        sp, dp = (C.c_void_p * 5)(*[t.data_ptr() for t in src]), (C.c_void_p * 5)(*[t.data_ptr() for t in dst])
+        return lib.cugs_b200_densify_apply(h, torch.cuda.current_stream().cuda_stream, n, n_out, Cn, fl.data_ptr(), sp, dp,
+                                           None, None, None, None, 7, None, temp.data_ptr(), temp.numel())
+    assert apply(want) == 0
+    for bad in (want - 3, want + 5):
+        assert apply(bad) == -1, "CUGS_ERR_INVALID_ARG expected"
+        assert b"does not match the flags" in lib.cugs_b200_last_error(h)

@@ -98,6 +98,30 @@ def main():
     if state.get("overflow"):
         errs.append("the row capacity overflowed")
 
+    # (c2) the C++ step driver's views phase, split at the last view's mask, with the mask collective hidden under the
+    # rest of that backward (parallel.MaskOverlap): same sums as the plain schedule and as the single-rank reference
+    tcfg = cugs.TrainConfig(densify=True, background=tuple(settings.background))
+    nat_bufs = cugs.FrameBuffers(n, W, H, 16, dev)
+    nat = cugs.NativeTrainer(model, [cams[v] for v in mine], [None] * len(mine), tcfg, total_views_per_step=V,
+                             grad_buffers=nat_bufs, dL_dcolors=[dLs[v] for v in mine], use_graph=True)
+    ov, st2 = parallel.MaskOverlap(dev), {}
+    for it in range(4):   # eager, capture, replay, replay
+        nat.step_views_until_mask(3000 + it)
+        ov.start(nat_bufs, st2)
+        nat.step_views_rest(3000 + it)
+        ov.finish()
+        parallel.sparse_allreduce_step(nat_bufs, with_stats=True, state=st2, dense_threshold=0.99, mask_reduced=True)
+    torch.cuda.synchronize()
+    _, ok, _, _ = nat.result()
+    if not ok or st2.get("overflow"):
+        errs.append("native trainer / overlapped exchange overflowed")
+    for nm, (off, sz) in layout.items():
+        if rel(nat_bufs.grad_arena[off:off + sz], ref_arena[off:off + sz]) > 1e-6:
+            errs.append(f"overlapped native schedule vs single-rank {nm}: {rel(nat_bufs.grad_arena[off:off + sz], ref_arena[off:off + sz]):.3e}")
+    if not torch.equal(nat_bufs.step_max_radii, ref_maxr) or not torch.equal(nat_bufs.step_grad_count, ref_buf.step_grad_count):
+        errs.append("overlapped native schedule: statistics differ")
+    nat.close()
+
     # (d) replicas stay identical: Adam (grad_scale = 1/V) + MCMC noise on the exchanged gradients
     opt = cugs.FusedAdam(model)
     opt.grad_scale = 1.0 / V
