@@ -325,56 +325,27 @@ def run_b200(args) -> dict:
             allreduce()
         step_no[0] += 1
 
-    # ---- end-to-end path: the public Python API, per view H2D target -> render -> loss -> backward -> D2H loss
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)] if V > 1 and not args.no_overlap else None
-    bufs = [buf, cugs.FrameBuffers(n, W, H, 16, dev, share_grads_with=buf)] if streams else [buf, buf]
-    for b in bufs:
-        b.ensure_capacity(max(Ps))
-
-    def run_views(per_view):
-        if streams is None:
-            for v in range(V):
-                per_view(v, bufs[0], None)
-            return
-        cur = torch.cuda.current_stream(dev)
-        start = torch.cuda.Event()
-        start.record(cur)
-        prev_bwd = None
-        for v in range(V):
-            s_ = streams[v % 2]
-            s_.wait_event(start)
-            with torch.cuda.stream(s_):
-                prev_bwd = per_view(v, bufs[v % 2], prev_bwd)
-        cur.wait_event(prev_bwd)
-
-    uploader = cugs.TargetUploader(H, W, dev)
-    uploader.prefetch(targets_host[0])
-    scal_hosts = [torch.empty((3,), dtype=torch.float32).pin_memory() for _ in range(V)]
-    stats_e2e = (buf.step_grad_accum, buf.step_grad_count, buf.step_max_radii) if with_stats else None
-
-    def view_e2e(v, b, prev_bwd):
-        # every view's target is copied host->device (pinned, side stream) INSIDE the step; the copy of
-        # the next view overlaps the rendering of the current one
-        tgt = uploader.get()
-        uploader.prefetch(targets_host[(v + 1) % V])                          # H2D of the next view's target
-        out = cugs.render(model, cams[v], settings, b, sync=False)            # no host round trip for P
-        sc, g = cugs.combined_loss_with_grad(out.color, tgt, 0.2)
-        uploader.release()
-        if prev_bwd is not None:
-            torch.cuda.current_stream(dev).wait_event(prev_bwd)
-        cugs.render_backward(g, out, model, cams[v], settings, b, stats=stats_e2e, accumulate=(v > 0),
-                             touch_mask=touch, sparse_rows=sparse)
-        scal_hosts[v].copy_(sc, non_blocking=True)                            # D2H of {loss, l1, ssim}
-        b.fetch_status()                                                      # D2H of {P, overflowed}
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
-        return ev
+    # ---- end-to-end path: the same C++ step driver through its public Python face, but with the loss in the step
+    # and HOST inputs: every view's target image is copied from pinned host memory inside the step (a copy stream,
+    # under the rendering of that view), the fused L1+SSIM loss produces dL/dcolor, and the step's {loss, l1, ssim,
+    # ok, largest P} block is copied device -> host at its end; the host then waits for it.
+    targets_dev = [torch.empty((H, W, 3), dtype=torch.float32, device=dev) for _ in range(V)]
+    nat_e2e = cugs.NativeTrainer(model, cams, targets_dev, tcfg, total_views_per_step=world * V, pair_capacity=p_cap,
+                                 frames_in_flight=1 if args.no_overlap else 2, use_graph=not args.no_graph,
+                                 sparse_rows=sparse, grad_buffers=buf)
+    nat_e2e.set_views(cams, targets_dev, None, targets_host)
 
     def step_e2e():
-        if with_stats:
-            buf.step_grad_accum.zero_(); buf.step_grad_count.zero_(); buf.step_max_radii.zero_()
-        run_views(view_e2e)
-        allreduce()
+        if overlap is not None:
+            nat_e2e.step_views_until_mask(step_no[0])
+            overlap.start(buf, exch_state)
+            nat_e2e.step_views_rest(step_no[0])
+            overlap.finish()
+            allreduce(mask_reduced=True)
+        else:
+            nat_e2e.step_views(step_no[0])
+            allreduce()
+        step_no[0] += 1
         torch.cuda.current_stream().synchronize()                             # the losses are on the host now
 
     def barrier():
@@ -469,8 +440,8 @@ def run_b200(args) -> dict:
         step_e2e()
     e2e_steps = agree_steps(calibrated_steps(args.steps, timed(step_e2e, 5) / 5))
     e2e_ms = timed(step_e2e, e2e_steps)
-    e2e_overflow = any(b.last_pairs()[1] for b in set(bufs))
-    assert not e2e_overflow, "an end-to-end frame overflowed its pair capacity"
+    e2e_scalars, e2e_ok, _, _ = nat_e2e.result()
+    assert e2e_ok, "an end-to-end frame overflowed its pair capacity"
     clocks = sampler.stop() if rank == 0 else {}
 
     views = world * V * steps
@@ -560,9 +531,11 @@ def run_b200(args) -> dict:
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 3), "unit": "views/s", "ms_per_view": round(e2e_ms / e2e_steps / V, 4),
                     "steps": e2e_steps,
-                    "h2d_bytes_per_step": V * H * W * 3 * 4, "d2h_bytes_per_step": V * (12 + 16),
-                    "what": "public Python API, per view: H2D target (pinned, side stream, overlapped with the previous view) -> "
-                            "render(sync=False) -> fused L1+SSIM loss+grad -> render_backward -> D2H {loss, l1, ssim} + {P, overflow}"},
+                    "h2d_bytes_per_step": V * H * W * 3 * 4, "d2h_bytes_per_step": 48,
+                    "loss": round(e2e_scalars[0], 6),
+                    "what": "NativeTrainer.step_views (cugs_b200_trainer_step), per view: H2D target from pinned host memory "
+                            "(copy stream, under the rendering of the same view) -> render -> fused L1+SSIM loss+grad -> "
+                            "render_backward; per step: D2H {loss, l1, ssim, ok, largest P} + host wait"},
             "gpu_launches": launches,
             "roofline": roofline,
             "work_view0": work,
@@ -579,6 +552,7 @@ def run_b200(args) -> dict:
         if world == 1 and not args.no_cpu_baseline:
             res["cpu_baseline"] = cpu_baseline(scene, args.workload)
     nat.close()
+    nat_e2e.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -121,7 +121,7 @@ SIGNATURES = {
     "cugs_b200_trainer_create": (_INT, [_P, _I64, _INT, _INT, _INT, _I64, C.POINTER(CugsTrainConfig),
                                          C.POINTER(CugsTrainTensors), _P, _SZ, C.POINTER(_P)]),
     "cugs_b200_trainer_destroy": (None, [_P]),
-    "cugs_b200_trainer_set_views": (_INT, [_P, _INT, _VP, C.POINTER(_P), C.POINTER(_P), _INT]),
+    "cugs_b200_trainer_set_views": (_INT, [_P, _INT, _VP, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _INT]),
     "cugs_b200_trainer_step": (_INT, [_P, _P, _INT, _INT]),
     "cugs_b200_trainer_result": (_INT, [_P, _P, C.POINTER(_F), C.POINTER(_I64)]),
     "cugs_b200_trainer_set_adam_steps": (_INT, [_P, _I64]),

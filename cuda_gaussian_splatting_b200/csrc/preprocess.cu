@@ -15,6 +15,10 @@
 //            to Gaussian q/12, channel (q%12)/4, coefficients 4*(q%4)..+3, so a 2-step xor-shuffle
 //            over groups of 4 lanes finishes one (Gaussian, channel) dot product and the result
 //            index is simply q/4 — no strided 192-byte-per-thread access anywhere.
+// Summation order of the SH dot product: the generic path (any C) sums k ascending like core/sh.cu:70-76; the
+// C = 16 fast path sums four 4-coefficient partials and combines them with two shuffles, so its rgb differs from
+// the reference by rounding (<= 2e-6 absolute, tests/test_gpu_parity.py) and the backward's ReLU gate `rgb > 0`
+// can flip only for colours inside that noise of the clamp (test_sh_colours_at_the_clamp_boundary_vs_reference).
 // HBM traffic is the compulsory 284 B/Gaussian forward (+48 B for the packed blend record) and
 // 336 B/Gaussian backward (the ReLU gate comes from the forward rgb, not from re-reading SH).
 #include "common.cuh"
@@ -313,8 +317,11 @@ k_preprocess_fwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
 // ================================================================================================
 // Backward
 // ================================================================================================
+#ifndef CUGS_PREBWD_MINBLOCKS
+#define CUGS_PREBWD_MINBLOCKS 4
+#endif
 template <bool kVecSH, bool kDeg3>
-__global__ void __launch_bounds__(kPreBlock)
+__global__ void __launch_bounds__(kPreBlock, CUGS_PREBWD_MINBLOCKS)
 k_preprocess_bwd(int64_t n, ViewParams vp, const float* __restrict__ positions,
                  const float* __restrict__ rotations, const float* __restrict__ scales,
                  const float* __restrict__ opacities, const float* __restrict__ sh,

@@ -83,11 +83,14 @@ struct cugs_trainer {
     bool ring_ev_used[kDynRing];
     cudaStream_t aux;  // second frame in flight
     cudaStream_t cap;  // capture origin: the caller's stream may be the legacy default stream, which cannot capture
+    cudaStream_t copy; // host -> device copies of the target images, under the rendering of the same view
+    cudaEvent_t ev_copy_fork, ev_copied[2], ev_copy_join;
     cudaEvent_t ev_fork, ev_bwd[2], ev_join;
     // the step's views
     std::vector<cugs_view_t> views;
     std::vector<const float*> targets;
     std::vector<const float*> dLs;  // optional per view: a given dL/dcolor replaces the loss (forward+backward only)
+    std::vector<const float*> targets_host;  // optional per view: pinned host image copied into targets[v] inside the step
     int total_views;
     // graph cache: one executable per phase mask (1, 2, 3), valid for (views generation, degree)
     cudaGraphExec_t exec[16];
@@ -219,6 +222,14 @@ int enqueue_views(cugs_trainer* t, cudaStream_t s, int degree, int part) {
     CUGS_LAUNCH_CHECK(h, "k_begin_step");
     const bool two = t->frames == 2 && V > 1;
     if (two) CUGS_TRY_RT(h, cudaEventRecord(t->ev_fork, s));
+    // end-to-end mode: the target image of every view comes from (pinned) host memory INSIDE the step. The copies
+    // run on their own stream in view order, each under the rendering of its own view; the loss waits for it.
+    bool any_copy = false;
+    for (int v = 0; v < V; ++v) any_copy |= t->targets_host[v] != nullptr && t->dLs[v] == nullptr;
+    if (any_copy) {
+        CUGS_TRY_RT(h, cudaEventRecord(t->ev_copy_fork, s));
+        CUGS_TRY_RT(h, cudaStreamWaitEvent(t->copy, t->ev_copy_fork, 0));
+    }
     bool have_prev = false;
     int prev_slot = 0;
     for (int v = 0; v < V; ++v) {
@@ -237,6 +248,14 @@ int enqueue_views(cugs_trainer* t, cudaStream_t s, int degree, int part) {
                                              f.n_contrib, f.ws, f.ws_bytes, f.pairs, f.pairs_bytes, f.status2))
             return e;
         const float* dL = f.dL;
+        if (t->targets_host[v] != nullptr && t->dLs[v] == nullptr) {
+            // (every such view has its own device buffer -- checked in set_views -- and the copy stream was forked
+            //  from this step's start, i.e. after the previous step's consumers)
+            CUGS_TRY_RT(h, cudaMemcpyAsync(const_cast<float*>(t->targets[v]), t->targets_host[v],
+                                           (size_t)t->W * t->H * 3 * sizeof(float), cudaMemcpyHostToDevice, t->copy));
+            CUGS_TRY_RT(h, cudaEventRecord(t->ev_copied[v & 1], t->copy));
+            CUGS_TRY_RT(h, cudaStreamWaitEvent(sv, t->ev_copied[v & 1], 0));
+        }
         if (t->dLs[v] != nullptr) {  // forward+backward only: the caller supplies dL/dcolor
             dL = t->dLs[v];
             CUGS_TRY_RT(h, cudaMemsetAsync(f.scalars3, 0, 16, sv));
@@ -265,6 +284,10 @@ int enqueue_views(cugs_trainer* t, cudaStream_t s, int degree, int part) {
     if (two) {  // join: everything the auxiliary stream did is ordered before what follows on s
         CUGS_TRY_RT(h, cudaEventRecord(t->ev_join, t->aux));
         CUGS_TRY_RT(h, cudaStreamWaitEvent(s, t->ev_join, 0));
+    }
+    if (any_copy) {  // join the copy stream (needed for graph capture; all its work was waited on already)
+        CUGS_TRY_RT(h, cudaEventRecord(t->ev_copy_join, t->copy));
+        CUGS_TRY_RT(h, cudaStreamWaitEvent(s, t->ev_copy_join, 0));
     }
     if (part == 1) return CUGS_OK;  // k_end_views closes part 2
     k_end_views<<<1, 1, 0, s>>>(t->res_dev, t->dyn_dev);
@@ -353,7 +376,8 @@ extern "C" int cugs_b200_trainer_create(cugs_handle_t* h, int64_t n, int num_coe
     for (int k = 0; k < t->frames; ++k) off += frame_bytes(n, width, height, p_capacity, &t->f[k], base + off);
     t->dyn_dev = reinterpret_cast<StepDyn*>(base + off); off += a256(sizeof(StepDyn));
     t->res_dev = reinterpret_cast<StepResult*>(base + off); off += a256(sizeof(StepResult));
-    t->dyn_pinned = nullptr; t->res_pinned = nullptr; t->aux = nullptr; t->cap = nullptr;
+    t->dyn_pinned = nullptr; t->res_pinned = nullptr; t->aux = nullptr; t->cap = nullptr; t->copy = nullptr;
+    t->ev_copy_fork = t->ev_copied[0] = t->ev_copied[1] = t->ev_copy_join = nullptr;
     t->dyn_seq = 0; t->total_views = 0; t->views_gen = 0;
     for (int k = 0; k < 16; ++k) {
         t->exec[k] = nullptr; t->exec_degree[k] = -1; t->exec_gen[k] = 0; t->warmed[k] = false; t->graph_kernels[k] = 0;
@@ -366,6 +390,11 @@ extern "C" int cugs_b200_trainer_create(cugs_handle_t* h, int64_t n, int num_coe
                                             cudaHostAllocPortable);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->aux, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->cap, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_copy_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_copied[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_copied[1], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_copy_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_bwd[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_bwd[1], cudaEventDisableTiming);
@@ -395,6 +424,9 @@ extern "C" void cugs_b200_trainer_destroy(cugs_trainer_t* t) {
     if (t->res_pinned) cudaFreeHost(t->res_pinned);
     if (t->aux) cudaStreamDestroy(t->aux);
     if (t->cap) cudaStreamDestroy(t->cap);
+    if (t->copy) cudaStreamDestroy(t->copy);
+    for (cudaEvent_t ev : {t->ev_copy_fork, t->ev_copied[0], t->ev_copied[1], t->ev_copy_join})
+        if (ev) cudaEventDestroy(ev);
     cudaEvent_t evs[4] = {t->ev_fork, t->ev_bwd[0], t->ev_bwd[1], t->ev_join};
     for (cudaEvent_t ev : evs)
         if (ev) cudaEventDestroy(ev);
@@ -405,26 +437,31 @@ extern "C" void cugs_b200_trainer_destroy(cugs_trainer_t* t) {
 
 extern "C" int cugs_b200_trainer_set_views(cugs_trainer_t* t, int num_views, const cugs_view_t* views,
                                            const float* const* targets_dev, const float* const* dL_dcolor_dev,
-                                           int total_views_per_step) {
+                                           const float* const* targets_host_pinned, int total_views_per_step) {
     if (!t) return CUGS_ERR_INVALID_ARG;
     cugs_handle_t* h = t->h;
     CUGS_REQUIRE(h, num_views >= 0 && (num_views == 0 || (views && (targets_dev || dL_dcolor_dev))), "bad views");
     CUGS_REQUIRE(h, total_views_per_step >= num_views, "total_views_per_step < num_views");
     auto tgt = [&](int v) { return targets_dev ? targets_dev[v] : nullptr; };
     auto dl = [&](int v) { return dL_dcolor_dev ? dL_dcolor_dev[v] : nullptr; };
+    auto th = [&](int v) { return targets_host_pinned ? targets_host_pinned[v] : nullptr; };
     bool same = (int)t->views.size() == num_views && t->total_views == total_views_per_step;
     for (int v = 0; same && v < num_views; ++v)
         same = std::memcmp(&t->views[v], &views[v], sizeof(cugs_view_t)) == 0 && t->targets[v] == tgt(v) &&
-               t->dLs[v] == dl(v);
+               t->dLs[v] == dl(v) && t->targets_host[v] == th(v);
     if (same) return CUGS_OK;
     for (int v = 0; v < num_views; ++v) {
         CUGS_REQUIRE(h, views[v].width == t->W && views[v].height == t->H, "view size differs from the trainer's");
         CUGS_REQUIRE(h, tgt(v) != nullptr || dl(v) != nullptr, "a view needs a target image or a given dL/dcolor");
+        CUGS_REQUIRE(h, th(v) == nullptr || tgt(v) != nullptr, "a host target needs a device buffer to be copied into");
+        for (int u = 0; u < v; ++u)
+            CUGS_REQUIRE(h, th(v) == nullptr || tgt(u) != tgt(v), "views with host targets need distinct device buffers");
     }
     t->views.assign(views, views + num_views);
     t->targets.resize(num_views);
     t->dLs.resize(num_views);
-    for (int v = 0; v < num_views; ++v) { t->targets[v] = tgt(v); t->dLs[v] = dl(v); }
+    t->targets_host.resize(num_views);
+    for (int v = 0; v < num_views; ++v) { t->targets[v] = tgt(v); t->dLs[v] = dl(v); t->targets_host[v] = th(v); }
     t->total_views = total_views_per_step;
     ++t->views_gen;  // invalidates the captured graphs
     return CUGS_OK;

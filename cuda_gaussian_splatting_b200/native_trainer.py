@@ -121,17 +121,26 @@ class NativeTrainer:
         _lib.check(self.h, st, "cugs_b200_trainer_create")
         self._t = out.value
         lib.cugs_b200_trainer_set_adam_steps(self._t, int(adam_steps))
-        self.set_views(self.cameras, self.targets, self._dLs)
+        self.set_views(self.cameras, self.targets, self._dLs, getattr(self, "_targets_host", None))
 
     def set_views(self, cameras: Sequence[CameraInfo], targets: Sequence[torch.Tensor],
-                  dL_dcolors: Optional[Sequence[Optional[torch.Tensor]]] = None) -> None:
+                  dL_dcolors: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                  targets_host: Optional[Sequence[Optional[torch.Tensor]]] = None) -> None:
         """``dL_dcolors`` (optional, per view): a given dL/dcolor replaces the loss of that view (forward +
-        backward only -- the headline benchmark's step)."""
+        backward only -- the headline benchmark's step). ``targets_host`` (optional, per view): PINNED host images
+        copied into ``targets[v]`` inside every step, under the rendering of the view (end-to-end mode)."""
         self.cameras, self.targets = list(cameras), [None if t is None else t.contiguous() for t in targets]
         V = len(self.cameras)
         views = (CugsView * V)()
         tg = (C.c_void_p * V)()
         dl = (C.c_void_p * V)()
+        th = (C.c_void_p * V)()
+        self._targets_host = list(targets_host) if targets_host is not None else [None] * V
+        for k, ht in enumerate(self._targets_host):
+            if ht is not None:
+                _check(tuple(ht.shape) == (self.H, self.W, 3) and ht.dtype == torch.float32 and ht.is_pinned()
+                       and ht.is_contiguous(), "targets_host must be pinned contiguous [H, W, 3] float32 tensors")
+                th[k] = ht.data_ptr()
         self._dLs = list(dL_dcolors) if dL_dcolors is not None else [None] * V
         for k, g in enumerate(self._dLs):
             if g is not None:
@@ -146,7 +155,7 @@ class NativeTrainer:
                 _check(tuple(tgt.shape) == (self.H, self.W, 3) and tgt.is_cuda and tgt.dtype == torch.float32,
                        "targets must be [H, W, 3] float32 CUDA tensors")
                 tg[k] = tgt.data_ptr()
-        st = self.lib.cugs_b200_trainer_set_views(self._t, V, views, tg, dl, self.total_views)
+        st = self.lib.cugs_b200_trainer_set_views(self._t, V, views, tg, dl, th, self.total_views)
         _lib.check(self.h, st, "cugs_b200_trainer_set_views")
 
     def _step(self, step: int, phases: int) -> None:

@@ -444,10 +444,14 @@ void cugs_b200_trainer_destroy(cugs_trainer_t* t);
 /* The views this rank renders every step (cameras + device target images [H,W,3]); total_views_per_step =
  * views of ALL ranks (Adam's gradient scale is 1 / total). active_sh_degree, num_coeffs, bg and
  * scale_modifier of the views are set by the trainer. dL_dcolor_dev (optional array, entries may be NULL):
- * a view with a given dL/dcolor [H,W,3] skips the loss (forward + backward only; its loss scalars are 0). */
+ * a view with a given dL/dcolor [H,W,3] skips the loss (forward + backward only; its loss scalars are 0).
+ * targets_host_pinned (optional array, entries may be NULL): the view's target image lives in PINNED host memory
+ * and is copied into targets_dev[v] inside every step, on a copy stream, under the rendering of that view
+ * (the reference uploads the image synchronously every iteration, training/trainer.cpp:186-198). Such views need
+ * distinct device buffers. */
 int cugs_b200_trainer_set_views(cugs_trainer_t* t, int num_views, const cugs_view_t* views,
                                 const float* const* targets_dev, const float* const* dL_dcolor_dev,
-                                int total_views_per_step);
+                                const float* const* targets_host_pinned, int total_views_per_step);
 /* phases: 1 = views (render -> loss -> backward), 2 = update (Adam [+ regulariser] [+ noise]), 3 = both.
  * View-parallel training calls 1, exchanges the gradients, then 2. Nothing blocks. */
 int cugs_b200_trainer_step(cugs_trainer_t* t, void* stream, int step, int phases);

@@ -115,6 +115,27 @@ def test_preprocess_vs_reference(ref, torch, name):
     assert np.abs(np_(o.rgb) - r_rgb).max() <= 2e-6  # SH: different summation order only
 
 
+def test_sh_colours_at_the_clamp_boundary_vs_reference(ref, torch):
+    """the C = 16 fast path sums the SH dot product as four 4-coefficient partials (the reference sums
+    k ascending), so rgb differs by ulps and the ReLU gate `rgb > 0` of the backward can only flip for colours
+    within that rounding noise of the clamp. Scene: DC terms placed so that raw colour + 0.5 straddles 0."""
+    scene = cugs.synth(20_000, 320, 240, seed=71)
+    rng = np.random.default_rng(72)
+    sh = scene.sh_coeffs.copy()
+    sh[:, :, 0] = (-0.5 / 0.28209479177387814) + rng.normal(scale=2e-3, size=sh[:, :, 0].shape).astype(np.float32)
+    sh[:, :, 1:] *= 1e-3                                   # higher bands: small, so the sum stays near the boundary
+    scene = Scene(scene.positions, sh, scene.opacities, scene.rotations, scene.scales, scene.camera)
+    m = to_torch(scene)
+    r = ref.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs, scene.camera.as_ref_list(), 3, 1.0)
+    o = cugs.project_gaussians(m.positions, m.rotations, m.scales, m.opacities, m.sh_coeffs, scene.camera, 3)
+    mine, theirs = np_(o.rgb), np_(r[5])
+    assert 0.2 < (theirs == 0).mean() < 0.8, "the scene must straddle the clamp"
+    assert np.abs(mine - theirs).max() <= 2e-6
+    flips = (mine > 0) != (theirs > 0)
+    assert flips.mean() <= 1e-3, f"gate flips {flips.mean():.2e}"
+    assert np.maximum(mine, theirs)[flips].max(initial=0.0) <= 2e-6, "a gate may only flip inside the rounding noise"
+
+
 def test_preprocess_scale_modifier_and_ring_camera(ref, torch):
     scene, deg = get_scene("small")
     cam = cugs.ring_cameras(scene, 3)[1]

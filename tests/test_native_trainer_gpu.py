@@ -120,3 +120,28 @@ def test_overflow_skips_the_update_and_grow_recovers(torch):
         assert _rel(getattr(model, nm), getattr(twin, nm)) <= 2e-5, nm
     assert nat.adam_steps == 1
     nat.close(); full.close()
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_host_targets_copied_inside_the_step(torch, use_graph):
+    """End-to-end mode: the target images live in pinned host memory and are copied inside every step (copy
+    stream, under the rendering of the same view). Same losses and parameters as with device-resident targets;
+    changing the host image between steps changes the next step's loss (the copy really happens per step)."""
+    scene, cams, targets = _setup(torch, views=3)
+    a, b = to_torch(scene), to_torch(scene)
+    dev_tr = cugs.NativeTrainer(a, cams, targets, cugs.TrainConfig(), use_graph=use_graph)
+    host = [t.cpu().pin_memory() for t in targets]
+    staging = [torch.empty_like(t) for t in targets]
+    host_tr = cugs.NativeTrainer(b, cams, staging, cugs.TrainConfig(), use_graph=use_graph)
+    host_tr.set_views(cams, staging, None, host)
+    for s in range(3000, 3005):
+        dev_tr.train_step(s)
+        host_tr.train_step(s)
+        assert np.allclose(host_tr.result()[0], dev_tr.result()[0], rtol=2e-5, atol=1e-6), s
+    for nm in PARAMS:
+        assert _rel(getattr(b, nm), getattr(a, nm)) <= 2e-5, nm
+    before = host_tr.result()[0][0]
+    host[0].zero_()                      # a different image in the same pinned buffer: no re-capture needed
+    host_tr.train_step(3005)
+    assert abs(host_tr.result()[0][0] - before) > 1e-3
+    dev_tr.close(); host_tr.close()
