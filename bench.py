@@ -256,11 +256,13 @@ def run_b200(args) -> dict:
     all_cams = bench_views(scene, world * V)
     cams = [all_cams[i] for i in cugs.shard_views(world * V, world, rank)]
     settings = cugs.RenderSettings((0.0, 0.0, 0.0), 3, 1.0)
-    buf = cugs.FrameBuffers(n, W, H, 16, dev)
     lib, h = _lib.load_library(), _lib.handle(local)
 
     if args.mode == "train_step":
         return run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world, local, dev, desc)
+    # N > 1: the gradient arena lives in symmetric memory so that the exchange can run peer to peer over NVLink
+    use_p2p = world > 1 and args.exchange == "p2p" and not args.dense_allreduce
+    buf = cugs.FrameBuffers(n, W, H, 16, dev, symmetric=use_p2p)
 
     # synthetic targets (host, pinned) and the resident dL/dcolor of each view; the blocking renders also
     # establish the pair capacity of every buffer used below
@@ -293,6 +295,8 @@ def run_b200(args) -> dict:
         if args.dense_allreduce:
             cugs.allreduce_step(buf.grad_arena, buf.step_max_radii if with_stats else None)
             exchange.update(mode="dense")
+        elif p2p is not None:
+            exchange.update(p2p.exchange(with_stats=with_stats))
         else:
             exchange.update(cugs.sparse_allreduce_step(buf, with_stats=with_stats, state=exch_state,
                                                        mask_reduced=mask_reduced))
@@ -300,6 +304,7 @@ def run_b200(args) -> dict:
     # the dense exchange is requested (it sums rows this rank's mask does not know about)
     sparse = not args.dense_allreduce
     touch = buf.touch_mask if sparse else None
+    p2p = cugs.P2PExchange(buf) if use_p2p else None
 
     # ---- headline path: the C++ step driver's "views" phase (cugs_b200_trainer_step, phases = 1) with a given
     # dL/dcolor per view = forward + backward only. No host round trip per view (device-side pair count),
@@ -311,7 +316,7 @@ def run_b200(args) -> dict:
     step_no = [3000]
     # the MAX all-reduce of the touch mask (and the scan of the union) run on a side stream under the chain rule
     # of the step's last backward
-    overlap = cugs.MaskOverlap(dev) if (world > 1 and sparse and not args.no_mask_overlap) else None
+    overlap = cugs.MaskOverlap(dev) if (world > 1 and sparse and p2p is None and not args.no_mask_overlap) else None
 
     def step_resident():
         if overlap is not None:
@@ -492,8 +497,10 @@ def run_b200(args) -> dict:
                           "achieved_tmufu": round(tm, 4), "frac_of_mufu_peak": round(tm / mufu_peak, 4),
                           "hbm_bytes": (40 * P + 20 * W * H) + (36 * P if nm == "blend_bwd" else 0)}
         if exchange_ms is not None:
-            ex_floats = exchange.get("floats") or buf.grad_arena.numel()
+            m_union = int((buf.touch_mask != 0).sum())
+            ex_floats = exchange.get("floats") or ((59 * m_union + 2 * n) if p2p is not None else buf.grad_arena.numel())
             rl_all["exchange"] = {"ms": round(exchange_ms, 4), "bound": "nvlink", "bytes_summed": 4 * int(ex_floats),
+                                  "touched_union": m_union,
                                   "bytes_max_reduced": 8 * n, "mode": exchange.get("mode"),
                                   "note": "whole exchange of one step, timed alone after a finished step (max over ranks)"}
         # `roofline`: the DOMINANT kernel of the step, k_blend_bwd, against the FP32-issue roofline of SURVEY 8(d)
@@ -522,8 +529,11 @@ def run_b200(args) -> dict:
                        "densification_stats_fused": with_stats,
                        "collective": "none" if world == 1 else (
                            "one NCCL all-reduce(sum) of the 61N-float arena per step (+ MAX of max_radii)" if args.dense_allreduce else
-                           "per step: int32 MAX all-reduce of [touch mask | max_radii] (8 B/Gaussian) + ONE all-reduce(sum) of the "
-                           "touched gradient rows and the additive statistics"),
+                           ("per step, peer to peer over NVLink on symmetric memory (no NCCL): k_xchg_masks (MAX of [touch mask | "
+                            "max_radii], SUM of the statistics) + k_xchg_rows (each rank sums its slice of the touched gradient rows "
+                            "across all arenas and writes it back to all), 3 device-side barriers") if p2p is not None else
+                           "per step: int32 MAX all-reduce of [touch mask | max_radii] (8 B/Gaussian) + ONE NCCL all-reduce(sum) of "
+                           "the touched gradient rows and the additive statistics"),
                        "gradient_exchange": exchange, "touched_fraction": touched_frac,
                        "mask_allreduce_overlapped": overlap is not None,
                        "min_timed_ms": MIN_TIMED_MS,
@@ -569,12 +579,16 @@ def run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world
     V = len(cams)
     rng = np.random.default_rng(4321 + rank)
     targets = [torch.from_numpy(rng.uniform(size=(H, W, 3)).astype(np.float32)).to(dev) for _ in range(V)]
+    use_p2p = world > 1 and args.exchange == "p2p"
+    gbuf = cugs.FrameBuffers(n, W, H, int(model.sh_coeffs.shape[2]), dev, symmetric=use_p2p)
     trainer = cugs.NativeTrainer(model, cams, targets, cugs.TrainConfig(), total_views_per_step=world * V,
-                                 frames_in_flight=1 if args.no_overlap else 2, use_graph=not args.no_graph)
+                                 frames_in_flight=1 if args.no_overlap else 2, use_graph=not args.no_graph,
+                                 grad_buffers=gbuf)
+    p2p = cugs.P2PExchange(gbuf) if use_p2p else None
     lib, h = _lib.load_library(), _lib.handle(local)
     step_no = [3000]  # SH degree 3 active (lr_schedule.hpp:70-72)
     exch_state = {}
-    overlap = cugs.MaskOverlap(dev) if (world > 1 and not args.no_mask_overlap) else None
+    overlap = cugs.MaskOverlap(dev) if (world > 1 and p2p is None and not args.no_mask_overlap) else None
 
     def step():
         if world == 1:
@@ -587,8 +601,11 @@ def run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world
                 overlap.finish()
             else:
                 trainer.step_views(step_no[0])
-            cugs.sparse_allreduce_step(trainer.buffers, with_stats=True, state=exch_state,
-                                       mask_reduced=overlap is not None)
+            if p2p is not None:
+                p2p.exchange(with_stats=True)
+            else:
+                cugs.sparse_allreduce_step(trainer.buffers, with_stats=True, state=exch_state,
+                                           mask_reduced=overlap is not None)
             b = trainer.buffers
             cugs.fold_step_stats(b.step_grad_accum, b.step_grad_count, b.step_max_radii, trainer.stats.grad_accum,
                                  trainer.stats.grad_count, trainer.stats.max_radii_2d)
@@ -797,6 +814,9 @@ def main():
     ap.add_argument("--views-total", type=int, default=0,
                     help="STRONG scaling: a fixed number of views per step split over the GPUs (16 = BASELINE config[3])")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA graph replay")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: gradient exchange as peer-to-peer kernels over NVLink symmetric memory (default) or as NCCL "
+                         "all-reduces around gather / scatter copies")
     ap.add_argument("--no-mask-overlap", action="store_true",
                     help="N > 1: run the MAX all-reduce of the touch mask after the backward instead of under it")
     ap.add_argument("--no-cpu-baseline", action="store_true")

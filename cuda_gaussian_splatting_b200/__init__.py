@@ -24,7 +24,7 @@ from .density import (  # noqa: F401
 )
 from .native_trainer import NativeTrainer  # noqa: F401
 from .parallel import (  # noqa: F401
-    allreduce_step, arena_layout, fold_step_stats, grad_scale_for, shard_views, sparse_allreduce_step, MaskOverlap,
+    allreduce_step, arena_layout, fold_step_stats, grad_scale_for, shard_views, sparse_allreduce_step, MaskOverlap, P2PExchange,
 )
 
 __all__ = [n for n in dir() if not n.startswith("_")]

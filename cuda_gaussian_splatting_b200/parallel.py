@@ -49,6 +49,72 @@ def allreduce_step(arena: torch.Tensor, max_radii: Optional[torch.Tensor] = None
     return works if async_op else []
 
 
+class P2PExchange:
+    """The step's gradient exchange as two kernels over NVLink peer memory instead of NCCL collectives around
+    local gather / scatter copies (csrc/grad_exchange.cu, "Peer-to-peer exchange"): the buffers must come from
+    ``FrameBuffers(..., symmetric=True)``. Per step:
+
+        barrier -> k_xchg_masks  (MAX of [touch mask | max_radii], SUM of the two statistics, sliced over the ranks)
+        barrier -> scan of the union mask + index list (local, identical on every rank; M stays on the device)
+                -> k_xchg_rows   (each rank sums ITS slice of the union rows across all arenas, in rank order,
+                                  and writes the result into all arenas)
+        barrier
+
+    Same sums as the all-reduce (each one computed exactly once, so every rank holds the same bits), the bytes of
+    one all-reduce on NVLink, no compact buffers, no row-capacity, nothing for the host to wait for."""
+
+    def __init__(self, buffers, group: Optional[dist.ProcessGroup] = None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from .rasterizer import _check
+        _check(getattr(buffers, "symmetric", False), "P2PExchange needs FrameBuffers(..., symmetric=True)")
+        self.b = buffers
+        self.group = group if group is not None else dist.group.WORLD
+        name = self.group.group_name
+        self.h_arena = symm_mem.rendezvous(buffers.grad_arena, name)
+        self.h_max = symm_mem.rendezvous(buffers.max_buf, name)
+        self.world, self.rank = int(self.h_arena.world_size), int(self.h_arena.rank)
+        _check(self.world <= 8, "P2PExchange supports up to 8 ranks (one NVSwitch box)")
+        b = buffers
+        base = b.grad_arena.data_ptr()
+        groups = (b.dL_dpositions, b.dL_dsh_coeffs, b.dL_dopacities, b.dL_dscales, b.dL_drotations)
+        offs = [t.data_ptr() - base for t in groups]
+        self._grads = (C.c_void_p * (self.world * 5))()
+        self._accum = (C.c_void_p * self.world)()
+        self._count = (C.c_void_p * self.world)()
+        self._maxbuf = (C.c_void_p * self.world)()
+        for p in range(self.world):
+            pb = int(self.h_arena.buffer_ptrs[p])
+            for k in range(5):
+                self._grads[p * 5 + k] = pb + offs[k]
+            self._accum[p] = pb + (b.step_grad_accum.data_ptr() - base)
+            self._count[p] = pb + (b.step_grad_count.data_ptr() - base)
+            self._maxbuf[p] = int(self.h_max.buffer_ptrs[p])
+        self.ops = _CudaRowOps()
+
+    def exchange(self, with_stats: bool = True) -> dict:
+        from . import _lib
+        from .rasterizer import _lib_and_handle, _stream
+        b = self.b
+        dev = b.grad_arena.device
+        lib, h = _lib_and_handle(dev)
+        n, C_ = int(b.n), int(b.dL_dsh_coeffs.shape[2])
+        self.h_max.barrier(channel=0)      # every rank's mask / statistics / gradient rows of this step are final
+        st = lib.cugs_b200_p2p_reduce_masks(h, _stream(dev), n, self.world, self.rank, self._maxbuf,
+                                            self._accum if with_stats else None, self._count if with_stats else None)
+        _lib.check(h, st, "cugs_b200_p2p_reduce_masks")
+        self.h_max.barrier(channel=1)      # all slices of the union mask have landed
+        offsets, m_dev = self.ops.scan_dev(b)
+        st = lib.cugs_b200_build_touch_index(h, _stream(dev), n, b.touch_mask.data_ptr(), offsets.data_ptr(),
+                                             b._touch_idx.data_ptr())
+        _lib.check(h, st, "cugs_b200_build_touch_index")
+        st = lib.cugs_b200_p2p_reduce_rows(h, _stream(dev), n, C_, self.world, self.rank, b._touch_idx.data_ptr(),
+                                           m_dev.data_ptr(), self._grads)
+        _lib.check(h, st, "cugs_b200_p2p_reduce_rows")
+        self.h_arena.barrier(channel=0)    # all sums written everywhere; nobody reads these rows any more
+        return {"mode": "p2p", "host_sync": False}
+
+
 class MaskOverlap:
     """Hides the first collective of the sparse exchange -- the MAX all-reduce of [touch mask | max_radii] and
     the scan of the union mask -- under the tail of the step's last backward: the mask is final after the

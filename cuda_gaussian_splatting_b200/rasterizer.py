@@ -428,7 +428,7 @@ class FrameBuffers:
     would otherwise allocate per call (the reference allocates ~45 tensors per frame)."""
 
     def __init__(self, n: int, width: int, height: int, num_coeffs: int, device, p_capacity: int = 0,
-                 share_grads_with: Optional["FrameBuffers"] = None):
+                 share_grads_with: Optional["FrameBuffers"] = None, symmetric: bool = False):
         f = dict(dtype=torch.float32, device=device)
         i = dict(dtype=torch.int32, device=device)
         self.n, self.width, self.height = n, width, height
@@ -460,7 +460,17 @@ class FrameBuffers:
         if share_grads_with is not None:
             _check(share_grads_with.n == n and share_grads_with.grad_arena.numel() == total,
                    "share_grads_with: incompatible FrameBuffers")
-        self.grad_arena = share_grads_with.grad_arena if share_grads_with is not None else torch.zeros((total,), **f)
+        # symmetric = True (view-parallel training, parallel.P2PExchange): the arena and the MAX buffer are
+        # allocated in torch symmetric memory, i.e. at the same offsets on every rank and mappable by the peers
+        self.symmetric = bool(symmetric) if share_grads_with is None else share_grads_with.symmetric
+        if share_grads_with is not None:
+            self.grad_arena = share_grads_with.grad_arena
+        elif symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.grad_arena = symm_mem.empty(total, dtype=torch.float32, device=torch.device(device))
+            self.grad_arena.zero_()
+        else:
+            self.grad_arena = torch.zeros((total,), **f)
         seg = lambda nm: self.grad_arena[layout[nm][0]:layout[nm][0] + layout[nm][1]]
         self.dL_dpositions = seg("positions").view(n, 3)
         self.dL_dsh_coeffs = seg("sh_coeffs").view(n, 3, num_coeffs)
@@ -471,8 +481,14 @@ class FrameBuffers:
         self.step_grad_count = seg("grad_count")   # number of the step's views in which the Gaussian was visible
         # quantities that need a MAX reduction live in one int32 buffer [touch mask | max_radii bits]
         # (non-negative floats order like their bit patterns, so one int32 MAX all-reduce serves both)
-        self.max_buf = (share_grads_with.max_buf if share_grads_with is not None
-                        else torch.zeros((2 * max(n, 1),), **i))
+        if share_grads_with is not None:
+            self.max_buf = share_grads_with.max_buf
+        elif symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.max_buf = symm_mem.empty(2 * max(n, 1), dtype=torch.int32, device=torch.device(device))
+            self.max_buf.zero_()
+        else:
+            self.max_buf = torch.zeros((2 * max(n, 1),), **i)
         self.touch_mask = self.max_buf[:n]                       # 1 where some view gave a non-zero gradient
         self.step_max_radii = self.max_buf[n:2 * n].view(torch.float32)
         self.grad_compact = None                                  # lazily allocated by parallel.sparse_allreduce_step

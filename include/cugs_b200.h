@@ -484,6 +484,24 @@ int cugs_b200_scatter_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int n
                                 const float* compact, float* const grads[5], int32_t* idx_scratch,
                                 const int64_t* m_dev);
 
+/* Peer-to-peer variant of the exchange (csrc/grad_exchange.cu): every rank's gradient arena, [touch mask |
+ * max_radii] buffer and statistics live in symmetric memory and each rank holds peer-mapped pointers to all of
+ * them (`*_peers[world]`, rank order, own buffers included). p2p_reduce_masks: MAX of the 2 N int32 of max_buf and
+ * SUM of the two statistics (NULL, NULL to skip them), each rank reducing its slice of [0, n) and writing the
+ * result into every peer. p2p_reduce_rows: the five gradient rows of every Gaussian of the union mask
+ * (idx = cugs_b200_build_touch_index of the reduced mask's scan, m_dev = that scan's device-side total) are summed
+ * across the ranks in rank order and written back into every arena; grads_peers[p * 5 + k] = group k
+ * (positions, sh_coeffs, opacities, scales, rotations) of rank p. No compact buffers, no host knowledge of M, the
+ * same bits on every rank. The CALLER synchronises the ranks (symmetric-memory barrier) before the first call,
+ * between the two, and after the second. */
+int cugs_b200_build_touch_index(cugs_handle_t* h, void* stream, int64_t n, const int32_t* touch,
+                                const int32_t* offsets, int32_t* idx);
+int cugs_b200_p2p_reduce_masks(cugs_handle_t* h, void* stream, int64_t n, int world, int rank,
+                               int32_t* const* max_buf_peers, float* const* grad_accum_peers,
+                               float* const* grad_count_peers);
+int cugs_b200_p2p_reduce_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs, int world, int rank,
+                              const int32_t* idx, const int64_t* m_dev, float* const* grads_peers);
+
 #ifdef __cplusplus
 }
 #endif
