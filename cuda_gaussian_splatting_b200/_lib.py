@@ -108,8 +108,8 @@ SIGNATURES = {
     "cugs_b200_gather_grad_rows": (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, C.POINTER(_P), _P, _P, _P, _P]),
     "cugs_b200_scatter_grad_rows": (_INT, [_P, _P, _I64, _INT, _P, _P, _I64, _P, C.POINTER(_P), _P, _P]),
     "cugs_b200_build_touch_index": (_INT, [_P, _P, _I64, _P, _P, _P]),
-    "cugs_b200_p2p_reduce_masks": (_INT, [_P, _P, _I64, _INT, _INT, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
-    "cugs_b200_p2p_reduce_rows": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, C.POINTER(_P)]),
+    "cugs_b200_p2p_reduce_masks": (_INT, [_P, _P, _I64, _INT, _INT, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _P, _P]),
+    "cugs_b200_p2p_reduce_rows": (_INT, [_P, _P, _I64, _INT, _INT, _INT, _P, _P, C.POINTER(_P), C.POINTER(_P)]),
     "cugs_b200_last_sort_plan": (_INT, [_P, C.POINTER(_INT), C.POINTER(_INT)]),
     "cugs_b200_set_stage_timing": (_INT, [_P, _INT]),
     "cugs_b200_get_stage_ms": (_INT, [_P, C.POINTER(_F)]),

@@ -199,8 +199,122 @@ k_xchg_masks(int64_t n, int world, int rank, PeerInts maxbuf, PeerFloats accum, 
 
 // phase 2: the rows of the union mask. idx[j] = Gaussian of union row j (identical on every rank), M on the device.
 // blockIdx.y = parameter group, as in k_move_grad_rows; the rank owns rows [rank M / R, (rank + 1) M / R).
+// kWorld is a template parameter so that the R peer loads of an element are R independent instructions issued back
+// to back (no predication, exact register arrays), and every thread keeps kUnroll elements in flight: the first
+// version (run-time world, one element per thread) moved 63 MB each way in 0.31 ms at 2 GPUs (~200 GB/s per
+// direction), latency bound on the remote reads.
+template <int kWorld, int kUnroll>
 __global__ void __launch_bounds__(256)
-k_xchg_rows(int C, const int* __restrict__ idx, const int64_t* __restrict__ m_dev, int world, int rank, PeerGroups peers) {
+k_xchg_rows(int C, const int* __restrict__ idx, const int64_t* __restrict__ m_dev, int rank, PeerGroups peers) {
+    const int grp = blockIdx.y;
+    const int64_t m = *m_dev;
+    const int64_t per = (m + kWorld - 1) / kWorld;
+    const int64_t j0 = (int64_t)rank * per, j1 = min(m, j0 + per);
+    if (j0 >= j1) return;
+    const int shw = 3 * C;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = (grp == 0) ? 3 : (grp == 1) ? shw : (grp == 2) ? 1 : (grp == 3) ? 3 : 4;
+    if ((w & 3) == 0) {  // SH (3C % 4 == 0) and rotations: 16-byte accesses
+        const unsigned w4 = (unsigned)(w >> 2);
+        const int64_t total = (j1 - j0) * w4;
+        for (int64_t e0 = t0; e0 < total; e0 += stride * kUnroll) {
+            int64_t off[kUnroll];
+            float4 v[kUnroll][kWorld];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t e = e0 + (int64_t)u * stride;
+                off[u] = -1;
+                if (e < total) {
+                    const unsigned jj = (unsigned)((uint64_t)e / w4);   // (e < 2^32 for any model that fits a GPU)
+                    off[u] = (int64_t)idx[j0 + jj] * w4 + (e - (int64_t)jj * w4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+                for (int p = 0; p < kWorld; ++p)
+                    if (off[u] >= 0) v[u][p] = reinterpret_cast<const float4*>(peers.g[p][grp])[off[u]];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (off[u] < 0) continue;
+                float4 s = v[u][0];
+#pragma unroll
+                for (int p = 1; p < kWorld; ++p) { s.x += v[u][p].x; s.y += v[u][p].y; s.z += v[u][p].z; s.w += v[u][p].w; }
+#pragma unroll
+                for (int p = 0; p < kWorld; ++p) reinterpret_cast<float4*>(peers.g[p][grp])[off[u]] = s;
+            }
+        }
+    } else {
+        const int64_t total = (j1 - j0) * w;
+        for (int64_t e = t0; e < total; e += stride) {
+            const int64_t jj = e / w;
+            const int64_t off = (int64_t)idx[j0 + jj] * w + (e - jj * w);
+            float v[kWorld];
+#pragma unroll
+            for (int p = 0; p < kWorld; ++p) v[p] = peers.g[p][grp][off];
+            float s = v[0];
+#pragma unroll
+            for (int p = 1; p < kWorld; ++p) s += v[p];
+#pragma unroll
+            for (int p = 0; p < kWorld; ++p) peers.g[p][grp][off] = s;
+        }
+    }
+}
+
+// ---- NVLS variant: the same two phases on the MULTICAST mapping of the symmetric buffers. multimem.ld_reduce
+// lets the NVSwitch fetch the element from every GPU, reduce it in the switch and return ONE value; multimem.st
+// stores once and the switch replicates it to every GPU. Per GPU and direction that is (R-1)/R + 1/R of the data
+// on the links instead of 2 (R-1)/R for unicast loads + stores: measured (profiles/r02/NOTES.md) the unicast
+// kernel is bound by NVLink at ~200-300 GB/s per direction on this pod, like NCCL's ring.
+struct McGroups { float* g[5]; };
+
+__device__ __forceinline__ float4 mc_ld_add_f32x4(const float* addr) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st_f32x4(float* addr, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float mc_ld_add_f32(const float* addr) {
+    float v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st_f32(float* addr, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ int mc_ld_max_s32(const int* addr) {
+    int v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.max.s32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st_s32(int* addr, int v) {
+    asm volatile("multimem.st.relaxed.sys.global.s32 [%0], %1;" :: "l"(addr), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_xchg_masks_mc(int64_t n, int world, int rank, int* __restrict__ maxbuf_mc, float* __restrict__ accum_mc,
+                float* __restrict__ count_mc, bool with_stats) {
+    const int64_t per = (n + world - 1) / world;
+    const int64_t i0 = (int64_t)rank * per, i1 = min(n, i0 + per);
+    for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = mc_ld_max_s32(maxbuf_mc + i);
+        const int r = mc_ld_max_s32(maxbuf_mc + n + i);
+        mc_st_s32(maxbuf_mc + i, m);
+        mc_st_s32(maxbuf_mc + n + i, r);
+        if (with_stats) {
+            const float a = mc_ld_add_f32(accum_mc + i), c = mc_ld_add_f32(count_mc + i);
+            mc_st_f32(accum_mc + i, a);
+            mc_st_f32(count_mc + i, c);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_xchg_rows_mc(int C, const int* __restrict__ idx, const int64_t* __restrict__ m_dev, int world, int rank, McGroups mc) {
     const int grp = blockIdx.y;
     const int64_t m = *m_dev;
     const int64_t per = (m + world - 1) / world;
@@ -209,34 +323,35 @@ k_xchg_rows(int C, const int* __restrict__ idx, const int64_t* __restrict__ m_de
     const int shw = 3 * C;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int w = (grp == 0) ? 3 : (grp == 1) ? shw : (grp == 2) ? 1 : (grp == 3) ? 3 : 4;
-    if ((w & 3) == 0) {  // SH (C multiple of 4 / 3 ... any 3C % 4 == 0) and rotations: 16-byte accesses
-        const int w4 = w >> 2;
-        for (int64_t e = t0; e < (j1 - j0) * w4; e += stride) {
-            const int64_t j = j0 + e / w4;
-            const int64_t off = (int64_t)idx[j] * w4 + (e - (j - j0) * w4);
-            float4 v[kMaxPeers];
+    float* base = mc.g[grp];
+    if ((w & 3) == 0) {
+        const unsigned w4 = (unsigned)(w >> 2);
+        const int64_t total = (j1 - j0) * w4;
+        for (int64_t e0 = t0; e0 < total; e0 += stride * 4) {
+            int64_t off[4];
+            float4 v[4];
 #pragma unroll
-            for (int p = 0; p < kMaxPeers; ++p)
-                if (p < world) v[p] = reinterpret_cast<const float4*>(peers.g[p][grp])[off];
-            float4 s = v[0];
+            for (int u = 0; u < 4; ++u) {
+                const int64_t e = e0 + (int64_t)u * stride;
+                off[u] = -1;
+                if (e < total) {
+                    const unsigned jj = (unsigned)((uint64_t)e / w4);
+                    off[u] = ((int64_t)idx[j0 + jj] * w4 + (e - (int64_t)jj * w4)) * 4;
+                }
+            }
 #pragma unroll
-            for (int p = 1; p < kMaxPeers; ++p)
-                if (p < world) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+            for (int u = 0; u < 4; ++u)
+                if (off[u] >= 0) v[u] = mc_ld_add_f32x4(base + off[u]);
 #pragma unroll
-            for (int p = 0; p < kMaxPeers; ++p)
-                if (p < world) reinterpret_cast<float4*>(peers.g[p][grp])[off] = s;
+            for (int u = 0; u < 4; ++u)
+                if (off[u] >= 0) mc_st_f32x4(base + off[u], v[u]);
         }
     } else {
-        for (int64_t e = t0; e < (j1 - j0) * w; e += stride) {
-            const int64_t j = j0 + e / w;
-            const int64_t off = (int64_t)idx[j] * w + (e - (j - j0) * w);
-            float s = 0.f;
-#pragma unroll
-            for (int p = 0; p < kMaxPeers; ++p)
-                if (p < world) s += peers.g[p][grp][off];
-#pragma unroll
-            for (int p = 0; p < kMaxPeers; ++p)
-                if (p < world) peers.g[p][grp][off] = s;
+        const int64_t total = (j1 - j0) * w;
+        for (int64_t e = t0; e < total; e += stride) {
+            const int64_t jj = e / w;
+            const int64_t off = (int64_t)idx[j0 + jj] * w + (e - jj * w);
+            mc_st_f32(base + off, mc_ld_add_f32(base + off));
         }
     }
 }
@@ -256,10 +371,22 @@ extern "C" int cugs_b200_build_touch_index(cugs_handle_t* h, void* stream, int64
 
 extern "C" int cugs_b200_p2p_reduce_masks(cugs_handle_t* h, void* stream, int64_t n, int world, int rank,
                                           int32_t* const* max_buf_peers, float* const* grad_accum_peers,
-                                          float* const* grad_count_peers) {
+                                          float* const* grad_count_peers, int32_t* max_buf_mc, float* grad_accum_mc,
+                                          float* grad_count_mc) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, n >= 0 && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "bad n / world / rank");
     if (n == 0) return CUGS_OK;
+    if (max_buf_mc != nullptr) {  // NVLS: multicast mapping
+        const bool stats = grad_accum_mc != nullptr;
+        CUGS_REQUIRE(h, stats == (grad_count_mc != nullptr), "grad_accum and grad_count go together");
+        const int64_t per_mc = (n + world - 1) / world;
+        int64_t blocks_mc = (per_mc + 255) / 256;
+        if (blocks_mc > (int64_t)h->sm_count * 8) blocks_mc = (int64_t)h->sm_count * 8;
+        k_xchg_masks_mc<<<(unsigned)blocks_mc, 256, 0, (cudaStream_t)stream>>>(n, world, rank, max_buf_mc, grad_accum_mc,
+                                                                               grad_count_mc, stats);
+        CUGS_LAUNCH_CHECK(h, "k_xchg_masks_mc");
+        return CUGS_OK;
+    }
     CUGS_REQUIRE(h, max_buf_peers != nullptr, "null pointer");
     const bool with_stats = grad_accum_peers != nullptr;
     CUGS_REQUIRE(h, with_stats == (grad_count_peers != nullptr), "grad_accum and grad_count go together");
@@ -283,12 +410,27 @@ extern "C" int cugs_b200_p2p_reduce_masks(cugs_handle_t* h, void* stream, int64_
 }
 
 extern "C" int cugs_b200_p2p_reduce_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs, int world, int rank,
-                                         const int32_t* idx, const int64_t* m_dev, float* const* grads_peers) {
+                                         const int32_t* idx, const int64_t* m_dev, float* const* grads_peers,
+                                         float* const* grads_mc) {
     CUGS_REQUIRE(h, h != nullptr, "handle is null");
     CUGS_REQUIRE(h, n >= 0 && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "bad n / world / rank");
     CUGS_REQUIRE(h, num_coeffs >= 1 && num_coeffs <= 64, "bad num_coeffs");
     if (n == 0) return CUGS_OK;
-    CUGS_REQUIRE(h, idx && m_dev && grads_peers, "null pointer");
+    CUGS_REQUIRE(h, idx && m_dev && (grads_peers || grads_mc), "null pointer");
+    if (grads_mc != nullptr) {  // NVLS: multicast mapping
+        McGroups mc{};
+        for (int k = 0; k < 5; ++k) {
+            CUGS_REQUIRE(h, grads_mc[k] != nullptr, "null multicast gradient pointer");
+            mc.g[k] = grads_mc[k];
+        }
+        int64_t bxm = ((n / world + 1) * (3 * num_coeffs / 4 + 1) / 4 + 255) / 256;
+        const int64_t capm = (int64_t)h->sm_count * 8;
+        if (bxm > capm) bxm = capm;
+        if (bxm < 1) bxm = 1;
+        k_xchg_rows_mc<<<dim3((unsigned)bxm, 5), 256, 0, (cudaStream_t)stream>>>(num_coeffs, idx, m_dev, world, rank, mc);
+        CUGS_LAUNCH_CHECK(h, "k_xchg_rows_mc");
+        return CUGS_OK;
+    }
     PeerGroups pg{};
     for (int p = 0; p < world; ++p)
         for (int k = 0; k < 5; ++k) {
@@ -300,7 +442,18 @@ extern "C" int cugs_b200_p2p_reduce_rows(cugs_handle_t* h, void* stream, int64_t
     const int64_t cap = (int64_t)h->sm_count * 8;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    k_xchg_rows<<<dim3((unsigned)bx, 5), 256, 0, (cudaStream_t)stream>>>(num_coeffs, idx, m_dev, world, rank, pg);
+    const dim3 grid((unsigned)bx, 5);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (world) {
+        case 1: k_xchg_rows<1, 4><<<grid, 256, 0, s>>>(num_coeffs, idx, m_dev, rank, pg); break;
+        case 2: k_xchg_rows<2, 4><<<grid, 256, 0, s>>>(num_coeffs, idx, m_dev, rank, pg); break;
+        case 3: k_xchg_rows<3, 2><<<grid, 256, 0, s>>>(num_coeffs, idx, m_dev, rank, pg); break;
+        case 4: k_xchg_rows<4, 2><<<grid, 256, 0, s>>>(num_coeffs, idx, m_dev, rank, pg); break;
+        case 5: k_xchg_rows<5, 2><<<grid, 256, 0, s>>>(num_coeffs, idx, m_dev, rank, pg); break;
+        case 6: k_xchg_rows<6, 2><<<grid, 256, 0, s>>>(num_coeffs, idx, m_dev, rank, pg); break;
+        case 7: k_xchg_rows<7, 2><<<grid, 256, 0, s>>>(num_coeffs, idx, m_dev, rank, pg); break;
+        default: k_xchg_rows<8, 2><<<grid, 256, 0, s>>>(num_coeffs, idx, m_dev, rank, pg); break;
+    }
     CUGS_LAUNCH_CHECK(h, "k_xchg_rows");
     return CUGS_OK;
 }

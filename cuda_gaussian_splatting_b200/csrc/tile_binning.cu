@@ -38,7 +38,17 @@ constexpr int kPkItemsSmall = 4;
 #ifndef CUGS_PK_SMALL_LIMIT
 #define CUGS_PK_SMALL_LIMIT 0  // elements up to which the small-tile variant is used; 0 = never
 #endif
-inline int pk_items_for(int64_t n) { return (n > 0 && n <= (int64_t)CUGS_PK_SMALL_LIMIT) ? kPkItemsSmall : kPkItems; }
+// Long inputs (the P pairs): 16 items per thread (8192-element tiles, two blocks per SM) halve the number of tiles
+// and with it the look-back polling per element, which is a third of the instructions of a pass at 8 items.
+constexpr int kPkItemsLarge = 16;
+#ifndef CUGS_PK_LARGE_LIMIT
+#define CUGS_PK_LARGE_LIMIT (1ll << 62)  // elements from which the large-tile variant is used; default: never
+#endif
+inline int pk_items_for(int64_t n) {
+    if (n > 0 && n <= (int64_t)CUGS_PK_SMALL_LIMIT) return kPkItemsSmall;
+    if (n >= (int64_t)CUGS_PK_LARGE_LIMIT) return kPkItemsLarge;
+    return kPkItems;
+}
 constexpr int kPkWarps = kPkThreads / 32;
 constexpr int kPkMaxPasses = 4;
 
@@ -199,7 +209,7 @@ constexpr size_t pk_smem_bytes(int items) {
 #endif
 // kBits = digit width of the pass (6, 7, 8), 0 = run-time width; kItems = elements per thread (8 or 4)
 template <bool kLast, int kBits, int kItems>
-__global__ void __launch_bounds__(kPkThreads, CUGS_OS_MINBLOCKS)
+__global__ void __launch_bounds__(kPkThreads, (kItems > 8 ? 2 : CUGS_OS_MINBLOCKS))
 k_onesweep_packed(int64_t n_cap, const int64_t* __restrict__ n_dev, const uint64_t* __restrict__ in,
                   uint64_t* __restrict__ out, int* __restrict__ out32, const unsigned* __restrict__ bin_base,
                   volatile unsigned* __restrict__ lookback, unsigned* __restrict__ ticket, int shift, int bits,
@@ -596,6 +606,7 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
 #define CUGS_OS_LAUNCH(LAST, BITS)                                                  \
     do {                                                                            \
         if (items == kPkItemsSmall) CUGS_OS_LAUNCH_I(LAST, BITS, kPkItemsSmall);    \
+        else if (items == kPkItemsLarge) CUGS_OS_LAUNCH_I(LAST, BITS, kPkItemsLarge); \
         else CUGS_OS_LAUNCH_I(LAST, BITS, kPkItems);                                \
     } while (0)
 #define CUGS_OS_DISPATCH(LAST)                          \

@@ -63,7 +63,10 @@ class P2PExchange:
     Same sums as the all-reduce (each one computed exactly once, so every rank holds the same bits), the bytes of
     one all-reduce on NVLink, no compact buffers, no row-capacity, nothing for the host to wait for."""
 
-    def __init__(self, buffers, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, buffers, group: Optional[dist.ProcessGroup] = None, use_multicast: Optional[bool] = None):
+        """``use_multicast``: None = use the NVSwitch multicast mapping (multimem.ld_reduce / multimem.st: the switch
+        reduces and replicates, about half the bytes per NVLink direction) when the symmetric buffers have one,
+        False = unicast peer loads / stores only."""
         import ctypes as C
         import torch.distributed._symmetric_memory as symm_mem
         from .rasterizer import _check
@@ -90,6 +93,21 @@ class P2PExchange:
             self._accum[p] = pb + (b.step_grad_accum.data_ptr() - base)
             self._count[p] = pb + (b.step_grad_count.data_ptr() - base)
             self._maxbuf[p] = int(self.h_max.buffer_ptrs[p])
+        mc_a = int(getattr(self.h_arena, "multicast_ptr", 0) or 0)
+        mc_m = int(getattr(self.h_max, "multicast_ptr", 0) or 0)
+        # default: multicast on a full 8-GPU box. The number of multimem operations of a rank falls with 1 / R while
+        # its unicast traffic grows with (R - 1) / R: measured (profiles/r02/) unicast is faster at 2 ranks (0.31 vs
+        # 0.56 ms for 531 k rows), multicast at 8 (0.70 vs 0.79 ms for 867 k rows, masks 0.15 vs 0.25 ms)
+        self.multicast = (bool(mc_a and mc_m) and self.world >= 8) if use_multicast is None \
+            else bool(use_multicast and mc_a and mc_m)
+        self._grads_mc = (C.c_void_p * 5)()
+        self._accum_mc = self._count_mc = self._maxbuf_mc = None
+        if self.multicast:
+            for k in range(5):
+                self._grads_mc[k] = mc_a + offs[k]
+            self._accum_mc = mc_a + (b.step_grad_accum.data_ptr() - base)
+            self._count_mc = mc_a + (b.step_grad_count.data_ptr() - base)
+            self._maxbuf_mc = mc_m
         self.ops = _CudaRowOps()
 
     def exchange(self, with_stats: bool = True) -> dict:
@@ -100,8 +118,12 @@ class P2PExchange:
         lib, h = _lib_and_handle(dev)
         n, C_ = int(b.n), int(b.dL_dsh_coeffs.shape[2])
         self.h_max.barrier(channel=0)      # every rank's mask / statistics / gradient rows of this step are final
+        mc = self.multicast
         st = lib.cugs_b200_p2p_reduce_masks(h, _stream(dev), n, self.world, self.rank, self._maxbuf,
-                                            self._accum if with_stats else None, self._count if with_stats else None)
+                                            self._accum if with_stats else None, self._count if with_stats else None,
+                                            self._maxbuf_mc if mc else None,
+                                            self._accum_mc if (mc and with_stats) else None,
+                                            self._count_mc if (mc and with_stats) else None)
         _lib.check(h, st, "cugs_b200_p2p_reduce_masks")
         self.h_max.barrier(channel=1)      # all slices of the union mask have landed
         offsets, m_dev = self.ops.scan_dev(b)
@@ -109,10 +131,10 @@ class P2PExchange:
                                              b._touch_idx.data_ptr())
         _lib.check(h, st, "cugs_b200_build_touch_index")
         st = lib.cugs_b200_p2p_reduce_rows(h, _stream(dev), n, C_, self.world, self.rank, b._touch_idx.data_ptr(),
-                                           m_dev.data_ptr(), self._grads)
+                                           m_dev.data_ptr(), self._grads, self._grads_mc if mc else None)
         _lib.check(h, st, "cugs_b200_p2p_reduce_rows")
         self.h_arena.barrier(channel=0)    # all sums written everywhere; nobody reads these rows any more
-        return {"mode": "p2p", "host_sync": False}
+        return {"mode": "p2p-multicast" if mc else "p2p", "host_sync": False}
 
 
 class MaskOverlap:

@@ -493,14 +493,20 @@ int cugs_b200_scatter_grad_rows(cugs_handle_t* h, void* stream, int64_t n, int n
  * across the ranks in rank order and written back into every arena; grads_peers[p * 5 + k] = group k
  * (positions, sh_coeffs, opacities, scales, rotations) of rank p. No compact buffers, no host knowledge of M, the
  * same bits on every rank. The CALLER synchronises the ranks (symmetric-memory barrier) before the first call,
- * between the two, and after the second. */
+ * between the two, and after the second.
+ * *_mc (optional): the MULTICAST mapping of the same symmetric buffers (NVSwitch / NVLS). When given, the kernels
+ * use multimem.ld_reduce (the switch reduces the element over all GPUs) and multimem.st (the switch replicates the
+ * store) instead of R unicast loads and R unicast stores -- about half the bytes per NVLink direction; the
+ * summation order inside the switch is unspecified (every rank still receives the same bits). */
 int cugs_b200_build_touch_index(cugs_handle_t* h, void* stream, int64_t n, const int32_t* touch,
                                 const int32_t* offsets, int32_t* idx);
 int cugs_b200_p2p_reduce_masks(cugs_handle_t* h, void* stream, int64_t n, int world, int rank,
                                int32_t* const* max_buf_peers, float* const* grad_accum_peers,
-                               float* const* grad_count_peers);
+                               float* const* grad_count_peers, int32_t* max_buf_mc, float* grad_accum_mc,
+                               float* grad_count_mc);
 int cugs_b200_p2p_reduce_rows(cugs_handle_t* h, void* stream, int64_t n, int num_coeffs, int world, int rank,
-                              const int32_t* idx, const int64_t* m_dev, float* const* grads_peers);
+                              const int32_t* idx, const int64_t* m_dev, float* const* grads_peers,
+                              float* const* grads_mc);
 
 #ifdef __cplusplus
 }

@@ -125,22 +125,30 @@ def main():
     # (c3) the peer-to-peer exchange over symmetric memory (no NCCL, no compact buffers): same sums, identical bits
     # on every rank
     pbuf = cugs.FrameBuffers(n, W, H, 16, dev, symmetric=True)
-    p2p = parallel.P2PExchange(pbuf)
-    for _ in range(3):   # consecutive steps: the mask / zero-row invariant must survive the exchange
-        accumulate(mine, pbuf, sparse=True, with_stats=True)
-        p2p.exchange(with_stats=True)
-    torch.cuda.synchronize()
-    for nm, (off, sz) in layout.items():
-        if rel(pbuf.grad_arena[off:off + sz], ref_arena[off:off + sz]) > 1e-6:
-            errs.append(f"p2p exchange vs single-rank {nm}: {rel(pbuf.grad_arena[off:off + sz], ref_arena[off:off + sz]):.3e}")
-    if not torch.equal(pbuf.step_max_radii, ref_maxr) or not torch.equal(pbuf.step_grad_count, ref_buf.step_grad_count):
-        errs.append("p2p exchange: statistics differ")
-    if not torch.equal(pbuf.touch_mask, sp.touch_mask):
-        errs.append("p2p exchange: union mask differs from the NCCL path")
-    root = pbuf.grad_arena.clone()
-    dist.broadcast(root, 0)
-    if not torch.equal(root, pbuf.grad_arena):
-        errs.append("p2p exchange: the arenas of the ranks are not bit-identical")
+    modes = []
+    for use_mc in (False, True):   # unicast peer loads / stores, then the NVSwitch multicast mapping (if there is one)
+        p2p = parallel.P2PExchange(pbuf, use_multicast=use_mc)
+        if use_mc and not p2p.multicast:
+            continue
+        modes.append("multicast" if p2p.multicast else "unicast")
+        tag = modes[-1]
+        for _ in range(3):   # consecutive steps: the mask / zero-row invariant must survive the exchange
+            accumulate(mine, pbuf, sparse=True, with_stats=True)
+            p2p.exchange(with_stats=True)
+        torch.cuda.synchronize()
+        for nm, (off, sz) in layout.items():
+            if rel(pbuf.grad_arena[off:off + sz], ref_arena[off:off + sz]) > 1e-6:
+                errs.append(f"p2p {tag} vs single-rank {nm}: {rel(pbuf.grad_arena[off:off + sz], ref_arena[off:off + sz]):.3e}")
+        if not torch.equal(pbuf.step_max_radii, ref_maxr) or not torch.equal(pbuf.step_grad_count, ref_buf.step_grad_count):
+            errs.append(f"p2p {tag}: statistics differ")
+        if not torch.equal(pbuf.touch_mask, sp.touch_mask):
+            errs.append(f"p2p {tag}: union mask differs from the NCCL path")
+        root = pbuf.grad_arena.clone()
+        dist.broadcast(root, 0)
+        if not torch.equal(root, pbuf.grad_arena):
+            errs.append(f"p2p {tag}: the arenas of the ranks are not bit-identical")
+    if rank == 0:
+        print(f"p2p exchange modes tested: {modes}", flush=True)
 
     # (d) replicas stay identical: Adam (grad_scale = 1/V) + MCMC noise on the exchanged gradients
     opt = cugs.FusedAdam(model)
