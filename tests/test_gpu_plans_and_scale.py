@@ -157,6 +157,31 @@ def test_packed_sort_count_on_the_device(torch, key_bits):
         assert np.array_equal(ranges, exp.astype(np.int32))
 
 
+@pytest.mark.parametrize("key_bits,n,cap", [(13, (8 << 20) - 1, None), (13, (8 << 20) + 8193, None),
+                                            (15, 5_000_003, 9_000_000), (24, (8 << 20) + 1, None)])
+def test_packed_sort_across_the_large_tile_limit(torch, key_bits, n, cap):
+    """From 8 Mi elements of launch capacity the passes use 8192-element tiles (16 items per thread,
+    tile_binning.cu pk_items_for): one element below the limit, ragged tails above it, a capacity above the
+    limit with a device-side count below it, and a 3-pass plan."""
+    lib, h = _lib.load_library(), _lib.handle(0)
+    rng = np.random.default_rng(n % 1000 + key_bits)
+    num_tiles = min(1 << key_bits, 32_400) if key_bits <= 16 else 0
+    hi = rng.integers(0, num_tiles or (1 << key_bits), size=n, dtype=np.uint64).astype(np.uint32)
+    hi[: n // 4] = hi[0]
+    lo = np.arange(n, dtype=np.uint32)
+    order = np.argsort(hi, kind="stable")
+    res, o32, ranges, elts = _packed_sort(torch, lib, h, hi, lo, key_bits, num_tiles, num_tiles > 0, True,
+                                          n_cap=cap, use_n_dev=cap is not None)
+    assert np.array_equal(o32[:n].view(np.uint32), lo[order])
+    if cap is not None:
+        assert (o32[n:] == -7).all()
+    if num_tiles:
+        counts = np.bincount(hi, minlength=num_tiles)[:num_tiles]
+        ends = np.cumsum(counts)
+        exp = np.stack([np.where(counts > 0, ends - counts, 0), np.where(counts > 0, ends, 0)], axis=1)
+        assert np.array_equal(ranges, exp.astype(np.int32))
+
+
 @pytest.mark.parametrize("name,n,W,H,seed", [("ragged", 3001, 333, 211, 12), ("A", 100_000, 1280, 720, 1235),
                                               ("adversarial", 20_000, 640, 360, 13)])
 def test_render_without_host_sync_equals_blocking_path(torch, name, n, W, H, seed):
