@@ -228,6 +228,28 @@ def calibrated_steps(requested: int, est_ms_per_step: float) -> int:
     return max(int(requested), int(math.ceil(MIN_TIMED_MS * 1.05 / max(est_ms_per_step, 1e-3))))
 
 
+def exchange_buffers(cugs, torch, dist, n, W, H, coeffs, dev, want_p2p):
+    """Gradient buffers of one rank + the peer-to-peer exchange over them. The P2P kernels need torch's symmetric
+    memory (NVLink peer mappings of every rank's arena); where a box cannot give it, ALL ranks fall back together to
+    the NCCL row exchange on ordinary device memory (still this library's gather / scatter kernels around NCCL) and
+    the bench line says so in config.gradient_exchange."""
+    if not want_p2p:
+        return cugs.FrameBuffers(n, W, H, coeffs, dev), None, None
+    buf = p2p = why = None
+    try:
+        buf = cugs.FrameBuffers(n, W, H, coeffs, dev, symmetric=True)
+        p2p = cugs.P2PExchange(buf)
+    except Exception as e:  # noqa: BLE001 -- any failure of the symmetric allocation / rendezvous
+        why = f"{type(e).__name__}: {str(e)[:160]}"
+    ok = torch.tensor([0 if why else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 1:
+        return buf, p2p, None
+    del p2p, buf
+    return cugs.FrameBuffers(n, W, H, coeffs, dev), None, "p2p exchange unavailable on this box (" + (
+        why or "another rank failed") + "): NCCL row exchange"
+
+
 def run_b200(args) -> dict:
     import ctypes as C
 
@@ -262,7 +284,7 @@ def run_b200(args) -> dict:
         return run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world, local, dev, desc)
     # N > 1: the gradient arena lives in symmetric memory so that the exchange can run peer to peer over NVLink
     use_p2p = world > 1 and args.exchange == "p2p" and not args.dense_allreduce
-    buf = cugs.FrameBuffers(n, W, H, 16, dev, symmetric=use_p2p)
+    buf, p2p, p2p_note = exchange_buffers(cugs, torch, dist, n, W, H, 16, dev, use_p2p)
 
     # synthetic targets (host, pinned) and the resident dL/dcolor of each view; the blocking renders also
     # establish the pair capacity of every buffer used below
@@ -284,6 +306,8 @@ def run_b200(args) -> dict:
 
     with_stats = world > 1   # north_star: "parameter gradients plus densification statistics" in the exchange
     exchange = {"mode": "single"}
+    if p2p_note:
+        exchange["note"] = p2p_note
     exch_state = {}
 
     def allreduce(mask_reduced=False):
@@ -304,7 +328,6 @@ def run_b200(args) -> dict:
     # the dense exchange is requested (it sums rows this rank's mask does not know about)
     sparse = not args.dense_allreduce
     touch = buf.touch_mask if sparse else None
-    p2p = cugs.P2PExchange(buf) if use_p2p else None
 
     # ---- headline path: the C++ step driver's "views" phase (cugs_b200_trainer_step, phases = 1) with a given
     # dL/dcolor per view = forward + backward only. No host round trip per view (device-side pair count),
@@ -580,11 +603,10 @@ def run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world
     rng = np.random.default_rng(4321 + rank)
     targets = [torch.from_numpy(rng.uniform(size=(H, W, 3)).astype(np.float32)).to(dev) for _ in range(V)]
     use_p2p = world > 1 and args.exchange == "p2p"
-    gbuf = cugs.FrameBuffers(n, W, H, int(model.sh_coeffs.shape[2]), dev, symmetric=use_p2p)
+    gbuf, p2p, p2p_note = exchange_buffers(cugs, torch, dist, n, W, H, int(model.sh_coeffs.shape[2]), dev, use_p2p)
     trainer = cugs.NativeTrainer(model, cams, targets, cugs.TrainConfig(), total_views_per_step=world * V,
                                  frames_in_flight=1 if args.no_overlap else 2, use_graph=not args.no_graph,
                                  grad_buffers=gbuf)
-    p2p = cugs.P2PExchange(gbuf) if use_p2p else None
     lib, h = _lib.load_library(), _lib.handle(local)
     step_no = [3000]  # SH degree 3 active (lr_schedule.hpp:70-72)
     exch_state = {}
@@ -665,7 +687,10 @@ def run_b200_train_step(args, cugs, torch, dist, scene, model, cams, rank, world
                        "views_per_step": world * V, "adam_elements": 59 * n, "l2": "inputs exceed L2",
                        "driver": "cugs_b200_trainer_step: C++ step driver, no host synchronisation, "
                                  + ("CUDA graph replay" if not args.no_graph else "eager launches"),
-                       "pair_capacity": trainer.pair_capacity, "largest_pair_count": pmax},
+                       "pair_capacity": trainer.pair_capacity, "largest_pair_count": pmax,
+                       "gradient_exchange": ("single" if world == 1 else
+                                             (p2p_note or ("p2p" + ("+multicast" if p2p.multicast else "")
+                                                           if p2p is not None else "nccl rows")))},
             "clocks": clocks, "gpu_launches": launches, "final_loss": scalars[0]}
 
 

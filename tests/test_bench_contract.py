@@ -62,3 +62,33 @@ def test_committed_bench_lines_carry_the_contract_keys():
     assert "workload" in line["config"] and "model" not in line["config"]
     ref = json.loads((ROOT / "profiles" / "r01" / "bench_reference_final.json").read_text().strip().splitlines()[-1])
     assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+
+
+def test_exchange_buffers_fall_back_together_when_symmetric_memory_is_missing():
+    """bench.exchange_buffers: a failing symmetric allocation / rendezvous turns into the NCCL row exchange on
+    every rank (agreed through a MIN all-reduce), and the reason lands in the bench line."""
+    import torch
+    import torch.distributed as dist
+
+    class FakeCugs:
+        made = []
+
+        @staticmethod
+        def FrameBuffers(n, W, H, coeffs, dev, symmetric=False):
+            if symmetric:
+                raise RuntimeError("no fabric handles on this box")
+            FakeCugs.made.append((n, W, H, coeffs))
+            return "plain-buffers"
+
+        @staticmethod
+        def P2PExchange(buf):
+            raise AssertionError("not reached")
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29641", rank=0, world_size=1)
+    try:
+        buf, p2p, note = bench.exchange_buffers(FakeCugs, torch, dist, 10, 64, 64, 16, "cpu", True)
+        assert buf == "plain-buffers" and p2p is None and "no fabric handles" in note and "NCCL" in note
+        buf, p2p, note = bench.exchange_buffers(FakeCugs, torch, dist, 10, 64, 64, 16, "cpu", False)
+        assert buf == "plain-buffers" and p2p is None and note is None
+    finally:
+        dist.destroy_process_group()
