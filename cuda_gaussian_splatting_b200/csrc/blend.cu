@@ -29,7 +29,12 @@
 //    in registers, then the warp reduces them with a multi-value butterfly (8 values in 7
 //    shuffle steps + 1 value in 5, instead of 9 x 5), and 9 lanes issue ONE coalesced
 //    red.global.add.f32 to the 9 consecutive floats of the Gaussian's packed gradient record —
-//    instead of the reference's nine scalar atomics per (pixel, Gaussian).
+//    instead of the reference's nine scalar atomics per (pixel, Gaussian);
+//  * backward, per contributing (pixel, Gaussian): the colour accumulated behind the Gaussian is carried as ONE
+//    scalar per pixel, G = sum_c dL/dC_c * S_c (dL/dC is constant along the walk), and the mean / conic gradients
+//    come from three per-thread moments (sum dLp, sum dLp dx, sum dLp dx^2; dy is common to a thread's pixels):
+//    40 instructions per pixel slot instead of 55, 76 registers without spills instead of 80 with
+//    (profiles/r02/NOTES.md: 0.909 -> 0.761 ms at workload B).
 #include "common.cuh"
 
 namespace cugs {
@@ -79,11 +84,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ float exp2f_fast(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 __device__ __forceinline__ float rcp_fast(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -478,7 +478,8 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
     const int nb = (count + kBatch - 1) / kBatch;
 
     // per-pixel forward outputs (backward.cu:65-87)
-    float pxf[kPix], T[kPix], g0[kPix], g1[kPix], g2[kPix], S0[kPix], S1[kPix], S2[kPix];
+    float pxf[kPix], T[kPix], g0[kPix], g1[kPix], g2[kPix];
+    float G[kPix];    // sum_c dL/dC_c * (colour accumulated behind the current Gaussian, background included)
     float lim[kPix];  // 0 while the pixel still has contributors to process, -inf afterwards (see forward)
     int left[kPix];   // contributors still to process; <= 0 means the pixel is done
 #pragma unroll
@@ -493,7 +494,7 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             g1[k] = dL_dcolor[pi * 3 + 1];
             g2[k] = dL_dcolor[pi * 3 + 2];
         }
-        S0[k] = T[k] * bg_r; S1[k] = T[k] * bg_g; S2[k] = T[k] * bg_b;
+        G[k] = T[k] * (g0[k] * bg_r + g1[k] * bg_g + g2[k] * bg_b);
         lim[k] = (left[k] > 0) ? 0.0f : -INFINITY;
     }
     const f32x2 px01 = pk2(pxf[0], pxf[1]), px23 = pk2(pxf[2], pxf[3]);
@@ -545,7 +546,7 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
             const float a = q0.z, bq = q0.w, c = q1.x;
             const float dy = pyf - q0.y;
             const float dyb = mul_rn(dy, bq), dyc = mul_rn(dy, c);
-            float power[kPix], dx[kPix], s1[kPix], s2[kPix];
+            float power[kPix], dx[kPix];
             bool pass[kPix];
             {
                 f32x2 dxa, s1a, s2a, dxb, s1b, s2b;
@@ -553,8 +554,6 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
                 const f32x2 pb = blend_power_x2(px23, -q0.x, dy, a, bq, dyb, dyc, dxb, s1b, s2b);
                 unpk2(pa, power[0], power[1]); unpk2(pb, power[2], power[3]);
                 unpk2(dxa, dx[0], dx[1]); unpk2(dxb, dx[2], dx[3]);
-                unpk2(s1a, s1[0], s1[1]); unpk2(s1b, s1[2], s1[3]);
-                unpk2(s2a, s2[0], s2[1]); unpk2(s2b, s2[2], s2[3]);
             }
             bool any = false;
 #pragma unroll
@@ -575,14 +574,11 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
 #pragma unroll
                 for (int k = 0; k < kPix; ++k) {
                     if (!pass[k]) continue;
-                    // ex2.approx (rel. error < 1e-6) unless alpha lands within a guard band of one of the
-                    // two thresholds the forward pass decided on with the accurate expf
-                    float ex = exp2f_fast(power[k] * 1.4426950408889634f);
-                    float oe = q1.z * ex;
-                    if (fabsf(oe - kAlphaMin) < 4e-8f || fabsf(oe - 0.99f) < 1e-5f) {
-                        ex = expf(power[k]);
-                        oe = mul_rn(q1.z, ex);
-                    }
+                    // the forward's own expf: same alpha >= 1/255 and alpha-clamp decisions bit for bit. (Round 1
+                    // used ex2.approx plus a guard band around the two thresholds; the band's two compares and
+                    // divergent branch cost more issue slots than expf's range reduction: 0.909 -> 0.858 ms.)
+                    const float ex = expf(power[k]);
+                    const float oe = mul_rn(q1.z, ex);
                     const float alpha = fminf(oe, 0.99f);
                     if (alpha < kAlphaMin) continue;       // backward.cu:137-139
                     if (--left[k] <= 0) lim[k] = -INFINITY;  // found++ ; found > n_contrib -> stop (:141-145)
@@ -595,21 +591,24 @@ k_blend_bwd(int ntx, int width, int height, float bg_r, float bg_g, float bg_b,
                     v[2] = fmaf(g2[k], w, v[2]);
                     // dL/dalpha = sum_c dL/dC_c * (T*rgb_c - S_c/oma)   (backward.cu:166-168)
                     const float gc = g0[k] * cr + g1[k] * cg + g2[k] * cb;
-                    const float gs = g0[k] * S0[k] + g1[k] * S1[k] + g2[k] * S2[k];
-                    const float dLa = T[k] * gc - inv * gs;
-                    S0[k] = fmaf(w, cr, S0[k]);
-                    S1[k] = fmaf(w, cg, S1[k]);
-                    S2[k] = fmaf(w, cb, S2[k]);
                     const bool clamped = (oe >= 0.99f);      // backward.cu:178-190
-                    const float dLp = clamped ? 0.0f : dLa * alpha;
-                    v[3] += clamped ? 0.0f : dLa * ex;
-                    v[4] = fmaf(dLp, s1[k], v[4]);           // a*dx + b*dy
-                    v[5] = fmaf(dLp, s2[k], v[5]);           // b*dx + c*dy
+                    // The pixel's dL/dC is constant along the walk, so the colour accumulated behind the Gaussian
+                    // (backward.cu's accum_rec) enters only through G = sum_c dL/dC_c * S_c: one G += w * gc replaces
+                    // three S updates and a dot product, and three registers per pixel.
+                    const float dLa = T[k] * gc - inv * G[k];
+                    G[k] = fmaf(w, gc, G[k]);
+                    const float dLa_c = clamped ? 0.0f : dLa;
+                    const float dLp = dLa_c * alpha;
+                    v[3] = fmaf(dLa_c, ex, v[3]);
                     const float pdx = dLp * dx[k];
                     m_p += dLp;
                     m_dx += pdx;
                     m_xx = fmaf(pdx, dx[k], m_xx);
                 }
+                // dL/dmean: sum dLp * (a dx + b dy) and sum dLp * (b dx + c dy), from the moments (dy is common to the
+                // thread's four pixels) instead of two FMAs per pixel
+                v[4] = fmaf(a, m_dx, dyb * m_p);
+                v[5] = fmaf(bq, m_dx, dyc * m_p);
                 v[6] = -0.5f * m_xx;            // sum dLp * (-0.5 dx^2)
                 v[7] = -(m_dx * dy);            // sum dLp * (-dx dy)
                 v[8] = -0.5f * (m_p * dy * dy); // sum dLp * (-0.5 dy^2)
