@@ -48,10 +48,14 @@ def test_algorithmic_bytes_model():
     assert bench.BWD_MUFU["contributing"] == 2 and bench.calibrated_steps(20, 4.0) >= 250   # >= 1 s timed region
 
 
-def test_committed_bench_lines_carry_the_contract_keys():
+import pytest
+
+
+@pytest.mark.parametrize("rnd", ["r01", "r02"])
+def test_committed_bench_lines_carry_the_contract_keys(rnd):
     need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
             "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"}
-    line = json.loads((ROOT / "profiles" / "r01" / "bench_b200_final.json").read_text().strip().splitlines()[-1])
+    line = json.loads((ROOT / "profiles" / rnd / "bench_b200_final.json").read_text().strip().splitlines()[-1])
     assert need <= set(line), need - set(line)
     assert line["unit"] == "views/s" and line["higher_is_better"] is True and line["scaling"] == "weak"
     assert line["dtype"] == "f32" and line["vs_baseline"] is None and line["warmup"] >= 3
@@ -60,8 +64,18 @@ def test_committed_bench_lines_carry_the_contract_keys():
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert line["e2e"]["h2d_bytes_per_step"] == 2 * 1920 * 1080 * 3 * 4 and line["gpu_launches"] > 0
     assert "workload" in line["config"] and "model" not in line["config"]
-    ref = json.loads((ROOT / "profiles" / "r01" / "bench_reference_final.json").read_text().strip().splitlines()[-1])
+    ref = json.loads((ROOT / "profiles" / rnd / "bench_reference_final.json").read_text().strip().splitlines()[-1])
     assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+    if rnd == "r02":   # round 2: work-based roofline of the dominant kernel, every stage in roofline_all, >= 1 s timed
+        r = line["roofline"]
+        assert r["kernel"] == "k_blend_bwd" and r["bound"] == "fp32-issue" and r["unit"] == "TFLOP/s"
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and {"mufu", "work"} <= set(r)
+        assert {"loss", "adam", "blend_fwd", "blend_bwd", "sort", "preprocess_fwd"} <= set(line["roofline_all"])
+        w = line["work_view0"]
+        assert w["E_bwd"] == w["bwd_rejected"] + w["bwd_contributing"] and w["E_fwd"] > 0
+        assert line["ms_per_step"] * line["steps"] >= 1000.0
+        drop = json.loads((ROOT / "profiles" / rnd / "bench_dropin_final.json").read_text().strip().splitlines()[-1])
+        assert drop["impl"] == "dropin" and drop["unit"] == "views/s" and drop["value"] > ref["value"]
 
 
 def test_exchange_buffers_fall_back_together_when_symmetric_memory_is_missing():
