@@ -521,11 +521,21 @@ using namespace cugs;
 // ------------------------------------------------------------------------------------------------
 // host-side launchers (internal; used by api.cu)
 // ------------------------------------------------------------------------------------------------
-size_t cugs_packed_sort_temp_bytes(int64_t n, int passes, int num_tiles) {
-    const int64_t tile_elts = (int64_t)kPkThreads * pk_items_for(n);
-    const int64_t tiles = (n + tile_elts - 1) / tile_elts;
+static size_t packed_temp_layout_bytes(int64_t tiles, int passes, int num_tiles) {
     return (size_t)kPkMaxPasses * kPkRadix * 4 + 64 + align_up((size_t)(num_tiles > 0 ? num_tiles : 1) * 4, 256) +
            (size_t)passes * (size_t)(tiles > 0 ? tiles : 1) * kPkRadix * 4;
+}
+// bytes of `temp` a sort of n elements really touches (histograms + the look-back state of its own tile size)
+static size_t packed_sort_used_bytes(int64_t n, int passes, int num_tiles) {
+    const int64_t tile_elts = (int64_t)kPkThreads * pk_items_for(n);
+    return packed_temp_layout_bytes((n + tile_elts - 1) / tile_elts, passes, num_tiles);
+}
+// What a caller must provide for a CAPACITY of n elements: sized on the smallest tile any variant uses, so that the
+// figure is monotone in n and a buffer sized for a capacity serves every smaller count (a count just below the
+// large-tile limit has twice the tiles of a capacity just above it).
+size_t cugs_packed_sort_temp_bytes(int64_t n, int passes, int num_tiles) {
+    const int64_t tile_elts = (int64_t)kPkThreads * ((int64_t)CUGS_PK_SMALL_LIMIT > 0 ? kPkItemsSmall : kPkItems);
+    return packed_temp_layout_bytes((n + tile_elts - 1) / tile_elts, passes, num_tiles);
 }
 
 int cugs_packed_passes(int key_bits) { return make_packed_plan(key_bits).passes; }
@@ -547,7 +557,7 @@ int cugs_packed_sort(cugs_handle_t* h, cudaStream_t s, int64_t n, int key_bits, 
     const PackedPlan plan = make_packed_plan(key_bits);
     if (n >= (1ll << 30))
         return set_error(h, CUGS_ERR_UNSUPPORTED, "n = %lld >= 2^30 elements is not supported", (long long)n);
-    const size_t need = cugs_packed_sort_temp_bytes(n, plan.passes, num_tiles);
+    const size_t need = packed_sort_used_bytes(n, plan.passes, num_tiles);
     if (temp_bytes < need)
         return set_error(h, CUGS_ERR_WORKSPACE, "packed sort temp too small: %zu < %zu", temp_bytes, need);
     if (tile_ranges && num_tiles > 0 && n == 0) {
@@ -635,7 +645,7 @@ int cugs_duplicate_sorted_hist(cugs_handle_t* h, cudaStream_t s, int64_t n, int 
                                const int64_t* p_dev, int key_bits, int num_tiles, void* sort_temp,
                                size_t sort_temp_bytes) {
     const PackedPlan plan = make_packed_plan(key_bits);
-    const size_t need = cugs_packed_sort_temp_bytes(p, plan.passes, num_tiles);
+    const size_t need = packed_sort_used_bytes(p, plan.passes, num_tiles);  // what the sort that follows touches
     if (sort_temp_bytes < need)
         return set_error(h, CUGS_ERR_WORKSPACE, "packed sort temp too small: %zu < %zu", sort_temp_bytes, need);
     CUGS_CUDA_TRY(h, cudaMemsetAsync(sort_temp, 0, need, s));

@@ -47,6 +47,24 @@ def test_size_queries_need_no_gpu():
     assert lib.cugs_b200_sort_num_passes(32, 32) == 8
 
 
+def test_capacity_sized_scratch_serves_every_smaller_count():
+    """A buffer sized for a pair CAPACITY must be large enough for every smaller pair count, also across the
+    element count from which the packed sort switches to 8192-element tiles (half the look-back state): the size
+    queries are monotone in their count argument."""
+    from cuda_gaussian_splatting_b200 import _lib
+    lib = _lib.load_library()
+    limit = 8 << 20
+    counts = [1, 4095, 4096, 4097, 1_000_000, limit - 8193, limit - 1, limit, limit + 1, limit + 8193, 2 * limit,
+              18_596_764, 124_800_000]
+    for fn in (lambda c: lib.cugs_b200_render_pair_scratch_bytes(c),
+               lambda c: lib.cugs_b200_sort_packed_temp_bytes(c, 13, 8160),
+               lambda c: lib.cugs_b200_sort_packed_temp_bytes(c, 32, 0),
+               lambda c: lib.cugs_b200_render_workspace_bytes(c, 0),
+               lambda c: lib.cugs_b200_trainer_workspace_bytes(1000, 16, 640, 360, c, 2)):
+        sizes = [int(fn(c)) for c in counts]
+        assert all(b >= a > 0 for a, b in zip(sizes, sizes[1:])), sizes
+
+
 def test_no_cpu_fallback_without_gpu():
     """On a box without a B200 the product must fail loudly, not fall back."""
     import pytest
